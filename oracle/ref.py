@@ -218,6 +218,13 @@ class RefSim:
     def map_id(self, map_index):
         return self.L.refb_map_id(self.d, map_index)
 
+    # scenario helpers: the argument each implementation expects for "the i-th map / effect set"
+    def map_arg(self, map_index):
+        return self.map_id(map_index)
+
+    def eff_arg(self, eff_index):
+        return self.eff_id(eff_index)
+
     def export_effects(self, eff_index=0):
         M = self.n_markers
         nnz = self.L.refb_eff_nnz(self.d, eff_index)
