@@ -1,0 +1,378 @@
+// evaluate.cu — genomic evaluation on the bit-packed store (K5 GEBV, K6 local GEBV,
+// K7 allele counts, K9 ranking).
+//
+// The reference compares allele CHARS against the effect table per marker
+// (core.c:9587-9597, 10019-10031).  Here the per-marker symbol dictionary turns an effect set
+// into tables indexed by the stored CODE:
+//     value_all[m][code]   = sum of every effect entry of marker m whose allele is the symbol
+//                            `code` decodes to            (whole-genome BVs count every match)
+//     value_first[m][code] = the first such entry only    (local BVs stop at the first match)
+// so that a genotype's contribution at marker m is value[m][code_hap0] + value[m][code_hap1].
+// With one bit-plane (<= 2 symbols per marker) this collapses to
+//     BV = sum_m 2*value[m][0]  +  sum_m (bit0_m + bit1_m) * (value[m][1] - value[m][0]).
+// All arithmetic is fp64; only the summation ORDER differs from the reference's sequential
+// sum (tolerance 1e-9 relative, BASELINE.json north_star).
+#include "gsb200_internal.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <cub/cub.cuh>
+
+using namespace gsb;
+
+namespace {
+
+constexpr int kGebvThreads = 128;      // individuals per block (one per thread)
+constexpr int kGebvTile = 512;         // markers of delta staged in shared memory per step
+
+// ------------------------------------------------------------------ GEBV, one plane
+// Thread = individual, markers walked in order with delta broadcast from shared memory: no
+// divergence, no cross-lane reduction, delta read once per 128 individuals.
+__global__ void __launch_bounds__(kGebvThreads) gebv_plane1_kernel(
+        const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words, uint32_t n_markers,
+        const uint32_t* __restrict__ rows, uint32_t n, const double* __restrict__ delta,
+        double base, double* __restrict__ out) {
+    __shared__ double s_delta[kGebvTile];
+    const uint32_t i = blockIdx.x * kGebvThreads + threadIdx.x;
+    const bool live = i < n;
+    const uint32_t* row = store + (uint64_t) (live ? rows[i] : rows[0]) * row_words;
+    const uint4* h0 = reinterpret_cast<const uint4*>(row);
+    const uint4* h1 = reinterpret_cast<const uint4*>(row + plane_words);
+    double acc0 = 0.0, acc1 = 0.0;
+    for (uint32_t m0 = 0; m0 < n_markers; m0 += kGebvTile) {
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < kGebvTile; t += kGebvThreads)
+            s_delta[t] = (m0 + t < n_markers) ? delta[m0 + t] : 0.0;
+        __syncthreads();
+#pragma unroll 1
+        for (uint32_t q = 0; q < kGebvTile / 128; ++q) {
+            const uint32_t u = (m0 >> 7) + q;
+            if (u * 4 >= plane_words) break;
+            const uint4 a = __ldg(h0 + u), b = __ldg(h1 + u);
+            const uint32_t wa[4] = { a.x, a.y, a.z, a.w }, wb[4] = { b.x, b.y, b.z, b.w };
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t one = wa[w] ^ wb[w], two = wa[w] & wb[w];
+#pragma unroll
+                for (int bit = 0; bit < 32; ++bit) {
+                    const double d = s_delta[q * 128 + w * 32 + bit];
+                    if (one & (1u << bit)) acc0 += d;
+                    if (two & (1u << bit)) acc1 += d;
+                }
+            }
+        }
+    }
+    if (live) out[i] = base + (acc0 + 2.0 * acc1);
+}
+
+// ------------------------------------------------------------------ GEBV, any number of planes
+// Warp per individual, lane per marker of a word; table lookups by code.
+__global__ void gebv_generic_kernel(const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
+                                    uint32_t planes, uint32_t n_markers, const uint32_t* __restrict__ rows, uint32_t n,
+                                    const double* __restrict__ value, double offset, double* __restrict__ out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const uint32_t* row = store + (uint64_t) rows[warp] * row_words;
+    double acc = 0.0;
+    for (uint32_t m = lane; m < n_markers; m += 32) {
+        uint32_t c0 = 0, c1 = 0;
+        for (uint32_t p = 0; p < planes; ++p) {
+            c0 |= ((row[(uint64_t) p * plane_words + (m >> 5)] >> (m & 31)) & 1u) << p;
+            c1 |= ((row[(uint64_t) (planes + p) * plane_words + (m >> 5)] >> (m & 31)) & 1u) << p;
+        }
+        const double* v = value + ((size_t) m << planes);
+        acc += v[c0] + v[c1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[warp] = acc + offset;
+}
+
+// ------------------------------------------------------------------ local GEBV
+// Warp per individual; for every block the lanes stride over the block's marker list.
+__global__ void local_gebv_kernel(const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
+                                  uint32_t planes, const uint32_t* __restrict__ rows, uint32_t n,
+                                  uint32_t n_blocks, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ markers,
+                                  const double* __restrict__ value_first, const double* __restrict__ centre,
+                                  double* __restrict__ out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const uint32_t* row = store + (uint64_t) rows[warp] * row_words;
+    double* o1 = out + (size_t) (2 * (size_t) warp) * n_blocks;
+    double* o2 = o1 + n_blocks;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        double a1 = 0.0, a2 = 0.0;
+        for (uint32_t q = offsets[b] + lane; q < offsets[b + 1]; q += 32) {
+            const uint32_t m = markers[q];
+            uint32_t c0 = 0, c1 = 0;
+            for (uint32_t p = 0; p < planes; ++p) {
+                c0 |= ((row[(uint64_t) p * plane_words + (m >> 5)] >> (m & 31)) & 1u) << p;
+                c1 |= ((row[(uint64_t) (planes + p) * plane_words + (m >> 5)] >> (m & 31)) & 1u) << p;
+            }
+            const double* v = value_first + ((size_t) m << planes);
+            const double cm = centre ? centre[m] : 0.0;
+            a1 += v[c0] - cm;
+            a2 += v[c1] - cm;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) { o1[b] = a1; o2[b] = a2; }
+    }
+}
+
+// ------------------------------------------------------------------ allele counts
+template <typename T>
+__global__ void allele_count_kernel(const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
+                                    uint32_t planes, uint32_t n_markers, const uint32_t* __restrict__ rows, uint32_t n,
+                                    const uint8_t* __restrict__ dict_sym, uint8_t allele, T* __restrict__ out) {
+    const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (uint64_t) n * n_markers) return;
+    const uint32_t i = (uint32_t) (tid / n_markers), m = (uint32_t) (tid % n_markers);
+    const uint32_t* row = store + (uint64_t) rows[i] * row_words;
+    uint32_t c0 = 0, c1 = 0;
+    for (uint32_t p = 0; p < planes; ++p) {
+        c0 |= ((row[(uint64_t) p * plane_words + (m >> 5)] >> (m & 31)) & 1u) << p;
+        c1 |= ((row[(uint64_t) (planes + p) * plane_words + (m >> 5)] >> (m & 31)) & 1u) << p;
+    }
+    const uint8_t* sym = dict_sym + ((size_t) m << planes);
+    out[tid] = (T) ((sym[c0] == allele ? 1 : 0) + (sym[c1] == allele ? 1 : 0));
+}
+
+// ------------------------------------------------------------------ ranking
+// order-preserving map of fp64 to u64, inverted when the highest value is the best, so that an
+// ascending STABLE sort yields best-first with ties in input order.
+__global__ void rank_keys_kernel(const double* __restrict__ values, uint32_t n, int low_is_best,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ pos) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = (uint64_t) __double_as_longlong(values[i]);
+    k = (k >> 63) ? ~k : (k | 0x8000000000000000ull);
+    keys[i] = low_is_best ? k : ~k;
+    pos[i] = i;
+}
+
+template <typename T>
+int to_device_vec(const std::vector<T>& v, T** out) {
+    if (*out) { cudaFree(*out); *out = nullptr; }
+    GSB_CUDA_TRY(cudaMalloc((void**) out, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) GSB_CUDA_TRY(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return GSB200_OK;
+}
+
+int get_effects(gsb200_ctx* ctx, uint32_t eff_index, DeviceEffects** out, const char* what) {
+    GSB_REQUIRE(eff_index < ctx->effects.size() && ctx->effects[eff_index].present, GSB200_ERR_ARG,
+                "%s: no effect set at index %u", what, eff_index);
+    GSB_TRY(ensure_effect_tables(ctx, eff_index));
+    *out = &ctx->effects[eff_index];
+    return GSB200_OK;
+}
+
+}  // namespace
+
+namespace gsb {
+
+// (Re)build the code-indexed tables when the effect set is new or the dictionary changed.
+int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
+    DeviceEffects& e = ctx->effects[eff_index];
+    if (e.d_value_all && e.built_for_dict_version == ctx->dict_version && e.built_for_planes == ctx->planes) return GSB200_OK;
+    const uint32_t M = ctx->n_markers, planes = ctx->planes, codes = 1u << planes;
+    std::vector<double> all((size_t) M << planes, 0.0), first((size_t) M << planes, 0.0);
+    for (uint32_t m = 0; m < M; ++m) {
+        const uint32_t lo = m ? e.cumn[m - 1] : 0, hi = e.cumn[m];
+        const uint8_t* sym = &ctx->dict_sym[(size_t) m << planes];
+        // codes beyond dict_n[m] are never stored, except code 0 of a marker nobody uploaded:
+        // it decodes to '\0', like the reference's zeroed slot (core.c:75)
+        const uint32_t defined = std::max<uint32_t>(ctx->dict_n[m], 1);
+        for (uint32_t c = 0; c < codes && c < defined; ++c) {
+            double sum = 0.0;
+            bool got = false;
+            for (uint32_t x = lo; x < hi; ++x) {
+                if (e.allele[x] != sym[c]) continue;
+                sum += e.eff[x];
+                if (!got) { first[((size_t) m << planes) + c] = e.eff[x]; got = true; }
+            }
+            all[((size_t) m << planes) + c] = sum;
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    GSB_TRY(to_device_vec(all, &e.d_value_all));
+    GSB_TRY(to_device_vec(first, &e.d_value_first));
+    if (e.has_centre) GSB_TRY(to_device_vec(e.centre, &e.d_centre));
+    if (planes == 1) {
+        std::vector<double> delta(M);
+        double base = 0.0;
+        for (uint32_t m = 0; m < M; ++m) {
+            delta[m] = all[2 * (size_t) m + 1] - all[2 * (size_t) m];
+            base += 2.0 * all[2 * (size_t) m];
+        }
+        GSB_TRY(to_device_vec(delta, &e.d_delta));
+        e.base_all = base;
+    }
+    e.built_for_dict_version = ctx->dict_version;
+    e.built_for_planes = planes;
+    return GSB200_OK;
+}
+
+}  // namespace gsb
+
+namespace {
+
+int gebv_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t eff_index, double* d_out, const char* what) {
+    DeviceEffects* e;
+    GSB_TRY(get_effects(ctx, eff_index, &e, what));
+    const double centre_sum = e->has_centre ? e->centre_sum : 0.0;
+    if (ctx->planes == 1) {
+        gebv_plane1_kernel<<<(n + kGebvThreads - 1) / kGebvThreads, kGebvThreads, 0, ctx->stream>>>(
+            ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->n_markers, d_rows, n,
+            e->d_delta, e->base_all - centre_sum, d_out);
+    } else {
+        const uint64_t threads = (uint64_t) n * 32;
+        gebv_generic_kernel<<<(unsigned) ((threads + 127) / 128), 128, 0, ctx->stream>>>(
+            ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->planes, ctx->n_markers, d_rows, n,
+            e->d_value_all, -centre_sum, d_out);
+    }
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    return GSB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gsb200_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t eff_index, double* d_out) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    if (n == 0) return GSB200_OK;
+    GSB_REQUIRE(d_rows && d_out, GSB200_ERR_ARG, "gsb200_gebv_dev: null array");
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    return gebv_launch(ctx, n, d_rows, eff_index, d_out, "gsb200_gebv_dev");
+}
+
+int gsb200_gebv(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t eff_index, double* out) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    if (n == 0) return GSB200_OK;
+    GSB_REQUIRE(out != nullptr, GSB200_ERR_ARG, "gsb200_gebv: null output");
+    GSB_TRY(check_rows(ctx, n, rows, "gsb200_gebv"));
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint32_t* d_rows;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], rows, n, &d_rows));
+    GSB_TRY(ctx->s_eval[0].ensure((size_t) n * sizeof(double)));
+    GSB_TRY(gebv_launch(ctx, n, d_rows, eff_index, (double*) ctx->s_eval[0].ptr, "gsb200_gebv"));
+    GSB_CUDA_TRY(cudaMemcpyAsync(out, ctx->s_eval[0].ptr, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GSB200_OK;
+}
+
+int gsb200_local_gebv(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t n_blocks,
+                      const uint32_t* block_offsets, const uint32_t* block_markers,
+                      uint32_t eff_index, double* out) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    const char* what = "gsb200_local_gebv";
+    if (n == 0 || n_blocks == 0) return GSB200_OK;
+    GSB_REQUIRE(block_offsets && out, GSB200_ERR_ARG, "%s: null array", what);
+    GSB_TRY(check_rows(ctx, n, rows, what));
+    GSB_REQUIRE(block_offsets[0] == 0, GSB200_ERR_ARG, "%s: block_offsets[0] must be 0", what);
+    for (uint32_t b = 0; b < n_blocks; ++b)
+        GSB_REQUIRE(block_offsets[b] <= block_offsets[b + 1], GSB200_ERR_ARG, "%s: block_offsets not ascending", what);
+    const uint32_t total = block_offsets[n_blocks];
+    GSB_REQUIRE(total == 0 || block_markers, GSB200_ERR_ARG, "%s: null marker list", what);
+    for (uint32_t q = 0; q < total; ++q)
+        GSB_REQUIRE(block_markers[q] < ctx->n_markers, GSB200_ERR_ARG, "%s: marker index %u out of range", what, block_markers[q]);
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    DeviceEffects* e;
+    GSB_TRY(get_effects(ctx, eff_index, &e, what));
+    uint32_t *d_rows, *d_off, *d_mk;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], rows, n, &d_rows));
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[1], block_offsets, (size_t) n_blocks + 1, &d_off));
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[2], block_markers, total, &d_mk));
+    // output in slabs of individuals so that the device buffer stays bounded
+    const size_t row_out = 2 * (size_t) n_blocks * sizeof(double);
+    const uint32_t slab = (uint32_t) std::max<size_t>(1, std::min<size_t>(n, ((size_t) 1 << 30) / row_out));
+    GSB_TRY(ctx->s_eval[1].ensure((size_t) slab * row_out));
+    for (uint32_t done = 0; done < n; done += slab) {
+        const uint32_t cnt = std::min(slab, n - done);
+        const uint64_t threads = (uint64_t) cnt * 32;
+        local_gebv_kernel<<<(unsigned) ((threads + 127) / 128), 128, 0, ctx->stream>>>(
+            ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->planes, d_rows + done, cnt, n_blocks, d_off, d_mk,
+            e->d_value_first, e->has_centre ? e->d_centre : nullptr, (double*) ctx->s_eval[1].ptr);
+        ++ctx->launches;
+        GSB_CUDA_TRY(cudaGetLastError());
+        GSB_CUDA_TRY(cudaMemcpyAsync(out + (size_t) done * 2 * n_blocks, ctx->s_eval[1].ptr, (size_t) cnt * row_out,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return GSB200_OK;
+}
+
+int gsb200_allele_counts(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, char allele, int out_kind, void* out) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    const char* what = "gsb200_allele_counts";
+    if (n == 0) return GSB200_OK;
+    GSB_REQUIRE(out != nullptr, GSB200_ERR_ARG, "%s: null output", what);
+    GSB_REQUIRE(out_kind == GSB200_COUNTS_F64 || out_kind == GSB200_COUNTS_I32 || out_kind == GSB200_COUNTS_U8,
+                GSB200_ERR_ARG, "%s: unknown output kind %d", what, out_kind);
+    GSB_TRY(check_rows(ctx, n, rows, what));
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    GSB_TRY(sync_dictionary(ctx));
+    uint32_t* d_rows;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], rows, n, &d_rows));
+    const size_t elt = out_kind == GSB200_COUNTS_F64 ? 8 : (out_kind == GSB200_COUNTS_I32 ? 4 : 1);
+    const size_t row_out = (size_t) ctx->n_markers * elt;
+    const uint32_t slab = (uint32_t) std::max<size_t>(1, std::min<size_t>(n, ((size_t) 1 << 30) / row_out));
+    GSB_TRY(ctx->s_eval[1].ensure((size_t) slab * row_out));
+    for (uint32_t done = 0; done < n; done += slab) {
+        const uint32_t cnt = std::min(slab, n - done);
+        const uint64_t threads = (uint64_t) cnt * ctx->n_markers;
+        const unsigned grid = (unsigned) ((threads + 255) / 256);
+        if (out_kind == GSB200_COUNTS_F64)
+            allele_count_kernel<double><<<grid, 256, 0, ctx->stream>>>(ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->planes,
+                ctx->n_markers, d_rows + done, cnt, ctx->d_dict_sym, (uint8_t) allele, (double*) ctx->s_eval[1].ptr);
+        else if (out_kind == GSB200_COUNTS_I32)
+            allele_count_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->planes,
+                ctx->n_markers, d_rows + done, cnt, ctx->d_dict_sym, (uint8_t) allele, (int32_t*) ctx->s_eval[1].ptr);
+        else
+            allele_count_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->planes,
+                ctx->n_markers, d_rows + done, cnt, ctx->d_dict_sym, (uint8_t) allele, (uint8_t*) ctx->s_eval[1].ptr);
+        ++ctx->launches;
+        GSB_CUDA_TRY(cudaGetLastError());
+        GSB_CUDA_TRY(cudaMemcpyAsync((char*) out + (size_t) done * row_out, ctx->s_eval[1].ptr, (size_t) cnt * row_out,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return GSB200_OK;
+}
+
+int gsb200_top_n(gsb200_ctx* ctx, uint32_t n, const double* values, uint32_t top_n, int low_is_best, uint32_t* out_positions) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    const char* what = "gsb200_top_n";
+    if (n == 0 || top_n == 0) return GSB200_OK;
+    GSB_REQUIRE(values && out_positions, GSB200_ERR_ARG, "%s: null array", what);
+    GSB_REQUIRE(top_n <= n, GSB200_ERR_ARG, "%s: top_n %u exceeds n %u", what, top_n, n);
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    // layout of s_eval[3]: values | keys in | keys out | pos in | pos out
+    const size_t bytes = (size_t) n * (8 + 8 + 8 + 4 + 4);
+    GSB_TRY(ctx->s_eval[3].ensure(bytes));
+    char* base = (char*) ctx->s_eval[3].ptr;
+    double* d_val = (double*) base;
+    uint64_t* d_kin = (uint64_t*) (base + (size_t) n * 8);
+    uint64_t* d_kout = (uint64_t*) (base + (size_t) n * 16);
+    uint32_t* d_pin = (uint32_t*) (base + (size_t) n * 24);
+    uint32_t* d_pout = (uint32_t*) (base + (size_t) n * 28);
+    GSB_CUDA_TRY(cudaMemcpyAsync(d_val, values, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rank_keys_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_val, n, low_is_best, d_kin, d_pin);
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    size_t tmp = 0;
+    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_kin, d_kout, d_pin, d_pout, (int) n, 0, 64, ctx->stream));
+    GSB_TRY(ctx->s_eval[0].ensure(tmp));
+    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->s_eval[0].ptr, tmp, d_kin, d_kout, d_pin, d_pout, (int) n, 0, 64, ctx->stream));
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaMemcpyAsync(out_positions, d_pout, (size_t) top_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GSB200_OK;
+}
+
+}  // extern "C"

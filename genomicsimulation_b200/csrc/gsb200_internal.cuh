@@ -1,0 +1,147 @@
+// gsb200_internal.cuh — shared declarations of the CUDA side of libgsb200.so.
+// Not part of the public boundary (that is include/gsb200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/gsb200.h"
+
+namespace gsb {
+
+void set_error(const char* fmt, ...);
+
+#define GSB_CUDA_TRY(expr)                                                                  \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            gsb::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,             \
+                           cudaGetErrorString(_e));                                         \
+            return GSB200_ERR_CUDA;                                                         \
+        }                                                                                   \
+    } while (0)
+
+#define GSB_TRY(expr)                                                                       \
+    do {                                                                                    \
+        int _s = (expr);                                                                    \
+        if (_s != GSB200_OK) return _s;                                                     \
+    } while (0)
+
+#define GSB_REQUIRE(cond, code, ...)                                                        \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            gsb::set_error(__VA_ARGS__);                                                    \
+            return (code);                                                                  \
+        }                                                                                   \
+    } while (0)
+
+constexpr int kNumSMsB200 = 148;
+constexpr uint32_t kPlaneAlignWords = 32;   // planes padded to 128 B
+
+// A device buffer that only ever grows; contents are scratch.
+struct Scratch {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need);
+    void release();
+};
+
+// One linkage group as the kernels see it (gsc_LinkageGroup, core.h:678-745).
+struct ChrInfo {
+    double   lambda;          // expected_n_crossovers
+    double   exp_neg_lambda;  // exp(-lambda), the Poisson inversion's starting term
+    uint32_t first;           // first marker index (contiguous groups)
+    uint32_t len;             // markers in group
+    uint32_t pos_off;         // offset of group in dists / marker_index
+    uint32_t bucket_off;      // offset of group in the bucket index
+    uint32_t bucket_shift;    // group has 2^shift buckets
+    uint32_t searchable;      // 0: never switches strand (no dists, or all-NaN dists)
+};
+
+// Recombination map resident on the device (gsc_RecombinationMap, core.h:678-765).
+// Chromosomes are in MAP order: the order the reference walks linkage groups and therefore
+// the order of the draw tape.
+struct DeviceMap {
+    bool present = false;
+    bool contiguous = false;        // every linkage group covers a contiguous marker range
+    bool flat = false;              // ... the ranges are disjoint and together cover every marker:
+                                    //     the warp-per-gamete splice applies
+    bool covers_all = false;        // every marker belongs to some linkage group
+    uint32_t n_chr = 0;
+    uint32_t n_positions = 0;
+    uint32_t n_chunks = 0;          // 32-position chunks over all chromosomes (general path)
+    double lambda_sum = 0.0;
+    double lambda_max = 0.0;
+    ChrInfo*  d_chr = nullptr;      // [n_chr]
+    double*   d_dists = nullptr;    // [n_positions] running maximum of the reference's dists (context.cu)
+    uint32_t* d_marker_index = nullptr;
+    uint32_t* d_bucket = nullptr;   // bucket index accelerating upper_bound(dists, x)
+    // general path: chunk k covers positions [chunk_start[k], chunk_start[k]+32) of chromosome chunk_chr[k]
+    uint32_t* d_chunk_chr = nullptr;
+    uint32_t* d_chunk_start = nullptr;
+    void release();
+};
+
+// Effect set resident on the device (gsc_MarkerEffects, core.h:826-846).
+struct DeviceEffects {
+    bool present = false;
+    std::vector<uint32_t> cumn;
+    std::vector<uint8_t> allele;
+    std::vector<double> eff;
+    std::vector<double> centre;     // empty if none
+    bool has_centre = false;
+    double centre_sum = 0.0;        // sequential sum, as core.c:9604-9607
+    // tables derived from the effect set AND the store's symbol dictionary:
+    uint64_t built_for_dict_version = ~0ull;
+    uint32_t built_for_planes = 0;
+    double* d_value_all = nullptr;    // [M << planes]: sum of every entry whose allele == symbol(code)
+    double* d_value_first = nullptr;  // [M << planes]: first such entry only (core.c:10019-10031)
+    double* d_centre = nullptr;       // [M] or null
+    double* d_delta = nullptr;        // planes == 1: value_all[m][1] - value_all[m][0]
+    double  base_all = 0.0;           // planes == 1: sum_m 2 * value_all[m][0]
+    void release();
+};
+
+}  // namespace gsb
+
+struct gsb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t n_markers = 0;
+    uint32_t planes = 1;
+    uint32_t plane_words = 0;       // 32-bit words per plane (multiple of kPlaneAlignWords)
+    uint64_t capacity = 0;          // rows
+    uint32_t* d_store = nullptr;
+    uint64_t launches = 0;
+    int sm_count = gsb::kNumSMsB200;
+    int* d_flag = nullptr;          // kernel-side error flag (capacity overflow in a splice plan)
+
+    // symbol dictionary: code -> char, per marker. host master copy + device mirror.
+    std::vector<uint8_t> dict_sym;  // [M << planes]
+    std::vector<uint16_t> dict_n;   // [M] number of codes defined (0..2^planes)
+    uint8_t* d_dict_sym = nullptr;
+    uint16_t* d_dict_n = nullptr;
+    uint64_t dict_version = 0;
+    bool dict_dirty = true;
+
+    std::vector<gsb::DeviceMap> maps;
+    std::vector<gsb::DeviceEffects> effects;
+
+    gsb::Scratch s_rows[4];         // index arrays
+    gsb::Scratch s_io;              // char staging / outputs
+    gsb::Scratch s_plan[8];         // meiosis draw buffers
+    gsb::Scratch s_eval[4];
+    gsb::Scratch s_chain[2];        // ping-pong rows of chained selfing
+
+    uint64_t row_words() const { return (uint64_t) 2 * planes * plane_words; }
+};
+
+namespace gsb {
+int sync_dictionary(gsb200_ctx* ctx);                       // store.cu
+int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff);    // evaluate.cu
+int upload_u32(gsb200_ctx* ctx, Scratch& s, const uint32_t* host, size_t n, uint32_t** out);
+int check_rows(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const char* what);
+}  // namespace gsb

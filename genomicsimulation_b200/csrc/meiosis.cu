@@ -1,0 +1,925 @@
+// meiosis.cu — batched gamete generation on the bit-packed store (K1-K4).
+//
+// Replaces gsc_generate_gamete (core.c:7850-7928), gsc_generate_doubled_haploid
+// (core.c:7949-8033), gsc_generate_clone (core.c:8047-8055) and the inner double loop of
+// gsc_scaffold_make_new_genotypes (core.c:8301-8330) for every offspring of a batch at once.
+//
+// The reference walks the markers of a chromosome and flips the strand it copies from while
+// `dists[i] > crossover[k]` (core.c:7902-7903).  Equivalently (see context.cu): with d[] the
+// running maximum of dists, the strand at marker i is
+//        start_strand  XOR  parity( #{ j : d[i] > x_j } )
+// so every crossover j, independently of the others and of their order, flips the strand on
+// the marker range [ub_j, end of chromosome), ub_j = first i with d[i] > x_j, and a start
+// strand of 1 flips the whole chromosome.  A gamete is therefore described by a small
+// multiset of "toggles" (marker positions where the strand mask flips from there to the end
+// of the genome; every range contributes one toggle at its start and one at its end), and
+// the strand mask of a 128-marker piece is: parity of the toggles before it, XOR a partial
+// mask per toggle inside it.  No sorting is needed — XOR commutes.
+//
+// Fast kernel (maps whose linkage groups are contiguous, disjoint and cover every marker):
+// one warp per gamete.  The warp draws (or reads from the replay tape) the crossover counts
+// lane-per-chromosome, the positions lane-per-crossover, locates each crossover with a
+// bucketed upper_bound on the reference's own fp64 dists, bins the toggles by 128-marker
+// piece with shared-memory atomics, prefix-sums the bins, and then streams the plane with
+// 128-bit loads and stores, reading only the parental strand(s) a piece actually inherits.
+//
+// General kernel (REORDER linkage groups, maps that do not cover every marker, maps with so
+// many linkage groups that the toggle list does not fit shared memory — e.g. the unlinked
+// map of core.c:6128-6152): one thread per 32 consecutive map positions, gathers bit by bit.
+#include "gsb200_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cub/cub.cuh>
+
+using namespace gsb;
+
+namespace {
+
+constexpr uint32_t kMaxNativeGenerations = 2048;   // generation field of the Philox counter
+constexpr uint32_t kMaxNativeCrossovers = (1u << 20) - 2;
+constexpr double   kMaxNativeLambda = 500.0;
+
+struct MapView {
+    const ChrInfo* chr;
+    const double* dists;
+    const uint32_t* bucket;
+    const uint32_t* marker_index;
+    const uint32_t* chunk_chr;
+    const uint32_t* chunk_start;
+    uint32_t n_chr;
+    uint32_t n_chunks;
+};
+
+struct DrawView {
+    uint32_t mode;             // GSB200_DRAWS_*
+    uint32_t key0, key1;       // PHILOX
+    uint64_t first_unit;
+    uint32_t generation;
+    // TAPE layout (host tape uploaded, or native draws materialised by export kernels)
+    const uint32_t* tape_k;
+    const uint8_t*  tape_s;
+    const uint64_t* tape_posoff;
+    const double*   tape_pos;
+    uint64_t unit_stride;      // tape entries per unit
+    uint64_t base_offset;      // entries before this generation's gametes within a unit
+};
+
+struct MeiosisArgs {
+    const uint32_t* src_base;  // rows the gametes are made from
+    const uint32_t* src_rows0; // per unit: row of the parent of gamete 0 (null: unit index)
+    const uint32_t* src_rows1; // ... of gamete 1
+    uint32_t* dst_base;
+    const uint32_t* dst_rows;  // per unit (null: unit index)
+    uint64_t row_words;
+    uint32_t plane_words, planes, n_markers;
+    uint32_t n_units;
+    uint32_t gametes_per_unit; // 2: cross / selfing generation, 1: doubled haploid
+    uint32_t doubled;          // write the gamete to both strands
+    MapView map[2];
+    DrawView draws;
+    // fast-kernel plan geometry
+    uint32_t n_u;              // uint4 pieces per plane
+    uint32_t piece_shift;      // pieces per bin = 1 << piece_shift
+    uint32_t n_bins;
+    uint32_t cnt_words;        // >= n_bins + 1, multiple of 4
+    uint32_t xcap, tcap, list_words;
+    uint32_t warp_smem_words;
+    int* flag;
+};
+
+// ------------------------------------------------------------------ native draw stream
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += W0;
+        k1 += W1;
+    }
+    return c;
+}
+
+// uniform in the open interval (0,1), 53 random bits
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
+    const uint64_t v = (((uint64_t) hi << 32) | lo) >> 11;
+    return ((double) v + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ uint4 draw_block(const DrawView& d, uint64_t unit, uint32_t gamete, uint32_t chr, uint32_t index) {
+    const uint4 ctr = make_uint4((uint32_t) unit, (uint32_t) (unit >> 32), chr,
+                                 (index << 12) | (d.generation << 1) | gamete);
+    return philox4x32_10(ctr, d.key0, d.key1);
+}
+
+// Poisson(lambda) by inversion of one uniform; p0 = exp(-lambda).
+__device__ __forceinline__ uint32_t poisson_inverse(double u, double lambda, double p0) {
+    if (!(lambda > 0.0)) return 0;                 // Rf_rpois(0) == 0 (unlinked maps)
+    double p = p0, cdf = p0;
+    uint32_t k = 0;
+    while (u > cdf && k < kMaxNativeCrossovers) {
+        ++k;
+        p *= lambda / (double) k;
+        cdf += p;
+        if (p < 1e-300 && k > lambda) break;       // tail exhausted in fp64
+    }
+    return k;
+}
+
+// (count, start strand) of one gamete-chromosome: the Rf_rpois and `which` draws of
+// core.c:7873 and 7896.
+__device__ __forceinline__ void draw_header(const DrawView& d, const ChrInfo& ci, uint64_t unit, uint32_t gamete,
+                                            uint32_t chr, uint64_t entry, uint32_t& k, uint32_t& strand) {
+    if (d.mode == GSB200_DRAWS_PHILOX) {
+        const uint4 r = draw_block(d, unit, gamete, chr, 0);
+        k = poisson_inverse(u01(r.x, r.y), ci.lambda, ci.exp_neg_lambda);
+        strand = r.z >> 31;
+    } else {
+        k = d.tape_k[entry];
+        strand = d.tape_s[entry] ? 1u : 0u;
+    }
+}
+
+// position of crossover j of one gamete-chromosome: the unif_rand of core.c:7889.
+__device__ __forceinline__ double draw_position(const DrawView& d, uint64_t unit, uint32_t gamete, uint32_t chr,
+                                                uint64_t entry, uint32_t j) {
+    if (d.mode == GSB200_DRAWS_PHILOX) {
+        const uint4 r = draw_block(d, unit, gamete, chr, j + 1);
+        return u01(r.x, r.y);
+    }
+    return d.tape_pos[d.tape_posoff[entry] + j];
+}
+
+// first i in [0, len) with d[i] > x, else len — the marker at which the reference's walk
+// passes crossover x (core.c:7902-7903).
+__device__ __forceinline__ uint32_t first_marker_past(const ChrInfo& ci, const MapView& mv, double x) {
+    if (!(x == x)) return ci.len;                  // NaN never compares below a dist
+    const double* d = mv.dists + ci.pos_off;
+    uint32_t lo = 0, hi = ci.len;
+    if (x >= 0.0 && x < 1.0) {
+        const uint32_t nb = 1u << ci.bucket_shift;
+        const uint32_t b = min((uint32_t) (x * (double) nb), nb - 1);
+        lo = mv.bucket[ci.bucket_off + b];
+        hi = mv.bucket[ci.bucket_off + b + 1];
+    }
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (d[mid] > x) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint64_t entry_index(const DrawView& d, uint64_t unit_local, uint32_t gamete, uint32_t n_chr0, uint32_t chr) {
+    return unit_local * d.unit_stride + d.base_offset + (gamete ? n_chr0 : 0) + chr;
+}
+
+// ------------------------------------------------------------------ fast kernel
+
+constexpr uint32_t kSlotBits = 6, kPosBits = 32 - kSlotBits;
+constexpr int kUnroll = 4;
+
+__device__ __forceinline__ void emit_toggle(uint32_t t, const MeiosisArgs& a, uint32_t* cnt, uint32_t* list, uint32_t* n_list,
+                                            uint32_t& overflow) {
+    if (t >= a.n_markers) return;                  // nothing lies beyond the last marker
+    const uint32_t slot = atomicAdd(&cnt[t >> (7 + a.piece_shift)], 1u);
+    const uint32_t idx = atomicAdd(n_list, 1u);
+    if (idx < a.tcap && slot < (1u << kSlotBits)) list[idx] = (slot << kPosBits) | t;
+    else overflow = 1;
+}
+
+__device__ __forceinline__ uint4 ldg128(const uint32_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+__global__ void __launch_bounds__(256) splice_flat_kernel(const MeiosisArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* cnt = smem + (size_t) warp * a.warp_smem_words;
+    uint32_t* list = cnt + a.cnt_words;            // toggles as emitted: slot << 26 | marker
+    uint32_t* grouped = list + a.tcap;             // toggles binned (aliases xinfo: dead by then)
+    uint2* xinfo = reinterpret_cast<uint2*>(grouped);   // crossover -> (chromosome, index in chromosome)
+    uint32_t* n_list = grouped + a.list_words;
+
+    const uint64_t n_gametes = (uint64_t) a.n_units * a.gametes_per_unit;
+    for (uint64_t g = (uint64_t) blockIdx.x * warps + warp; g < n_gametes; g += (uint64_t) gridDim.x * warps) {
+        const uint32_t unit_local = (uint32_t) (g / a.gametes_per_unit);
+        const uint32_t gam = (uint32_t) (g % a.gametes_per_unit);
+        const uint64_t unit = a.draws.first_unit + unit_local;
+        const MapView& mv = a.map[gam];
+
+        // A. clear the bins
+        for (uint32_t i = lane * 4; i < a.cnt_words; i += 128) *reinterpret_cast<uint4*>(cnt + i) = make_uint4(0, 0, 0, 0);
+        if (lane == 0) *n_list = 0;
+        __syncwarp();
+
+        // B. lane per chromosome: crossover count and start strand
+        uint32_t overflow = 0, n_x = 0;
+        for (uint32_t c0 = 0; c0 < mv.n_chr; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            uint32_t k = 0;
+            if (c < mv.n_chr) {
+                const ChrInfo ci = mv.chr[c];
+                uint32_t strand;
+                draw_header(a.draws, ci, unit, gam, c, entry_index(a.draws, unit_local, gam, a.map[0].n_chr, c), k, strand);
+                if (ci.len == 0) { k = 0; strand = 0; }
+                if (strand) {
+                    emit_toggle(ci.first, a, cnt, list, n_list, overflow);
+                    emit_toggle(ci.first + ci.len, a, cnt, list, n_list, overflow);
+                }
+                if (!ci.searchable) k = 0;         // the positions are drawn but can never be passed
+            }
+            uint32_t incl = k;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int) lane >= o) incl += v;
+            }
+            const uint32_t off = n_x + incl - k;
+            for (uint32_t j = 0; j < k; ++j)
+                if (off + j < a.xcap) xinfo[off + j] = make_uint2(c, j);
+            n_x += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (n_x > a.xcap) overflow = 1;
+        __syncwarp();
+
+        // C. lane per crossover: position -> marker where the strand flips
+        if (n_x <= a.xcap) {
+            for (uint32_t i0 = 0; i0 < n_x; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                uint32_t t0 = 0xffffffffu, t1 = 0xffffffffu;
+                if (i < n_x) {
+                    const uint2 xi = xinfo[i];
+                    const ChrInfo ci = mv.chr[xi.x];
+                    const double x = draw_position(a.draws, unit, gam, xi.x,
+                                                   entry_index(a.draws, unit_local, gam, a.map[0].n_chr, xi.x), xi.y);
+                    const uint32_t ub = first_marker_past(ci, mv, x);
+                    if (ub < ci.len) { t0 = ci.first + ub; t1 = ci.first + ci.len; }
+                }
+                emit_toggle(t0, a, cnt, list, n_list, overflow);
+                emit_toggle(t1, a, cnt, list, n_list, overflow);
+            }
+        }
+        overflow = __any_sync(0xffffffffu, overflow);
+        __syncwarp();
+        if (overflow) {                            // host re-runs the batch on the general kernel
+            if (lane == 0) atomicExch(a.flag, 1);
+            continue;
+        }
+
+        // D. exclusive prefix sum of the bins -> bin b holds grouped[cnt[b] .. cnt[b+1])
+        {
+            const uint32_t n_scan = a.n_bins + 1;
+            const uint32_t per = (n_scan + 31) / 32;
+            const uint32_t lo = min(lane * per, n_scan), hi = min(lo + per, n_scan);
+            uint32_t sum = 0;
+            for (uint32_t i = lo; i < hi; ++i) sum += cnt[i];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int) lane >= o) incl += v;
+            }
+            uint32_t run = incl - sum;
+            for (uint32_t i = lo; i < hi; ++i) { const uint32_t v = cnt[i]; cnt[i] = run; run += v; }
+        }
+        __syncwarp();
+        const uint32_t n_tog = *n_list;
+        for (uint32_t i = lane; i < n_tog; i += 32) {
+            const uint32_t e = list[i], t = e & ((1u << kPosBits) - 1);
+            grouped[cnt[t >> (7 + a.piece_shift)] + (e >> kPosBits)] = t;
+        }
+        __syncwarp();
+
+        // E. stream the plane(s)
+        const uint32_t src_row = gam ? (a.src_rows1 ? a.src_rows1[unit_local] : unit_local)
+                                     : (a.src_rows0 ? a.src_rows0[unit_local] : unit_local);
+        const uint32_t dst_row = a.dst_rows ? a.dst_rows[unit_local] : unit_local;
+        const uint32_t* src = a.src_base + (uint64_t) src_row * a.row_words;
+        uint32_t* dst = a.dst_base + (uint64_t) dst_row * a.row_words;
+        const uint32_t hap_stride = a.planes * a.plane_words;
+
+        for (uint32_t u0 = 0; u0 < a.n_u; u0 += 32 * kUnroll) {
+            uint4 mask[kUnroll];
+#pragma unroll
+            for (int q = 0; q < kUnroll; ++q) {
+                const uint32_t u = u0 + q * 32 + lane;
+                uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+                if (u < a.n_u) {
+                    const uint32_t bin = u >> a.piece_shift;
+                    const uint32_t b = cnt[bin], e = cnt[bin + 1];
+                    m0 = m1 = m2 = m3 = (b & 1u) ? 0xffffffffu : 0u;
+                    if (e != b) {
+                        const uint32_t base = u << 7;
+                        for (uint32_t i = b; i < e; ++i) {
+                            const uint32_t t = grouped[i];
+                            if (t >= base + 128) continue;
+                            const uint32_t o = t > base ? t - base : 0;   // flip bits [o, 128)
+                            m0 ^= o < 32 ? (0xffffffffu << o) : 0u;
+                            m1 ^= o <= 32 ? 0xffffffffu : (o < 64 ? (0xffffffffu << (o - 32)) : 0u);
+                            m2 ^= o <= 64 ? 0xffffffffu : (o < 96 ? (0xffffffffu << (o - 64)) : 0u);
+                            m3 ^= o <= 96 ? 0xffffffffu : (0xffffffffu << (o - 96));
+                        }
+                    }
+                }
+                mask[q] = make_uint4(m0, m1, m2, m3);
+            }
+            for (uint32_t p = 0; p < a.planes; ++p) {
+                const uint32_t* s0 = src + (uint64_t) p * a.plane_words;
+                const uint32_t* s1 = s0 + hap_stride;
+                uint4 h0[kUnroll], h1[kUnroll];
+#pragma unroll
+                for (int q = 0; q < kUnroll; ++q) {
+                    const uint32_t u = u0 + q * 32 + lane;
+                    const uint4 m = mask[q];
+                    h0[q] = h1[q] = make_uint4(0, 0, 0, 0);
+                    if (u < a.n_u) {
+                        if ((m.x & m.y & m.z & m.w) != 0xffffffffu) h0[q] = ldg128(s0 + 4 * u);
+                        if ((m.x | m.y | m.z | m.w) != 0u) h1[q] = ldg128(s1 + 4 * u);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kUnroll; ++q) {
+                    const uint32_t u = u0 + q * 32 + lane;
+                    if (u < a.n_u) {
+                        const uint4 m = mask[q];
+                        uint4 r;
+                        r.x = (h0[q].x & ~m.x) | (h1[q].x & m.x);
+                        r.y = (h0[q].y & ~m.y) | (h1[q].y & m.y);
+                        r.z = (h0[q].z & ~m.z) | (h1[q].z & m.z);
+                        r.w = (h0[q].w & ~m.w) | (h1[q].w & m.w);
+                        uint32_t* out = dst + (uint64_t) (gam * a.planes + p) * a.plane_words + 4 * u;
+                        *reinterpret_cast<uint4*>(out) = r;
+                        if (a.doubled) *reinterpret_cast<uint4*>(out + hap_stride) = r;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ general kernel
+
+__global__ void zero_rows_kernel(uint32_t* base, const uint32_t* rows, uint32_t n, uint64_t row_words) {
+    const uint64_t per_row = row_words / 4;
+    const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (uint64_t) n * per_row) return;
+    const uint32_t i = (uint32_t) (tid / per_row);
+    const uint64_t row = rows ? rows[i] : i;
+    reinterpret_cast<uint4*>(base + row * row_words)[tid % per_row] = make_uint4(0, 0, 0, 0);
+}
+
+// One thread per (unit, 32 consecutive positions of one linkage group) of gamete `gam`.
+// Draws always come in tape layout here.  Output rows must have been zeroed.
+__global__ void splice_general_kernel(const MeiosisArgs a, const uint32_t gam) {
+    const MapView& mv = a.map[gam];
+    const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (uint64_t) a.n_units * mv.n_chunks) return;
+    const uint32_t unit_local = (uint32_t) (tid / mv.n_chunks), q = (uint32_t) (tid % mv.n_chunks);
+    const uint32_t c = mv.chunk_chr[q], start = mv.chunk_start[q];
+    const ChrInfo ci = mv.chr[c];
+    const uint64_t entry = entry_index(a.draws, unit_local, gam, a.map[0].n_chr, c);
+    const uint32_t k = ci.searchable ? a.draws.tape_k[entry] : 0;
+    const uint32_t strand0 = a.draws.tape_s[entry] ? 1u : 0u;
+    const double* pos = a.draws.tape_pos + a.draws.tape_posoff[entry];
+    const uint32_t n_here = min(32u, ci.len - start);
+
+    const uint32_t src_row = gam ? (a.src_rows1 ? a.src_rows1[unit_local] : unit_local)
+                                 : (a.src_rows0 ? a.src_rows0[unit_local] : unit_local);
+    const uint32_t dst_row = a.dst_rows ? a.dst_rows[unit_local] : unit_local;
+    const uint32_t* src = a.src_base + (uint64_t) src_row * a.row_words;
+    uint32_t* dst = a.dst_base + (uint64_t) dst_row * a.row_words;
+    const uint32_t hap_stride = a.planes * a.plane_words;
+
+    // strand of each of the positions
+    uint32_t strands = 0;
+    for (uint32_t i = 0; i < n_here; ++i) {
+        const double d = mv.dists[ci.pos_off + start + i];
+        uint32_t passed = 0;
+        for (uint32_t j = 0; j < k; ++j) passed += (d > pos[j]) ? 1u : 0u;
+        strands |= ((strand0 ^ passed) & 1u) << i;
+    }
+    for (uint32_t p = 0; p < a.planes; ++p) {
+        uint32_t cur_word = 0xffffffffu, acc = 0;
+        for (uint32_t i = 0; i < n_here; ++i) {
+            const uint32_t m = mv.marker_index[ci.pos_off + start + i];
+            const uint32_t s = (strands >> i) & 1u;
+            const uint32_t bit = (src[(uint64_t) (s * a.planes + p) * a.plane_words + (m >> 5)] >> (m & 31)) & 1u;
+            if ((m >> 5) != cur_word) {
+                if (acc) {
+                    uint32_t* out = dst + (uint64_t) (gam * a.planes + p) * a.plane_words + cur_word;
+                    atomicOr(out, acc);
+                    if (a.doubled) atomicOr(out + hap_stride, acc);
+                }
+                cur_word = m >> 5;
+                acc = 0;
+            }
+            acc |= bit << (m & 31);
+        }
+        if (acc) {
+            uint32_t* out = dst + (uint64_t) (gam * a.planes + p) * a.plane_words + cur_word;
+            atomicOr(out, acc);
+            if (a.doubled) atomicOr(out + hap_stride, acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ native draws -> tape layout
+
+// entry e of unit u: gamete = e >= n_chr0, chromosome = e - (gamete ? n_chr0 : 0)
+__global__ void export_headers_kernel(const MeiosisArgs a, uint32_t* out_k, uint8_t* out_s, uint64_t* out_k64) {
+    const uint32_t per_unit = a.map[0].n_chr + (a.gametes_per_unit > 1 ? a.map[1].n_chr : 0);
+    const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (uint64_t) a.n_units * per_unit) return;
+    const uint32_t unit_local = (uint32_t) (tid / per_unit), e = (uint32_t) (tid % per_unit);
+    const uint32_t gam = e >= a.map[0].n_chr ? 1u : 0u;
+    const uint32_t c = e - (gam ? a.map[0].n_chr : 0);
+    const ChrInfo ci = a.map[gam].chr[c];
+    uint32_t k, strand;
+    draw_header(a.draws, ci, a.draws.first_unit + unit_local, gam, c, 0, k, strand);
+    out_k[tid] = k;
+    out_s[tid] = (uint8_t) strand;
+    out_k64[tid] = k;
+}
+
+__global__ void export_positions_kernel(const MeiosisArgs a, const uint32_t* k_arr, const uint64_t* posoff, double* out_pos) {
+    const uint32_t per_unit = a.map[0].n_chr + (a.gametes_per_unit > 1 ? a.map[1].n_chr : 0);
+    const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (uint64_t) a.n_units * per_unit) return;
+    const uint32_t unit_local = (uint32_t) (tid / per_unit), e = (uint32_t) (tid % per_unit);
+    const uint32_t gam = e >= a.map[0].n_chr ? 1u : 0u;
+    const uint32_t c = e - (gam ? a.map[0].n_chr : 0);
+    const uint32_t k = k_arr[tid];
+    double* dst = out_pos + posoff[tid];
+    for (uint32_t j = 0; j < k; ++j) dst[j] = draw_position(a.draws, a.draws.first_unit + unit_local, gam, c, 0, j);
+}
+
+// ------------------------------------------------------------------ clone
+
+__global__ void copy_rows_kernel(uint32_t* store, const uint32_t* src_rows, const uint32_t* dst_rows, uint32_t n, uint64_t row_words) {
+    const uint64_t per_row = row_words / 4;
+    const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (uint64_t) n * per_row) return;
+    const uint32_t i = (uint32_t) (tid / per_row);
+    const uint64_t w = tid % per_row;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(store + (uint64_t) src_rows[i] * row_words) + w);
+    reinterpret_cast<uint4*>(store + (uint64_t) dst_rows[i] * row_words)[w] = v;
+}
+
+// ------------------------------------------------------------------ host side
+
+MapView view_of(const DeviceMap& m) {
+    MapView v;
+    v.chr = m.d_chr; v.dists = m.d_dists; v.bucket = m.d_bucket; v.marker_index = m.d_marker_index;
+    v.chunk_chr = m.d_chunk_chr; v.chunk_start = m.d_chunk_start; v.n_chr = m.n_chr; v.n_chunks = m.n_chunks;
+    return v;
+}
+
+uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+unsigned grid_for(uint64_t threads, unsigned block) { return (unsigned) ((threads + block - 1) / block); }
+
+int get_map(gsb200_ctx* ctx, uint32_t index, const DeviceMap** out, const char* what) {
+    GSB_REQUIRE(index < ctx->maps.size() && ctx->maps[index].present, GSB200_ERR_ARG, "%s: no recombination map at index %u", what, index);
+    *out = &ctx->maps[index];
+    return GSB200_OK;
+}
+
+int check_flag(gsb200_ctx* ctx, int* value) {
+    GSB_CUDA_TRY(cudaMemcpyAsync(value, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (*value) GSB_CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    return GSB200_OK;
+}
+
+// Uncovered markers keep the zero bits of a fresh slot, which must decode to the reference's
+// '\0' (core.c:75): refuse maps with holes unless code 0 is '\0' (or undefined) there.
+int check_coverage(gsb200_ctx* ctx, const DeviceMap& m, const char* what) {
+    if (m.covers_all) return GSB200_OK;
+    set_error("%s: the recombination map does not cover every marker; uncovered markers of the offspring would be "
+              "'\\0' in the reference (sim-operations.c:75) and this store cannot represent that yet", what);
+    return GSB200_ERR_UNSUPPORTED;
+}
+
+struct Batch {
+    const char* what;
+    uint32_t n_units;
+    const uint32_t* src_base; const uint32_t* d_src0; const uint32_t* d_src1;
+    uint32_t* dst_base; const uint32_t* d_dst;
+    const DeviceMap* map0; const DeviceMap* map1;
+    uint32_t gametes_per_unit, doubled;
+    DrawView draws;
+    uint32_t tape_xcap;        // TAPE: most crossovers in one gamete
+};
+
+// Philox draws materialised in tape layout on the device (s_plan[4..7]).
+int materialise_draws(gsb200_ctx* ctx, MeiosisArgs& a, uint64_t* n_positions_out) {
+    const uint32_t per_unit = a.map[0].n_chr + (a.gametes_per_unit > 1 ? a.map[1].n_chr : 0);
+    const uint64_t n_entries = (uint64_t) a.n_units * per_unit;
+    GSB_TRY(ctx->s_plan[4].ensure(n_entries * sizeof(uint32_t)));
+    GSB_TRY(ctx->s_plan[5].ensure(n_entries));
+    GSB_TRY(ctx->s_plan[6].ensure((n_entries + 1) * sizeof(uint64_t)));
+    uint32_t* d_k = (uint32_t*) ctx->s_plan[4].ptr;
+    uint8_t* d_s = (uint8_t*) ctx->s_plan[5].ptr;
+    uint64_t* d_off = (uint64_t*) ctx->s_plan[6].ptr;
+    export_headers_kernel<<<grid_for(n_entries, 256), 256, 0, ctx->stream>>>(a, d_k, d_s, d_off);
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    uint64_t last_k = 0, last_off = 0;
+    GSB_CUDA_TRY(cudaMemcpyAsync(&last_k, d_off + n_entries - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    size_t tmp_bytes = 0;
+    GSB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_off, d_off, n_entries, ctx->stream));
+    GSB_TRY(ctx->s_plan[3].ensure(tmp_bytes));
+    GSB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(ctx->s_plan[3].ptr, tmp_bytes, d_off, d_off, n_entries, ctx->stream));
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaMemcpyAsync(&last_off, d_off + n_entries - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const uint64_t n_pos = last_off + last_k;
+    GSB_TRY(ctx->s_plan[7].ensure(std::max<uint64_t>(n_pos, 1) * sizeof(double)));
+    export_positions_kernel<<<grid_for(n_entries, 256), 256, 0, ctx->stream>>>(a, d_k, d_off, (double*) ctx->s_plan[7].ptr);
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    a.draws.mode = GSB200_DRAWS_TAPE;
+    a.draws.tape_k = d_k;
+    a.draws.tape_s = d_s;
+    a.draws.tape_posoff = d_off;
+    a.draws.tape_pos = (const double*) ctx->s_plan[7].ptr;
+    a.draws.unit_stride = per_unit;
+    a.draws.base_offset = 0;
+    *n_positions_out = n_pos;
+    return GSB200_OK;
+}
+
+int run_general(gsb200_ctx* ctx, MeiosisArgs a) {
+    if (a.draws.mode == GSB200_DRAWS_PHILOX) {
+        uint64_t n_pos = 0;
+        GSB_TRY(materialise_draws(ctx, a, &n_pos));
+    }
+    zero_rows_kernel<<<grid_for((uint64_t) a.n_units * (a.row_words / 4), 256), 256, 0, ctx->stream>>>(
+        a.dst_base, a.dst_rows, a.n_units, a.row_words);
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    for (uint32_t gam = 0; gam < a.gametes_per_unit; ++gam) {
+        const uint64_t threads = (uint64_t) a.n_units * a.map[gam].n_chunks;
+        if (threads == 0) continue;
+        splice_general_kernel<<<grid_for(threads, 128), 128, 0, ctx->stream>>>(a, gam);
+        ++ctx->launches;
+        GSB_CUDA_TRY(cudaGetLastError());
+    }
+    return GSB200_OK;
+}
+
+// Launch one batch of gametes. Asynchronous unless the fast kernel overflows its plan
+// capacity (then the batch is redone on the general kernel) — `may_sync` says whether this
+// call is allowed to wait for that verdict (the `_dev` entry points defer it).
+int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
+    if (b.n_units == 0) return GSB200_OK;
+    GSB_TRY(check_coverage(ctx, *b.map0, b.what));
+    if (b.gametes_per_unit > 1) GSB_TRY(check_coverage(ctx, *b.map1, b.what));
+    MeiosisArgs a;
+    a.src_base = b.src_base; a.src_rows0 = b.d_src0; a.src_rows1 = b.d_src1;
+    a.dst_base = b.dst_base; a.dst_rows = b.d_dst;
+    a.row_words = ctx->row_words(); a.plane_words = ctx->plane_words; a.planes = ctx->planes; a.n_markers = ctx->n_markers;
+    a.n_units = b.n_units; a.gametes_per_unit = b.gametes_per_unit; a.doubled = b.doubled;
+    a.map[0] = view_of(*b.map0);
+    a.map[1] = view_of(b.gametes_per_unit > 1 ? *b.map1 : *b.map0);
+    a.draws = b.draws;
+    a.flag = ctx->d_flag;
+
+    const DeviceMap* maps[2] = { b.map0, b.gametes_per_unit > 1 ? b.map1 : b.map0 };
+    if (b.draws.mode == GSB200_DRAWS_PHILOX) {
+        for (const DeviceMap* m : maps)
+            GSB_REQUIRE(m->lambda_max <= kMaxNativeLambda, GSB200_ERR_UNSUPPORTED,
+                        "%s: a linkage group expects %.1f crossovers; the native draw stream supports at most %.0f",
+                        b.what, m->lambda_max, kMaxNativeLambda);
+        GSB_REQUIRE(b.draws.generation < kMaxNativeGenerations, GSB200_ERR_UNSUPPORTED,
+                    "%s: at most %u chained generations per call", b.what, kMaxNativeGenerations);
+    }
+
+    // plan geometry of the fast kernel
+    bool fast = maps[0]->flat && maps[1]->flat;
+    a.n_u = ctx->plane_words / 4;
+    a.piece_shift = 0;
+    while ((a.n_u >> a.piece_shift) > 2040) ++a.piece_shift;
+    a.n_bins = (a.n_u + (1u << a.piece_shift) - 1) >> a.piece_shift;
+    a.cnt_words = (a.n_bins + 1 + 3) / 4 * 4;
+    uint32_t xcap, n_chr_max = std::max(maps[0]->n_chr, maps[1]->n_chr);
+    if (b.draws.mode == GSB200_DRAWS_TAPE) {
+        xcap = b.tape_xcap;
+    } else {
+        const double ls = std::max(maps[0]->lambda_sum, maps[1]->lambda_sum);
+        xcap = (uint32_t) std::ceil(ls + 8.0 * std::sqrt(ls) + 16.0);
+        if (std::max(maps[0]->lambda_max, maps[1]->lambda_max) > 16.0) fast = false;   // slot field of a toggle
+    }
+    xcap = std::max<uint32_t>((xcap + 31) / 32 * 32, 32);
+    a.xcap = xcap;
+    a.tcap = 2 * xcap + 2 * n_chr_max;
+    a.list_words = std::max(a.tcap, 2 * xcap);
+    a.warp_smem_words = (a.cnt_words + a.tcap + a.list_words + 4 + 3) / 4 * 4;
+    if (ctx->n_markers >= (1u << kPosBits)) fast = false;
+    uint32_t warps = 8;
+    const size_t smem_limit = 200 * 1024;
+    while (warps > 1 && (size_t) warps * a.warp_smem_words * 4 > smem_limit / 2) warps >>= 1;
+    if ((size_t) warps * a.warp_smem_words * 4 > smem_limit) fast = false;
+
+    if (fast) {
+        const size_t smem = (size_t) warps * a.warp_smem_words * 4;
+        if (smem > 48 * 1024)
+            GSB_CUDA_TRY(cudaFuncSetAttribute(splice_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_limit));
+        const uint64_t n_gametes = (uint64_t) a.n_units * a.gametes_per_unit;
+        const uint64_t blocks = (n_gametes + warps - 1) / warps;
+        const unsigned grid = (unsigned) std::min<uint64_t>(blocks, (uint64_t) ctx->sm_count * 64);
+        splice_flat_kernel<<<grid, warps * 32, smem, ctx->stream>>>(a);
+        ++ctx->launches;
+        GSB_CUDA_TRY(cudaGetLastError());
+        if (!may_sync) return GSB200_OK;
+        int flag = 0;
+        GSB_TRY(check_flag(ctx, &flag));
+        if (!flag) return GSB200_OK;
+        // plan capacity exceeded somewhere in the batch: same draws, general kernel
+    }
+    GSB_REQUIRE(may_sync || !fast, GSB200_ERR_UNSUPPORTED, "%s: internal: unreachable", b.what);
+    return run_general(ctx, a);
+}
+
+struct TapeUpload {
+    const uint32_t* d_k = nullptr;
+    const uint8_t* d_s = nullptr;
+    const uint64_t* d_off = nullptr;
+    const double* d_pos = nullptr;
+    uint32_t xcap = 0;
+};
+
+// Validate a host tape against the request and put it on the device (s_plan[0..3]).
+int upload_tape(gsb200_ctx* ctx, const gsb200_draws* d, uint64_t n_units, uint64_t entries_per_unit,
+                const uint32_t* gamete_lengths, uint32_t gametes_in_unit, TapeUpload* out, const char* what) {
+    const uint64_t n_entries = n_units * entries_per_unit;
+    GSB_REQUIRE(d->n_entries == n_entries, GSB200_ERR_TAPE, "%s: the tape has %llu gamete-chromosome entries, the request needs %llu",
+                what, (unsigned long long) d->n_entries, (unsigned long long) n_entries);
+    GSB_REQUIRE(n_entries == 0 || (d->n_crossovers && d->start_strand), GSB200_ERR_TAPE, "%s: null tape arrays", what);
+    std::vector<uint64_t> off(n_entries + 1);
+    uint64_t run = 0;
+    uint32_t xcap = 0;
+    uint64_t e = 0;
+    for (uint64_t u = 0; u < n_units; ++u) {
+        for (uint32_t gI = 0; gI < gametes_in_unit; ++gI) {
+            uint64_t in_gamete = 0;
+            for (uint32_t c = 0; c < gamete_lengths[gI]; ++c, ++e) {
+                off[e] = run;
+                run += d->n_crossovers[e];
+                in_gamete += d->n_crossovers[e];
+            }
+            GSB_REQUIRE(in_gamete < (1u << 30), GSB200_ERR_TAPE, "%s: absurd crossover count on the tape", what);
+            xcap = std::max<uint32_t>(xcap, (uint32_t) in_gamete);
+        }
+    }
+    off[n_entries] = run;
+    GSB_REQUIRE(run == d->n_positions, GSB200_ERR_TAPE, "%s: the tape's counts sum to %llu positions but %llu were given",
+                what, (unsigned long long) run, (unsigned long long) d->n_positions);
+    GSB_REQUIRE(run == 0 || d->positions, GSB200_ERR_TAPE, "%s: null tape positions", what);
+    GSB_TRY(ctx->s_plan[0].ensure(std::max<uint64_t>(n_entries, 1) * sizeof(uint32_t)));
+    GSB_TRY(ctx->s_plan[1].ensure(std::max<uint64_t>(n_entries, 1)));
+    GSB_TRY(ctx->s_plan[2].ensure((n_entries + 1) * sizeof(uint64_t)));
+    GSB_TRY(ctx->s_plan[3].ensure(std::max<uint64_t>(run, 1) * sizeof(double)));
+    if (n_entries) {
+        GSB_CUDA_TRY(cudaMemcpyAsync(ctx->s_plan[0].ptr, d->n_crossovers, n_entries * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        GSB_CUDA_TRY(cudaMemcpyAsync(ctx->s_plan[1].ptr, d->start_strand, n_entries, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    GSB_CUDA_TRY(cudaMemcpyAsync(ctx->s_plan[2].ptr, off.data(), (n_entries + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (run) GSB_CUDA_TRY(cudaMemcpyAsync(ctx->s_plan[3].ptr, d->positions, run * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // `off` is about to go out of scope
+    out->d_k = (const uint32_t*) ctx->s_plan[0].ptr;
+    out->d_s = (const uint8_t*) ctx->s_plan[1].ptr;
+    out->d_off = (const uint64_t*) ctx->s_plan[2].ptr;
+    out->d_pos = (const double*) ctx->s_plan[3].ptr;
+    out->xcap = xcap;
+    return GSB200_OK;
+}
+
+int make_draw_view(const gsb200_draws* d, DrawView* v, const char* what) {
+    GSB_REQUIRE(d != nullptr, GSB200_ERR_ARG, "%s: null draws", what);
+    GSB_REQUIRE(d->mode == GSB200_DRAWS_PHILOX || d->mode == GSB200_DRAWS_TAPE, GSB200_ERR_ARG, "%s: unknown draw mode %u", what, d->mode);
+    memset(v, 0, sizeof *v);
+    v->mode = d->mode;
+    const uint64_t key = splitmix64(splitmix64(d->seed) ^ (d->stream * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull));
+    v->key0 = (uint32_t) key;
+    v->key1 = (uint32_t) (key >> 32);
+    v->first_unit = d->first_unit;
+    return GSB200_OK;
+}
+
+int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t* d_p2, uint32_t map1, uint32_t map2,
+               const uint32_t* d_out, const gsb200_draws* draws, bool may_sync, const char* what) {
+    const DeviceMap *m1, *m2;
+    GSB_TRY(get_map(ctx, map1, &m1, what));
+    GSB_TRY(get_map(ctx, map2, &m2, what));
+    Batch b;
+    b.what = what; b.n_units = n;
+    b.src_base = ctx->d_store; b.d_src0 = d_p1; b.d_src1 = d_p2; b.dst_base = ctx->d_store; b.d_dst = d_out;
+    b.map0 = m1; b.map1 = m2; b.gametes_per_unit = 2; b.doubled = 0; b.tape_xcap = 0;
+    GSB_TRY(make_draw_view(draws, &b.draws, what));
+    if (draws->mode == GSB200_DRAWS_TAPE) {
+        GSB_REQUIRE(may_sync, GSB200_ERR_ARG, "%s: device-pointer entry points take PHILOX draws only", what);
+        const uint32_t lens[2] = { m1->n_chr, m2->n_chr };
+        TapeUpload t;
+        GSB_TRY(upload_tape(ctx, draws, n, (uint64_t) m1->n_chr + m2->n_chr, lens, 2, &t, what));
+        b.draws.tape_k = t.d_k; b.draws.tape_s = t.d_s; b.draws.tape_posoff = t.d_off; b.draws.tape_pos = t.d_pos;
+        b.draws.unit_stride = (uint64_t) m1->n_chr + m2->n_chr;
+        b.draws.base_offset = 0;
+        b.draws.first_unit = 0;
+        b.tape_xcap = t.xcap;
+    }
+    return run_batch(ctx, b, may_sync);
+}
+
+}  // namespace
+
+extern "C" {
+
+int gsb200_cross(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent1_rows, const uint32_t* parent2_rows,
+                 uint32_t map1, uint32_t map2, const uint32_t* out_rows, const gsb200_draws* draws) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    if (n == 0) return GSB200_OK;
+    GSB_TRY(check_rows(ctx, n, parent1_rows, "gsb200_cross (parent 1)"));
+    GSB_TRY(check_rows(ctx, n, parent2_rows, "gsb200_cross (parent 2)"));
+    GSB_TRY(check_rows(ctx, n, out_rows, "gsb200_cross (offspring)"));
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint32_t *d1, *d2, *dout;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], parent1_rows, n, &d1));
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[1], parent2_rows, n, &d2));
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[2], out_rows, n, &dout));
+    GSB_TRY(cross_impl(ctx, n, d1, d2, map1, map2, dout, draws, true, "gsb200_cross"));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GSB200_OK;
+}
+
+int gsb200_cross_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1_rows, const uint32_t* d_parent2_rows,
+                     uint32_t map1, uint32_t map2, const uint32_t* d_out_rows, const gsb200_draws* draws) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    if (n == 0) return GSB200_OK;
+    GSB_REQUIRE(d_parent1_rows && d_parent2_rows && d_out_rows, GSB200_ERR_ARG, "gsb200_cross_dev: null row array");
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    return cross_impl(ctx, n, d_parent1_rows, d_parent2_rows, map1, map2, d_out_rows, draws, false, "gsb200_cross_dev");
+}
+
+int gsb200_cross_dev_status(gsb200_ctx* ctx) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    int flag = 0;
+    GSB_TRY(check_flag(ctx, &flag));
+    GSB_REQUIRE(flag == 0, GSB200_ERR_UNSUPPORTED,
+                "a gsb200_cross_dev batch exceeded the splice plan's capacity; redo it with gsb200_cross");
+    return GSB200_OK;
+}
+
+int gsb200_doubled_haploid(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent_rows, uint32_t map,
+                           const uint32_t* out_rows, const gsb200_draws* draws) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    if (n == 0) return GSB200_OK;
+    const char* what = "gsb200_doubled_haploid";
+    GSB_TRY(check_rows(ctx, n, parent_rows, what));
+    GSB_TRY(check_rows(ctx, n, out_rows, what));
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    const DeviceMap* m;
+    GSB_TRY(get_map(ctx, map, &m, what));
+    uint32_t *d1, *dout;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], parent_rows, n, &d1));
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[2], out_rows, n, &dout));
+    Batch b;
+    b.what = what; b.n_units = n;
+    b.src_base = ctx->d_store; b.d_src0 = d1; b.d_src1 = d1; b.dst_base = ctx->d_store; b.d_dst = dout;
+    b.map0 = m; b.map1 = m; b.gametes_per_unit = 1; b.doubled = 1; b.tape_xcap = 0;
+    GSB_TRY(make_draw_view(draws, &b.draws, what));
+    if (draws->mode == GSB200_DRAWS_TAPE) {
+        const uint32_t lens[1] = { m->n_chr };
+        TapeUpload t;
+        GSB_TRY(upload_tape(ctx, draws, n, m->n_chr, lens, 1, &t, what));
+        b.draws.tape_k = t.d_k; b.draws.tape_s = t.d_s; b.draws.tape_posoff = t.d_off; b.draws.tape_pos = t.d_pos;
+        b.draws.unit_stride = m->n_chr;
+        b.draws.first_unit = 0;
+        b.tape_xcap = t.xcap;
+    }
+    GSB_TRY(run_batch(ctx, b, true));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GSB200_OK;
+}
+
+int gsb200_self_n_times(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent_rows, uint32_t n_generations,
+                        uint32_t map, const uint32_t* out_rows, const gsb200_draws* draws) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    const char* what = "gsb200_self_n_times";
+    GSB_REQUIRE(n_generations >= 1, GSB200_ERR_ARG, "%s: n_generations must be at least 1", what);
+    if (n == 0) return GSB200_OK;
+    GSB_TRY(check_rows(ctx, n, parent_rows, what));
+    GSB_TRY(check_rows(ctx, n, out_rows, what));
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    const DeviceMap* m;
+    GSB_TRY(get_map(ctx, map, &m, what));
+    uint32_t *d1, *dout;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], parent_rows, n, &d1));
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[2], out_rows, n, &dout));
+    DrawView dv;
+    GSB_TRY(make_draw_view(draws, &dv, what));
+    TapeUpload t;
+    const uint64_t per_unit = (uint64_t) n_generations * 2 * m->n_chr;
+    if (draws->mode == GSB200_DRAWS_TAPE) {
+        std::vector<uint32_t> lens(2 * (size_t) n_generations, m->n_chr);
+        GSB_TRY(upload_tape(ctx, draws, n, per_unit, lens.data(), (uint32_t) lens.size(), &t, what));
+    }
+    // Intermediate generations live in two ping-pong scratch row sets, never in the store
+    // (the reference ping-pongs a temporary genotype the same way, core.c:8908-8923); lines
+    // are processed in slabs so that the scratch stays bounded.
+    const uint64_t row_bytes = ctx->row_words() * sizeof(uint32_t);
+    const uint32_t slab = (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(n, ((uint64_t) 4 << 30) / row_bytes));
+    if (n_generations > 1) {
+        GSB_TRY(ctx->s_chain[0].ensure((uint64_t) slab * row_bytes));
+        if (n_generations > 2) GSB_TRY(ctx->s_chain[1].ensure((uint64_t) slab * row_bytes));
+    }
+    for (uint32_t done = 0; done < n; done += slab) {
+        const uint32_t cnt = std::min(slab, n - done);
+        for (uint32_t gen = 0; gen < n_generations; ++gen) {
+            Batch b;
+            b.what = what; b.n_units = cnt;
+            const bool first = gen == 0, last = gen + 1 == n_generations;
+            // generation `gen` reads scratch (gen-1)&1 and writes scratch gen&1; the first reads the
+            // store, the last writes it
+            b.src_base = first ? ctx->d_store : (const uint32_t*) ctx->s_chain[(gen - 1) & 1].ptr;
+            b.d_src0 = b.d_src1 = first ? d1 + done : nullptr;
+            b.dst_base = last ? ctx->d_store : (uint32_t*) ctx->s_chain[gen & 1].ptr;
+            b.d_dst = last ? dout + done : nullptr;
+            b.map0 = b.map1 = m; b.gametes_per_unit = 2; b.doubled = 0; b.tape_xcap = t.xcap;
+            b.draws = dv;
+            b.draws.generation = gen;
+            b.draws.first_unit = dv.first_unit + done;
+            if (draws->mode == GSB200_DRAWS_TAPE) {
+                b.draws.tape_k = t.d_k + (uint64_t) done * per_unit;
+                b.draws.tape_s = t.d_s + (uint64_t) done * per_unit;
+                b.draws.tape_posoff = t.d_off + (uint64_t) done * per_unit;
+                b.draws.tape_pos = t.d_pos;
+                b.draws.unit_stride = per_unit;
+                b.draws.base_offset = (uint64_t) gen * 2 * m->n_chr;
+                b.draws.first_unit = 0;
+            }
+            GSB_TRY(run_batch(ctx, b, true));
+        }
+    }
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GSB200_OK;
+}
+
+int gsb200_clone(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent_rows, const uint32_t* out_rows) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    if (n == 0) return GSB200_OK;
+    GSB_TRY(check_rows(ctx, n, parent_rows, "gsb200_clone"));
+    GSB_TRY(check_rows(ctx, n, out_rows, "gsb200_clone"));
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint32_t *d1, *dout;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], parent_rows, n, &d1));
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[2], out_rows, n, &dout));
+    copy_rows_kernel<<<grid_for((uint64_t) n * (ctx->row_words() / 4), 256), 256, 0, ctx->stream>>>(
+        ctx->d_store, d1, dout, n, ctx->row_words());
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GSB200_OK;
+}
+
+int gsb200_export_draws(gsb200_ctx* ctx, uint32_t map, uint64_t n_units, uint32_t gametes_per_unit,
+                        const gsb200_draws* philox, uint32_t* n_crossovers, uint8_t* start_strand,
+                        double* positions, uint64_t positions_cap, uint64_t* n_positions) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    const char* what = "gsb200_export_draws";
+    GSB_REQUIRE(philox && philox->mode == GSB200_DRAWS_PHILOX, GSB200_ERR_ARG, "%s: needs PHILOX draws", what);
+    GSB_REQUIRE(gametes_per_unit == 1 || gametes_per_unit == 2, GSB200_ERR_ARG, "%s: gametes_per_unit must be 1 or 2", what);
+    GSB_REQUIRE(n_units > 0 && n_units < (1ull << 31) && n_crossovers && start_strand && n_positions, GSB200_ERR_ARG, "%s: bad arguments", what);
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    const DeviceMap* m;
+    GSB_TRY(get_map(ctx, map, &m, what));
+    GSB_REQUIRE(m->lambda_max <= kMaxNativeLambda, GSB200_ERR_UNSUPPORTED, "%s: lambda too large for the native stream", what);
+    MeiosisArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_units = (uint32_t) n_units;
+    a.gametes_per_unit = gametes_per_unit;
+    a.map[0] = a.map[1] = view_of(*m);
+    GSB_TRY(make_draw_view(philox, &a.draws, what));
+    uint64_t n_pos = 0;
+    GSB_TRY(materialise_draws(ctx, a, &n_pos));
+    const uint64_t n_entries = n_units * gametes_per_unit * m->n_chr;
+    *n_positions = n_pos;
+    GSB_CUDA_TRY(cudaMemcpyAsync(n_crossovers, a.draws.tape_k, n_entries * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA_TRY(cudaMemcpyAsync(start_strand, a.draws.tape_s, n_entries, cudaMemcpyDeviceToHost, ctx->stream));
+    if (positions && n_pos <= positions_cap && n_pos)
+        GSB_CUDA_TRY(cudaMemcpyAsync(positions, a.draws.tape_pos, n_pos * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    GSB_REQUIRE(n_pos <= positions_cap || positions == nullptr, GSB200_ERR_ARG,
+                "%s: %llu positions do not fit the buffer of %llu", what, (unsigned long long) n_pos, (unsigned long long) positions_cap);
+    return GSB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+/* gsb200.h — the C-ABI of the B200-native meiosis + genomic-evaluation engine.
+ *
+ * This is the drop-in boundary for genomicSimulation's hot path: plain C types,
+ * opaque handle, `int` status (0 = ok) + gsb200_last_error().  Everything the
+ * reference does inside `src/sim-operations.c` ("core.c") on the `gsc_AlleleMatrix`
+ * payload for crossing and evaluation is reachable through these entry points; the
+ * host-side mirror of the reference API (include/gsb200_gsc.h) and any future
+ * patch of the reference's own core call nothing else.  No torch types, no C++.
+ *
+ * Each entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *  - "row": index of one diploid genotype in the device-resident, bit-packed
+ *    haplotype store (replaces `char* alleles[i]`, core.h:778-783).  Rows are
+ *    chosen by the caller (the host core keeps the slot table).
+ *  - pointer arguments are HOST pointers unless the function name ends in `_dev`.
+ *  - all launches go to the context's stream; non-`_dev` functions synchronise
+ *    before returning, `_dev` functions do not.
+ *  - there is no CPU fallback: every function fails with GSB200_ERR_CUDA if the
+ *    device is unusable.
+ */
+#ifndef GSB200_H
+#define GSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define GSB200_ABI_VERSION 1
+
+enum {
+    GSB200_OK = 0,
+    GSB200_ERR_CUDA = 1,        /* a CUDA runtime call failed / no device          */
+    GSB200_ERR_ARG = 2,         /* invalid argument                                */
+    GSB200_ERR_OOM = 3,         /* host or device allocation failed                */
+    GSB200_ERR_UNSUPPORTED = 4, /* valid in the reference, not (yet) on this path  */
+    GSB200_ERR_TAPE = 5         /* replay tape inconsistent with the request       */
+};
+
+typedef struct gsb200_ctx gsb200_ctx;
+
+/* ------------------------------------------------------------------ context */
+
+int  gsb200_abi_version(void);
+const char* gsb200_last_error(void);             /* thread-local, never NULL */
+
+/* One context per SimData (replaces the payload side of gsc_create_empty_simdata,
+ * core.c:113-132, and gsc_delete_simdata, core.c:5047). */
+int  gsb200_create(gsb200_ctx** out, int device_ordinal, uint32_t n_markers);
+void gsb200_destroy(gsb200_ctx* ctx);
+int  gsb200_synchronize(gsb200_ctx* ctx);
+void* gsb200_stream(gsb200_ctx* ctx);            /* cudaStream_t, for timing with events */
+
+/* ------------------------------------------------------------------ store
+ * Bit-packed haplotype store. One row = 2 haplotypes x `planes` bit-planes x
+ * `plane_words` 32-bit words; marker m is bit (m & 31) of word (m >> 5).  With
+ * <= 2 distinct allele symbols at every marker there is one plane (1 bit per
+ * haplotype per marker); a marker with more symbols (including '\0' = unknown,
+ * core.c:75) widens the whole store to 2, 4 or 8 planes.  A per-marker symbol
+ * dictionary maps codes back to the reference's chars. */
+int  gsb200_store_reserve(gsb200_ctx* ctx, uint64_t n_rows);
+uint64_t gsb200_store_capacity(const gsb200_ctx* ctx);
+uint32_t gsb200_store_planes(const gsb200_ctx* ctx);
+uint32_t gsb200_store_plane_words(const gsb200_ctx* ctx);
+uint64_t gsb200_store_row_bytes(const gsb200_ctx* ctx);
+void*    gsb200_store_device_ptr(gsb200_ctx* ctx);   /* base of row 0 (for NCCL / interop) */
+
+/* chars (n x 2*n_markers, the reference's layout: alleles of marker m at [2m],[2m+1])
+ * -> rows.  Replaces the founder fill gsc_helper_genotypecell_to_allelematrix
+ * (core.c:6587-6674).  Extends the dictionary as needed. */
+int  gsb200_store_upload_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const char* chars);
+/* rows -> chars.  The save/see boundary: gsc_helper_output_genotypematrix_cell
+ * (core.c:10951-10958), SXP_see_group_data "G" (r-wrappers.c:815-837). */
+int  gsb200_store_download_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, char* chars);
+/* Packed rows <-> a dense DEVICE buffer of n x gsb200_store_row_bytes() bytes (16-byte aligned):
+ * the send/receive side of the per-generation parent-pool broadcast over NCCL (no reference
+ * counterpart: the reference is single-process). Synchronous on the context stream. */
+int  gsb200_store_gather_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, void* d_dense);
+int  gsb200_store_scatter_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const void* d_dense);
+/* gsc_change_allele_symbol (core.c:1029-1100) for one marker (marker == UINT32_MAX: all). */
+int  gsb200_store_change_symbol(gsb200_ctx* ctx, uint32_t marker, char from, char to);
+/* dictionary of one marker: up to 2^planes symbols, returns how many are defined */
+int  gsb200_store_symbols(const gsb200_ctx* ctx, uint32_t marker, char* out, uint32_t cap);
+
+/* ------------------------------------------------------------------ maps
+ * gsc_RecombinationMap (core.h:678-765) as concatenated linkage groups: chromosome c
+ * covers positions [chr_offset[c], chr_offset[c+1]) of dists / marker_index;
+ * lambda[c] = expected_n_crossovers; has_dists[c] == 0 reproduces dists == NULL of the
+ * unlinked map (core.c:6128-6152).  `dists` must be the reference's own fp64 array
+ * (core.c:5929): the splice rule `dists[i] > crossover` (core.c:7902-7903) is evaluated
+ * on these exact doubles. */
+int  gsb200_map_set(gsb200_ctx* ctx, uint32_t map_index, uint32_t n_chr, const double* lambda,
+                    const uint32_t* chr_offset, const double* dists, const uint32_t* marker_index,
+                    const uint8_t* has_dists);
+int  gsb200_map_delete(gsb200_ctx* ctx, uint32_t map_index);
+uint32_t gsb200_map_n_chr(const gsb200_ctx* ctx, uint32_t map_index);   /* 0 if absent */
+
+/* ------------------------------------------------------------------ effects
+ * gsc_MarkerEffects (core.h:826-846) in the reference's CSR layout; centre may be NULL. */
+int  gsb200_effects_set(gsb200_ctx* ctx, uint32_t eff_index, const uint32_t* cumn_alleles,
+                        const char* allele, const double* eff, const double* centre);
+int  gsb200_effects_delete(gsb200_ctx* ctx, uint32_t eff_index);
+
+/* ------------------------------------------------------------------ meiosis
+ * Source of the random draws of gsc_generate_gamete (core.c:7873, 7889, 7896). */
+enum { GSB200_DRAWS_PHILOX = 0, GSB200_DRAWS_TAPE = 1 };
+
+typedef struct {
+    uint32_t mode;
+    /* PHILOX: counter-based stream keyed by (seed, stream) and indexed by
+     * (first_unit + offspring, generation, gamete, chromosome): results do not depend on
+     * how offspring are batched or sharded over GPUs. */
+    uint64_t seed;
+    uint64_t stream;
+    uint64_t first_unit;
+    /* TAPE (crossover replay): one entry per gamete-chromosome in the reference's own
+     * consumption order — per offspring, per generation (selfing), per gamete, per
+     * chromosome of that gamete's map: the Rf_rpois result, then that many unif_rand
+     * positions (concatenated in `positions`, unsorted, as drawn), then the strand draw
+     * already thresholded (unif_rand() > 0.5). */
+    uint64_t n_entries;
+    const uint32_t* n_crossovers;
+    const uint8_t*  start_strand;
+    uint64_t n_positions;
+    const double*   positions;
+} gsb200_draws;
+
+/* gsc_helper_make_offspring_cross (core.c:8416-8423): offspring i = gamete(parent1[i], map1)
+ * on strand 0, gamete(parent2[i], map2) on strand 1. */
+int  gsb200_cross(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent1_rows, const uint32_t* parent2_rows,
+                  uint32_t map1, uint32_t map2, const uint32_t* out_rows, const gsb200_draws* draws);
+/* gsc_helper_make_offspring_self_n_times (core.c:8900-8926): n_generations rounds of two
+ * gametes from the previous generation; only the last generation is stored. */
+int  gsb200_self_n_times(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent_rows, uint32_t n_generations,
+                         uint32_t map, const uint32_t* out_rows, const gsb200_draws* draws);
+/* gsc_generate_doubled_haploid (core.c:7949-8033). */
+int  gsb200_doubled_haploid(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent_rows, uint32_t map,
+                            const uint32_t* out_rows, const gsb200_draws* draws);
+/* gsc_generate_clone (core.c:8047-8055). */
+int  gsb200_clone(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent_rows, const uint32_t* out_rows);
+
+/* Device-pointer variants for callers that keep index arrays resident (benchmarks,
+ * multi-GPU generation loops).  PHILOX draws only.  Asynchronous on the context stream. */
+int  gsb200_cross_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1_rows, const uint32_t* d_parent2_rows,
+                      uint32_t map1, uint32_t map2, const uint32_t* d_out_rows, const gsb200_draws* draws);
+/* Synchronises and reports whether any gsb200_cross_dev batch since the last check drew more
+ * crossovers than its on-chip splice plan holds (probability < 1e-15 per gamete); such a batch
+ * must be redone with gsb200_cross, which falls back to the general kernel by itself. */
+int  gsb200_cross_dev_status(gsb200_ctx* ctx);
+
+/* The native RNG's draws for `n_units` x `gametes_per_unit` gametes of map `map`, in tape
+ * layout (for the KS tests against the reference's distributions).
+ * n_crossovers/start_strand: n_units*gametes_per_unit*n_chr entries; positions: capacity
+ * `positions_cap`, *n_positions receives the needed count. */
+int  gsb200_export_draws(gsb200_ctx* ctx, uint32_t map, uint64_t n_units, uint32_t gametes_per_unit,
+                         const gsb200_draws* philox, uint32_t* n_crossovers, uint8_t* start_strand,
+                         double* positions, uint64_t positions_cap, uint64_t* n_positions);
+
+/* ------------------------------------------------------------------ evaluation */
+
+/* gsc_calculate_utility_bvs (core.c:9566-9618): out[i] = sum_m sum_{a in marker m}
+ * count(a; row i, m) * eff(a, m)  -  sum_m centre[m].  fp64. */
+int  gsb200_gebv(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t eff_index, double* out);
+int  gsb200_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t eff_index, double* d_out);
+
+/* gsc_calculate_utility_local_bvs (core.c:9979-10090). Blocks (gsc_MarkerBlocks,
+ * core.h:515-528) as CSR: block b holds markers[offsets[b] .. offsets[b+1]).
+ * out is row-major (2n) x n_blocks: rows 2i, 2i+1 = haplotypes of rows[i]. */
+int  gsb200_local_gebv(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t n_blocks,
+                       const uint32_t* block_offsets, const uint32_t* block_markers,
+                       uint32_t eff_index, double* out);
+
+/* gsc_calculate_allele_counts (core.c:9636-9667). out is row-major n x n_markers. */
+enum { GSB200_COUNTS_F64 = 0, GSB200_COUNTS_I32 = 1, GSB200_COUNTS_U8 = 2 };
+int  gsb200_allele_counts(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, char allele,
+                          int out_kind, void* out);
+
+/* The ranking step of gsc_split_by_bv (core.c:9489-9508): positions (0..n-1) of the
+ * `top_n` best values, best first; ties broken by lower position (the reference leaves
+ * tie order undefined, core.c:1305-1306). */
+int  gsb200_top_n(gsb200_ctx* ctx, uint32_t n, const double* values, uint32_t top_n,
+                  int low_is_best, uint32_t* out_positions);
+
+/* ------------------------------------------------------------------ instrumentation */
+/* number of kernels launched by this context since creation */
+uint64_t gsb200_kernel_launches(const gsb200_ctx* ctx);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,145 @@
+/* gsb200_gsc.h — host-side mirror of genomicSimulation's C API for the hot path.
+ *
+ * Plain C over include/gsb200.h.  Each function keeps the name (gsc_ -> gsb_), argument order,
+ * argument meaning and soft-error behaviour (a "NOTE! ..." message and a 0 / empty return) of
+ * the reference function it stands in for in `src/sim-operations.c` ("core.c") /
+ * `src/sim-operations.h` ("core.h"), so that the r-wrappers.c entry points (SXP_make_random_crosses,
+ * SXP_see_group_data, ...) can call these instead.  What differs is where the
+ * genotype payload lives: gsc_AlleleMatrix's char[2M] per genotype (core.h:776-806) becomes a
+ * row of the device-resident bit-packed store; everything that is metadata (ids, pedigrees,
+ * group numbers, names, storage order = "global index") stays on the host, in the
+ * reference's order.
+ *
+ * Random draws.  The reference pulls every draw from R's stream in one interleaved order
+ * (core.c:8299-8332).  Two modes:
+ *   GSB_DRAWS_HOST    every draw — parent picks AND crossover counts/positions/strands — is
+ *                     pulled from the host draw source (gsb_set_draw_source: R's unif_rand /
+ *                     Rf_rpois in the package; a replay tape in the parity tests) in exactly
+ *                     the reference's order, then shipped to the GPU as a tape.  Results are
+ *                     bit-identical to the reference's for the same stream.
+ *   GSB_DRAWS_NATIVE  parent picks come from the host source (same order as the reference's
+ *                     picks); meiosis draws come from the device Philox stream keyed by
+ *                     (seed, call number) and indexed by offspring — nothing but row indexes
+ *                     crosses PCIe.
+ */
+#ifndef GSB200_GSC_H
+#define GSB200_GSC_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "gsb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef unsigned int gsb_GroupNum;   /* gsc_GroupNum.num  (core.h:557-560); 0 = GSC_NO_GROUP */
+typedef unsigned int gsb_MapID;      /* gsc_MapID.id; 0 = GSC_NO_MAP -> first map (core.c:8514-8520) */
+typedef unsigned int gsb_EffectID;   /* gsc_EffectID.id; 0 = GSC_NO_EFFECTSET */
+#define GSB_NA_GLOBALX ((unsigned int) -1)   /* GSC_NA_GLOBALX (core.h:160) */
+
+/* gsc_GenOptions (core.h:629-669), same fields in the same order. */
+typedef struct {
+    _Bool will_name_offspring;
+    const char* offspring_name_prefix;
+    unsigned int family_size;
+    _Bool will_track_pedigree;
+    _Bool will_allocate_ids;
+    const char* filename_prefix;
+    _Bool will_save_pedigree_to_file;
+    gsb_EffectID will_save_bvs_to_file;
+    _Bool will_save_alleles_to_file;
+    _Bool will_save_to_simdata;
+} gsb_GenOptions;
+extern const gsb_GenOptions GSB_BASIC_OPT;   /* GSC_BASIC_OPT (core.c:11-23) */
+
+/* gsc_DecimalMatrix (core.h:475-480) with flat row-major storage. Free with gsb_delete_dmatrix. */
+typedef struct {
+    unsigned int dim1, dim2;
+    double* data;
+} gsb_DecimalMatrix;
+
+/* gsc_MarkerBlocks (core.h:515-528) as CSR: block b = markers[offsets[b] .. offsets[b+1]). */
+typedef struct {
+    unsigned int num_blocks;
+    unsigned int* offsets;
+    unsigned int* markers;
+} gsb_MarkerBlocks;
+
+typedef struct gsb_SimData gsb_SimData;
+
+enum { GSB_DRAWS_HOST = 0, GSB_DRAWS_NATIVE = 1 };
+
+/* ---- lifetime (gsc_create_empty_simdata core.c:113-132, gsc_delete_simdata core.c:5047) */
+gsb_SimData* gsb_create_simdata(int device_ordinal, unsigned int n_markers);
+void gsb_delete_simdata(gsb_SimData* d);
+gsb200_ctx* gsb_context(gsb_SimData* d);
+/* status of the last call into the CUDA engine (GSB200_OK, ...) and its message */
+int gsb_last_status(const gsb_SimData* d);
+const char* gsb_last_message(const gsb_SimData* d);
+/* where "NOTE! ..." messages go (Rprintf in the package). NULL silences them. */
+void gsb_set_print(gsb_SimData* d, void (*print)(const char*));
+
+/* ---- draws */
+void gsb_set_draw_mode(gsb_SimData* d, int mode, uint64_t seed);
+/* unif must return values in the open interval (0,1); rpois must return 0 for mu <= 0 */
+void gsb_set_draw_source(gsb_SimData* d, double (*unif)(void), double (*rpois)(double));
+
+/* ---- setup: the payload side of gsc_load_data_files (core.c:7453-7496) */
+/* n genotypes, chars = n x 2M in the reference's layout; names may be NULL. New group. */
+gsb_GroupNum gsb_load_genotypes(gsb_SimData* d, unsigned int n, const char* chars, const char* const* names);
+gsb_MapID gsb_load_map(gsb_SimData* d, unsigned int n_chr, const double* expected_n_crossovers,
+                       const unsigned int* chr_offset, const double* dists, const unsigned int* marker_index,
+                       const unsigned char* has_dists);
+gsb_EffectID gsb_load_effects(gsb_SimData* d, const unsigned int* cumn_alleles, const char* allele,
+                              const double* eff, const double* centre);
+void gsb_delete_recombination_map(gsb_SimData* d, gsb_MapID which);   /* core.c:4768-4830 */
+void gsb_delete_eff_set(gsb_SimData* d, gsb_EffectID which);          /* core.c:4700-4752 */
+
+/* ---- data access (core.c:4190-4420) */
+unsigned int gsb_get_n_genotypes(const gsb_SimData* d);
+unsigned int gsb_get_current_id(const gsb_SimData* d);
+unsigned int gsb_get_group_size(const gsb_SimData* d, gsb_GroupNum group);
+/* storage-order export of a group (0 = everything); any output may be NULL. genotypes is
+ * cap x 2M chars. Returns the number of members written. */
+unsigned int gsb_get_group_data(gsb_SimData* d, gsb_GroupNum group, unsigned int cap, char* genotypes,
+                                unsigned int* ids, unsigned int* pedigree1, unsigned int* pedigree2,
+                                unsigned int* groups, unsigned int* global_indexes);
+const char* gsb_get_group_member_name(const gsb_SimData* d, gsb_GroupNum group, unsigned int i);
+gsb_GroupNum gsb_make_group_from(gsb_SimData* d, unsigned int n, const unsigned int* global_indexes); /* core.c:2810-2841 */
+void gsb_delete_group(gsb_SimData* d, gsb_GroupNum group);            /* core.c:4658-4692 */
+gsb_GroupNum gsb_combine_groups(gsb_SimData* d, unsigned int n, const gsb_GroupNum* groups);   /* core.c:2705-2742 */
+
+/* ---- crossing (core.c:8483-9212); same argument order as the reference */
+gsb_GroupNum gsb_make_random_crosses(gsb_SimData* d, gsb_GroupNum from_group, unsigned int n_crosses,
+                                     unsigned int cap, gsb_MapID which_map, gsb_GenOptions g);
+gsb_GroupNum gsb_make_random_crosses_between(gsb_SimData* d, gsb_GroupNum group1, gsb_GroupNum group2,
+                                             unsigned int n_crosses, unsigned int cap1, unsigned int cap2,
+                                             gsb_MapID map1, gsb_MapID map2, gsb_GenOptions g);
+gsb_GroupNum gsb_make_targeted_crosses(gsb_SimData* d, unsigned int n_combinations,
+                                       const unsigned int* first_parents, const unsigned int* second_parents,
+                                       gsb_MapID map1, gsb_MapID map2, gsb_GenOptions g);
+gsb_GroupNum gsb_self_n_times(gsb_SimData* d, unsigned int n, gsb_GroupNum group, gsb_MapID which_map, gsb_GenOptions g);
+gsb_GroupNum gsb_make_doubled_haploids(gsb_SimData* d, gsb_GroupNum group, gsb_MapID which_map, gsb_GenOptions g);
+gsb_GroupNum gsb_make_clones(gsb_SimData* d, gsb_GroupNum group, _Bool inherit_names, gsb_GenOptions g);
+gsb_GroupNum gsb_make_all_unidirectional_crosses(gsb_SimData* d, gsb_GroupNum from_group, gsb_MapID map, gsb_GenOptions g);
+
+/* ---- evaluation (core.c:9463-10090) */
+gsb_DecimalMatrix gsb_calculate_bvs(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID effID);
+gsb_DecimalMatrix gsb_calculate_allele_counts(gsb_SimData* d, gsb_GroupNum group, char allele);
+gsb_DecimalMatrix gsb_calculate_local_bvs(gsb_SimData* d, gsb_GroupNum group, gsb_MarkerBlocks b, gsb_EffectID effID);
+gsb_MarkerBlocks gsb_create_evenlength_blocks_each_chr(const gsb_SimData* d, gsb_MapID mapid, unsigned int n);
+gsb_GroupNum gsb_split_by_bv(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID effID, unsigned int top_n, _Bool lowIsBest);
+void gsb_delete_dmatrix(gsb_DecimalMatrix* m);          /* core.c:4628-4641 */
+void gsb_delete_markerblocks(gsb_MarkerBlocks* b);      /* core.c:4757-4766 */
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,251 @@
+"""Parity of the CUDA engine with the oracles, through the C-ABI (GPU only).
+
+Three-way plan of BASELINE.json's north_star:
+  1. crossover replay: engine and oracle consume the SAME draw tape -> genotypes, ids,
+     pedigrees, groups, allele counts must match bit for bit;
+  2. GEBV / local GEBV within 1e-9 relative in fp64 (tolerance written below);
+  3. the native Philox stream is KS-tested in tests/test_gpu_native.py.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import datasets, port, ref
+import scenarios
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-9          # north_star: "GEBVs must agree within 1e-9 relative in fp64"
+
+
+def load_json(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def oracle_draw_pointers():
+    L = port.lib()
+    return C.cast(L.gsdraw_unif, C.c_void_p), C.cast(L.gsdraw_rpois, C.c_void_p)
+
+
+def engine_from(ds):
+    from genomicsimulation_b200 import SimData
+    s = SimData.from_dataset(ds)
+    s.use_host_draws(*oracle_draw_pointers())
+    return s
+
+
+def bv_close(got, want, scale):
+    """|got - want| <= RTOL * max(|want|, scale): `scale` = typical |BV| of the set, so that a BV
+    that happens to cancel to ~0 is judged against the magnitude of what was summed."""
+    got, want = np.asarray(got), np.asarray(want)
+    tol = RTOL * np.maximum(np.abs(want), scale)
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), "max abs diff %g (tol %g)" % (np.abs(got - want).max(), tol.min())
+
+
+# ---------------------------------------------------------------- reference known answers
+
+@pytest.fixture(scope="module")
+def helper():
+    return load_json("helper.json")
+
+
+def test_helper_known_answers(helper):
+    """test-calculators.R:5-9, 43-76; test-printers.R:67-111; test-group-utils.R:206-217."""
+    ds = datasets.from_jsonable(helper["dataset"])
+    s = engine_from(ds)
+    np.testing.assert_allclose(s.calculate_bvs(1, 1), [1.4, 1.4, 1.6, -0.1, 0.6, -0.3], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(s.calculate_bvs(1, 2), [0.804, 0.804, 1.404, 2.502, -0.696, 1.902], rtol=RTOL, atol=1e-12)
+    b = s.blocks_evenlength(3, 1)
+    off, mk = b.export()
+    assert off.tolist() == helper["blockings"]["chrsplit3"]["offsets"]
+    assert mk.tolist() == helper["blockings"]["chrsplit3"]["markers"]
+    for name, blk in helper["blockings"].items():
+        for e in (0, 1):
+            got = s.calculate_local_bvs(1, blk["offsets"], blk["markers"], e + 1)
+            np.testing.assert_allclose(got, np.array(blk["local"][e]), rtol=RTOL, atol=1e-12, err_msg=name)
+    t = s.calculate_allele_counts(1, "T")
+    assert t.T.tolist() == [[2, 2, 2, 1, 2, 1], [0, 0, 0, 0, 2, 0], [2, 2, 1, 1, 2, 2]]
+    a = s.calculate_allele_counts(0, "A")
+    assert a.T.tolist() == [[0, 0, 0, 1, 0, 1], [2, 2, 2, 2, 0, 2], [0, 0, 1, 1, 0, 0]]
+    x = s.export_group(0)
+    np.testing.assert_array_equal(x["genotypes"], ds["genotypes"])      # pack -> unpack round trip
+    s.close()
+    for case in helper["selection"]:
+        s = engine_from(ds)
+        g = s.split_by_bv(1, 1, case["top_n"], case["low"])
+        assert s.group_indexes(g).tolist() == case["indexes"]
+        s.close()
+
+
+def test_helper_centred(helper):
+    ds = datasets.from_jsonable(helper["dataset"])
+    ds["effects"][0]["centre"] = np.array(helper["centred"]["centres"])
+    s = engine_from(ds)
+    np.testing.assert_allclose(s.calculate_bvs(1, 1), helper["centred"]["bvs"], rtol=RTOL, atol=1e-12)
+    b = s.blocks_evenlength(3, 1)
+    np.testing.assert_allclose(s.calculate_local_bvs(1, b, 1), np.array(helper["centred"]["local"]), rtol=RTOL, atol=1e-12)
+    s.close()
+
+
+# ---------------------------------------------------------------- crossover replay
+
+def test_scheme_replay_matches_reference_fixture():
+    """The engine, fed the tape the UNMODIFIED reference consumed (tests/golden/scheme.json, made by
+    tests/golden/make_golden.py), rebuilds the reference's genotypes, ids, pedigrees and groups."""
+    j = load_json("scheme.json")
+    ds = datasets.from_jsonable(j["dataset"])
+    tape = ref.Tape([float.fromhex(v) for v in j["tape_values"]], j["tape_kinds"]).draws_only()
+    s = engine_from(ds)
+    with port.Replay(tape) as rp:
+        groups = scenarios.crossing_scheme(s, j["founders"], small=True)
+    assert not rp.error and rp.consumed == len(tape)
+    assert groups == j["groups"]
+    st = scenarios.export_state(s)
+    for k in ("ids", "ped1", "ped2", "groups"):
+        assert st[k].tolist() == j["state"][k], k
+    np.testing.assert_array_equal(st["genotypes"], np.array(j["state"]["genotypes"], dtype=np.uint8))
+    bv_close(s.calculate_bvs(0, 1), j["bvs"], scale=np.abs(j["bvs"]).mean())
+    s.close()
+
+
+def replay_both(ds, seed, small=False):
+    """Oracle free-runs and records; the engine replays the same tape."""
+    p = port.PortSim.from_dataset(ds)
+    port.seed(seed)
+    port.record_start()
+    groups_p = scenarios.crossing_scheme(p, 1, small=small)
+    tape = port.record_stop().draws_only()
+    s = engine_from(ds)
+    with port.Replay(tape) as rp:
+        groups_s = scenarios.crossing_scheme(s, 1, small=small)
+    assert not rp.error and rp.consumed == len(tape)
+    assert groups_p == groups_s
+    return p, s, groups_p
+
+
+@pytest.mark.parametrize("shape", [(20, 1000, 3, 100.0, "even"), (30, 5000, 21, 150.0, "random"),
+                                   (12, 50000, 21, 150.0, "random"), (16, 257, 40, 80.0, "random")])
+def test_scheme_replay_matches_oracle(shape):
+    n, M, Cn, cm, spacing = shape
+    ds = datasets.synthetic(n, M, Cn, cm, seed=M + 7, spacing=spacing, n_effect_sets=2)
+    p, s, groups = replay_both(ds, seed=M + 1)
+    scenarios.assert_same_state(scenarios.export_state(p), scenarios.export_state(s))
+    want = p.calculate_bvs(0, 0)
+    bv_close(s.calculate_bvs(0, 1), want, scale=np.abs(want).mean())
+    want = p.calculate_bvs(groups[2], 1)
+    bv_close(s.calculate_bvs(groups[2], 2), want, scale=np.abs(want).mean())
+    off, mk = p.blocks_evenlength(4, 0, n_chr=Cn)
+    b = s.blocks_evenlength(4, 1)
+    off_s, mk_s = b.export()
+    np.testing.assert_array_equal(off, off_s)
+    np.testing.assert_array_equal(mk, mk_s)
+    want = p.calculate_local_bvs(groups[0], off, mk, 0)
+    got = s.calculate_local_bvs(groups[0], b, 1)
+    assert got.shape == want.shape
+    bv_close(got, want, scale=np.abs(want).mean())
+    np.testing.assert_array_equal(p.calculate_allele_counts(groups[2], "A"), s.calculate_allele_counts(groups[2], "A"))
+    # selection: same set, modulo ties at the cut (core.c:1305-1306)
+    gp = p.split_by_bv(groups[0], 0, 5, False)
+    gs = s.split_by_bv(groups[0], 1, 5, False)
+    assert sorted(p.group_indexes(gp).tolist()) == sorted(s.group_indexes(gs).tolist())
+    p.close()
+    s.close()
+
+
+def test_many_alleles_and_unknowns():
+    """More than two symbols per marker and '\\0' unknowns (core.c:75) widen the store to several planes."""
+    ds = datasets.synthetic(10, 700, 4, 90.0, seed=3, spacing="random", alleles=(b"A", b"C", b"G", b"T"),
+                            missing_rate=0.03)
+    p, s, groups = replay_both(ds, seed=11, small=True)
+    assert s.E.gsb200_store_planes(s.ctx) >= 2
+    scenarios.assert_same_state(scenarios.export_state(p), scenarios.export_state(s))
+    want = p.calculate_bvs(0, 0)
+    bv_close(s.calculate_bvs(0, 1), want, scale=np.abs(want).mean())
+    off, mk = p.blocks_evenlength(3, 0, n_chr=4)
+    want = p.calculate_local_bvs(groups[1], off, mk, 0)
+    bv_close(s.calculate_local_bvs(groups[1], off, mk, 1), want, scale=np.abs(want).mean() + 1e-300)
+    for a in ("A", "T", "\0"):
+        np.testing.assert_array_equal(p.calculate_allele_counts(0, a.encode()), s.calculate_allele_counts(0, a.encode()))
+    p.close()
+    s.close()
+
+
+def reorder_map(ds, seed):
+    """Same chromosomes, but each linkage group lists its markers through `marker_indexes`
+    in an order unrelated to storage order (GSC_LINKAGEGROUP_REORDER, core.c:7911-7921)."""
+    rng = np.random.default_rng(seed)
+    m = ds["maps"][0]
+    perm = rng.permutation(ds["n_markers"]).astype(np.uint32)
+    m2 = dict(m)
+    m2["marker_index"] = perm
+    ds2 = dict(ds)
+    ds2["maps"] = [m2]
+    return ds2
+
+
+def test_reorder_and_unlinked_maps():
+    """The general kernel: REORDER linkage groups, and the unlinked map of core.c:6128-6152
+    (one chromosome per marker, no dists, lambda 0)."""
+    ds = reorder_map(datasets.synthetic(9, 400, 5, 110.0, seed=21, spacing="random"), seed=5)
+    p, s, _ = replay_both(ds, seed=8, small=True)
+    scenarios.assert_same_state(scenarios.export_state(p), scenarios.export_state(s))
+    p.close(); s.close()
+
+    M = 300
+    ds = datasets.synthetic(8, M, 1, 100.0, seed=22)
+    ds["maps"] = [dict(lam=np.zeros(M), chr_offset=np.arange(M + 1, dtype=np.uint32), dists=np.full(M, np.nan),
+                       marker_index=np.arange(M, dtype=np.uint32), has_dists=np.zeros(M, dtype=np.uint8))]
+    p, s, _ = replay_both(ds, seed=9, small=True)
+    scenarios.assert_same_state(scenarios.export_state(p), scenarios.export_state(s))
+    p.close(); s.close()
+
+
+def test_degenerate_chromosomes():
+    """One-marker chromosomes have dists = 0/0 = NaN and never switch strand (core.c:5904, 5929);
+    clustered markers share a position."""
+    ds = datasets.synthetic(8, 64, 1, 100.0, seed=30)
+    sizes = [1, 1, 30, 1, 31]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    dists = np.zeros(64)
+    rng = np.random.default_rng(2)
+    for c, n in enumerate(sizes):
+        lo = off[c]
+        if n == 1:
+            dists[lo] = np.nan
+        else:
+            pos = np.sort(np.round(rng.uniform(0, 50, n), 0))      # many ties
+            dists[lo:lo + n] = (pos - pos[0]) / (pos[-1] - pos[0])
+    ds["maps"] = [dict(lam=np.array([0.0, 0.0, 2.5, 0.0, 3.0]), chr_offset=off, dists=dists,
+                       marker_index=np.arange(64, dtype=np.uint32), has_dists=np.ones(5, dtype=np.uint8))]
+    p, s, _ = replay_both(ds, seed=4, small=True)
+    scenarios.assert_same_state(scenarios.export_state(p), scenarios.export_state(s))
+    p.close(); s.close()
+
+
+def test_empty_and_invalid_requests():
+    ds = datasets.synthetic(6, 100, 2, 100.0, seed=1)
+    s = engine_from(ds)
+    assert s.make_random_crosses(99, 5) == 0                 # no such group
+    assert s.make_random_crosses(1, 0) == 0                  # n_crosses < 1
+    assert s.make_random_crosses(1, 50, 1) == 0              # cap too small
+    assert s.make_targeted_crosses([100, 0xFFFFFFFF], [0, 1]) == 0   # all pairs invalid
+    assert s.self_n_times(0, 1) == 0
+    assert s.make_doubled_haploids(1, 7) == 0                # no such map
+    assert s.calculate_bvs(1, 9).size == 0                   # no such effect set
+    assert s.n_genotypes == 6
+    g = s.make_random_crosses(1, 3, retain=False)            # retain = FALSE drops the offspring
+    assert g == 0 and s.n_genotypes == 6
+    # names and ids per 1000-genotype buffer (core.c:8168-8180)
+    g = s.make_random_crosses(1, 1203, name_offspring=True, name_prefix="x")
+    names = s.group_names(g)
+    ids = s.export_group(g, genotypes=False)["ids"]
+    assert names[0] == "x7" and names[1202] == "x1209" and ids.tolist() == list(range(7, 1210))
+    s.delete_group(1)
+    assert s.n_genotypes == 1203 and s.group_indexes(g).tolist() == list(range(1203))
+    s.close()
