@@ -15,6 +15,7 @@
 #include "gsb200_internal.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <cub/cub.cuh>
 
@@ -22,47 +23,78 @@ using namespace gsb;
 
 namespace {
 
-constexpr int kGebvThreads = 128;      // individuals per block (one per thread)
-constexpr int kGebvTile = 512;         // markers of delta staged in shared memory per step
-
 // ------------------------------------------------------------------ GEBV, one plane
-// Thread = individual, markers walked in order with delta broadcast from shared memory: no
-// divergence, no cross-lane reduction, delta read once per 128 individuals.
-__global__ void __launch_bounds__(kGebvThreads) gebv_plane1_kernel(
-        const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words, uint32_t n_markers,
-        const uint32_t* __restrict__ rows, uint32_t n, const double* __restrict__ delta,
-        double base, double* __restrict__ out) {
-    __shared__ double s_delta[kGebvTile];
-    const uint32_t i = blockIdx.x * kGebvThreads + threadIdx.x;
-    const bool live = i < n;
-    const uint32_t* row = store + (uint64_t) (live ? rows[i] : rows[0]) * row_words;
-    const uint4* h0 = reinterpret_cast<const uint4*>(row);
-    const uint4* h1 = reinterpret_cast<const uint4*>(row + plane_words);
-    double acc0 = 0.0, acc1 = 0.0;
-    for (uint32_t m0 = 0; m0 < n_markers; m0 += kGebvTile) {
-        __syncthreads();
-        for (uint32_t t = threadIdx.x; t < kGebvTile; t += kGebvThreads)
-            s_delta[t] = (m0 + t < n_markers) ? delta[m0 + t] : 0.0;
-        __syncthreads();
+// BV_i = base + sum_m delta_m * (bit0_im + bit1_im) is a {0,1}-matrix times a vector.  Walking it
+// marker by marker on the CUDA cores costs ~5 instructions (two of them FP64) per marker and
+// individual — 4x more issue slots than the 1/4 byte per marker the HBM stream delivers.  So the
+// product is done EXACTLY in integers on the tensor cores instead: delta_m is turned (on the
+// host, once per effect set) into a 62-bit fixed-point number split into 8 balanced base-256
+// digits, the digits are the 8 columns of the B operand of mma.m16n8k32 (u8 x s8 -> s32), the
+// genotype bits of 16 individuals x 32 markers — expanded to 0/1 bytes with one shift and one
+// AND per register, by choosing the k <-> marker permutation so that a register's four bytes
+// are bits 8 apart — are the A operand, and the eight int32 digit sums per individual are
+// recombined in fp64 at the end.  Integer accumulation is exact and order-free, so marker
+// segments can be summed with integer atomics and the result is still deterministic.
+constexpr int kGebvWarps = 4;                  // warps per block, 16 individuals each
+constexpr uint32_t kGebvMaxMarkers = 1u << 22; // 2 strands * M * 128 must stay below 2^31
+
+__device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// bfrag[w * 32 + lane] = the two B registers of `lane` for marker word w (see build_digit_fragments)
+__global__ void __launch_bounds__(kGebvWarps * 32) gebv_digits_kernel(
+        const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
+        const uint32_t* __restrict__ rows, uint32_t n, const uint2* __restrict__ bfrag,
+        uint32_t n_segments, uint32_t seg_len /* uint4 steps per segment */, int* __restrict__ digit_sums) {
+    const uint32_t warp_global = blockIdx.x * kGebvWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const uint32_t n_groups = (n + 15) / 16;
+    if (warp_global >= n_groups * n_segments) return;
+    const uint32_t group = warp_global % n_groups, seg = warp_global / n_groups;   // neighbours share B
+    const uint32_t g = lane >> 2, c = lane & 3;
+    const uint32_t ia = group * 16 + g, ib = ia + 8;
+    const uint32_t* ra = store + (uint64_t) rows[min(ia, n - 1)] * row_words;
+    const uint32_t* rb = store + (uint64_t) rows[min(ib, n - 1)] * row_words;
+    const uint32_t step_lo = seg * seg_len, step_hi = min(step_lo + seg_len, plane_words / 4);
+    int acc[4] = { 0, 0, 0, 0 };
+    constexpr uint32_t K = 0x01010101u;
 #pragma unroll 1
-        for (uint32_t q = 0; q < kGebvTile / 128; ++q) {
-            const uint32_t u = (m0 >> 7) + q;
-            if (u * 4 >= plane_words) break;
-            const uint4 a = __ldg(h0 + u), b = __ldg(h1 + u);
-            const uint32_t wa[4] = { a.x, a.y, a.z, a.w }, wb[4] = { b.x, b.y, b.z, b.w };
+    for (uint32_t st = step_lo; st < step_hi; ++st) {
+        const uint4 xa0 = __ldg(reinterpret_cast<const uint4*>(ra) + st);
+        const uint4 xb0 = __ldg(reinterpret_cast<const uint4*>(rb) + st);
+        const uint4 xa1 = __ldg(reinterpret_cast<const uint4*>(ra + plane_words) + st);
+        const uint4 xb1 = __ldg(reinterpret_cast<const uint4*>(rb + plane_words) + st);
+        const uint32_t wa0[4] = { xa0.x, xa0.y, xa0.z, xa0.w }, wb0[4] = { xb0.x, xb0.y, xb0.z, xb0.w };
+        const uint32_t wa1[4] = { xa1.x, xa1.y, xa1.z, xa1.w }, wb1[4] = { xb1.x, xb1.y, xb1.z, xb1.w };
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const uint32_t one = wa[w] ^ wb[w], two = wa[w] & wb[w];
-#pragma unroll
-                for (int bit = 0; bit < 32; ++bit) {
-                    const double d = s_delta[q * 128 + w * 32 + bit];
-                    if (one & (1u << bit)) acc0 += d;
-                    if (two & (1u << bit)) acc1 += d;
-                }
-            }
+        for (int k = 0; k < 4; ++k) {
+            const uint2 b = __ldg(bfrag + ((size_t) (st * 4 + k) * 32 + lane));
+            uint32_t ta = wa0[k] >> c, tb = wb0[k] >> c;
+            mma_u8s8(acc, ta & K, tb & K, (ta >> 4) & K, (tb >> 4) & K, b.x, b.y);
+            ta = wa1[k] >> c; tb = wb1[k] >> c;
+            mma_u8s8(acc, ta & K, tb & K, (ta >> 4) & K, (tb >> 4) & K, b.x, b.y);
         }
     }
-    if (live) out[i] = base + (acc0 + 2.0 * acc1);
+    // acc[0],acc[1]: individual ia, digits 2c, 2c+1;  acc[2],acc[3]: individual ib
+    if (ia < n) { atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c], acc[0]); atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c + 1], acc[1]); }
+    if (ib < n) { atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c], acc[2]); atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c + 1], acc[3]); }
+}
+
+// BV_i = offset + scale * sum_j digit_sums[i][j] * 256^j, most significant digit first
+__global__ void gebv_finish_kernel(const int* __restrict__ digit_sums, uint32_t n, double scale, double offset, double* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 lo = reinterpret_cast<const int4*>(digit_sums)[2 * (size_t) i], hi = reinterpret_cast<const int4*>(digit_sums)[2 * (size_t) i + 1];
+    double v = (double) hi.w;
+    v = v * 256.0 + (double) hi.z;
+    v = v * 256.0 + (double) hi.y;
+    v = v * 256.0 + (double) hi.x;
+    v = v * 256.0 + (double) lo.w;
+    v = v * 256.0 + (double) lo.z;
+    v = v * 256.0 + (double) lo.y;
+    v = v * 256.0 + (double) lo.x;
+    out[i] = offset + v * scale;
 }
 
 // ------------------------------------------------------------------ GEBV, any number of planes
@@ -210,6 +242,27 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
         }
         GSB_TRY(to_device_vec(delta, &e.d_delta));
         e.base_all = base;
+        // 62-bit fixed point, 8 balanced base-256 digits, in mma B-fragment order: lane = 4*digit + c
+        // holds, for marker word w, register `half` (0/1) whose byte j is the digit of marker
+        // 32*w + 8*j + c + 4*half — the k <-> marker permutation the kernel's A expansion uses.
+        double maxabs = 0.0;
+        for (uint32_t m = 0; m < M; ++m) maxabs = std::max(maxabs, std::fabs(delta[m]));
+        int exp2 = 0;
+        if (maxabs > 0.0 && std::isfinite(maxabs)) exp2 = 61 - std::ilogb(maxabs);
+        e.digit_scale = std::ldexp(1.0, -exp2);
+        const uint32_t words = ctx->plane_words;
+        std::vector<uint32_t> frag((size_t) words * 64, 0u);
+        for (uint32_t m = 0; m < M; ++m) {
+            long long q = std::isfinite(delta[m]) ? std::llrint(std::ldexp(delta[m], exp2)) : 0;
+            const uint32_t w = m >> 5, bit = m & 31, j = bit >> 3, sft = bit & 7, cc = sft & 3, half = sft >> 2;
+            for (uint32_t dg = 0; dg < 8; ++dg) {
+                const long long d8 = ((q + 128) & 255) - 128;
+                q = (q - d8) >> 8;
+                const uint32_t lane = 4 * dg + cc;
+                frag[((size_t) w * 32 + lane) * 2 + half] |= ((uint32_t) (uint8_t) (int8_t) d8) << (8 * j);
+            }
+        }
+        GSB_TRY(to_device_vec(frag, &e.d_digit_frag));
     }
     e.built_for_dict_version = ctx->dict_version;
     e.built_for_planes = planes;
@@ -224,10 +277,23 @@ int gebv_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t ef
     DeviceEffects* e;
     GSB_TRY(get_effects(ctx, eff_index, &e, what));
     const double centre_sum = e->has_centre ? e->centre_sum : 0.0;
-    if (ctx->planes == 1) {
-        gebv_plane1_kernel<<<(n + kGebvThreads - 1) / kGebvThreads, kGebvThreads, 0, ctx->stream>>>(
-            ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->n_markers, d_rows, n,
-            e->d_delta, e->base_all - centre_sum, d_out);
+    if (ctx->planes == 1 && ctx->n_markers <= kGebvMaxMarkers) {
+        GSB_TRY(ctx->s_eval[2].ensure((size_t) n * 8 * sizeof(int)));
+        int* d_digits = (int*) ctx->s_eval[2].ptr;
+        GSB_CUDA_TRY(cudaMemsetAsync(d_digits, 0, (size_t) n * 8 * sizeof(int), ctx->stream));
+        const uint32_t steps = ctx->plane_words / 4, n_groups = (n + 15) / 16;
+        // enough marker segments to fill the machine a few times over, at least 16 steps each
+        uint32_t n_segments = (uint32_t) std::min<uint64_t>(std::max<uint32_t>(steps / 16, 1),
+                                                            ((uint64_t) ctx->sm_count * 64 * 4 + n_groups - 1) / n_groups);
+        n_segments = std::max<uint32_t>(n_segments, 1);
+        const uint32_t seg_len = (steps + n_segments - 1) / n_segments;
+        n_segments = (steps + seg_len - 1) / seg_len;
+        const uint64_t warps = (uint64_t) n_groups * n_segments;
+        gebv_digits_kernel<<<(unsigned) ((warps + kGebvWarps - 1) / kGebvWarps), kGebvWarps * 32, 0, ctx->stream>>>(
+            ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, (const uint2*) e->d_digit_frag, n_segments, seg_len, d_digits);
+        ++ctx->launches;
+        GSB_CUDA_TRY(cudaGetLastError());
+        gebv_finish_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_digits, n, e->digit_scale, e->base_all - centre_sum, d_out);
     } else {
         const uint64_t threads = (uint64_t) n * 32;
         gebv_generic_kernel<<<(unsigned) ((threads + 127) / 128), 128, 0, ctx->stream>>>(

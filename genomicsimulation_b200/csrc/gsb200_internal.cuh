@@ -102,6 +102,8 @@ struct DeviceEffects {
     double* d_centre = nullptr;       // [M] or null
     double* d_delta = nullptr;        // planes == 1: value_all[m][1] - value_all[m][0]
     double  base_all = 0.0;           // planes == 1: sum_m 2 * value_all[m][0]
+    uint32_t* d_digit_frag = nullptr; // planes == 1: fixed-point digits of delta as mma B fragments
+    double  digit_scale = 1.0;        // value of one fixed-point unit
     void release();
 };
 

@@ -115,6 +115,11 @@ __device__ __forceinline__ uint4 draw_block(const DrawView& d, uint64_t unit, ui
     return philox4x32_10(ctr, d.key0, d.key1);
 }
 
+__constant__ double kInverse[32] = {
+    0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13,
+    1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25,
+    1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31 };
+
 // Poisson(lambda) by inversion of one uniform; p0 = exp(-lambda).
 __device__ __forceinline__ uint32_t poisson_inverse(double u, double lambda, double p0) {
     if (!(lambda > 0.0)) return 0;                 // Rf_rpois(0) == 0 (unlinked maps)
@@ -122,7 +127,7 @@ __device__ __forceinline__ uint32_t poisson_inverse(double u, double lambda, dou
     uint32_t k = 0;
     while (u > cdf && k < kMaxNativeCrossovers) {
         ++k;
-        p *= lambda / (double) k;
+        p *= k < 32 ? lambda * kInverse[k] : lambda / (double) k;
         cdf += p;
         if (p < 1e-300 && k > lambda) break;       // tail exhausted in fp64
     }
@@ -190,9 +195,16 @@ __device__ __forceinline__ void emit_toggle(uint32_t t, const MeiosisArgs& a, ui
     else overflow = 1;
 }
 
+// x << n with n in [0, 32]: PTX shl.b32 clamps shift amounts above 31, giving 0 at n = 32
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, int n) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
+
 __device__ __forceinline__ uint4 ldg128(const uint32_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-__global__ void __launch_bounds__(256) splice_flat_kernel(const MeiosisArgs a) {
+__global__ void __launch_bounds__(256, 4) splice_flat_kernel(const MeiosisArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* cnt = smem + (size_t) warp * a.warp_smem_words;
@@ -299,59 +311,67 @@ __global__ void __launch_bounds__(256) splice_flat_kernel(const MeiosisArgs a) {
         uint32_t* dst = a.dst_base + (uint64_t) dst_row * a.row_words;
         const uint32_t hap_stride = a.planes * a.plane_words;
 
-        for (uint32_t u0 = 0; u0 < a.n_u; u0 += 32 * kUnroll) {
-            uint4 mask[kUnroll];
+        // E1. pieces whose bin holds no toggle inherit one strand whole: a plain 128-bit copy
+        //     from the strand the parity of the toggles before the bin selects.
+        for (uint32_t p = 0; p < a.planes; ++p) {
+            const uint32_t* s0 = src + (uint64_t) p * a.plane_words;
+            uint32_t* out = dst + (uint64_t) (gam * a.planes + p) * a.plane_words;
+            for (uint32_t u0 = 0; u0 < a.n_u; u0 += 32 * kUnroll) {
+                uint4 v[kUnroll];
+                bool plain[kUnroll];
 #pragma unroll
-            for (int q = 0; q < kUnroll; ++q) {
-                const uint32_t u = u0 + q * 32 + lane;
-                uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-                if (u < a.n_u) {
-                    const uint32_t bin = u >> a.piece_shift;
-                    const uint32_t b = cnt[bin], e = cnt[bin + 1];
-                    m0 = m1 = m2 = m3 = (b & 1u) ? 0xffffffffu : 0u;
-                    if (e != b) {
-                        const uint32_t base = u << 7;
-                        for (uint32_t i = b; i < e; ++i) {
-                            const uint32_t t = grouped[i];
-                            if (t >= base + 128) continue;
-                            const uint32_t o = t > base ? t - base : 0;   // flip bits [o, 128)
-                            m0 ^= o < 32 ? (0xffffffffu << o) : 0u;
-                            m1 ^= o <= 32 ? 0xffffffffu : (o < 64 ? (0xffffffffu << (o - 32)) : 0u);
-                            m2 ^= o <= 64 ? 0xffffffffu : (o < 96 ? (0xffffffffu << (o - 64)) : 0u);
-                            m3 ^= o <= 96 ? 0xffffffffu : (0xffffffffu << (o - 96));
-                        }
+                for (int q = 0; q < kUnroll; ++q) {
+                    const uint32_t u = u0 + q * 32 + lane;
+                    plain[q] = false;
+                    if (u < a.n_u) {
+                        const uint32_t bin = u >> a.piece_shift;
+                        const uint32_t b = cnt[bin], e = cnt[bin + 1];
+                        plain[q] = (b == e);
+                        if (plain[q]) v[q] = ldg128(s0 + ((b & 1u) ? hap_stride : 0u) + 4 * u);
                     }
                 }
-                mask[q] = make_uint4(m0, m1, m2, m3);
+#pragma unroll
+                for (int q = 0; q < kUnroll; ++q) {
+                    if (plain[q]) {
+                        const uint32_t u = u0 + q * 32 + lane;
+                        *reinterpret_cast<uint4*>(out + 4 * u) = v[q];
+                        if (a.doubled) *reinterpret_cast<uint4*>(out + hap_stride + 4 * u) = v[q];
+                    }
+                }
             }
-            for (uint32_t p = 0; p < a.planes; ++p) {
-                const uint32_t* s0 = src + (uint64_t) p * a.plane_words;
-                const uint32_t* s1 = s0 + hap_stride;
-                uint4 h0[kUnroll], h1[kUnroll];
-#pragma unroll
-                for (int q = 0; q < kUnroll; ++q) {
-                    const uint32_t u = u0 + q * 32 + lane;
-                    const uint4 m = mask[q];
-                    h0[q] = h1[q] = make_uint4(0, 0, 0, 0);
-                    if (u < a.n_u) {
-                        if ((m.x & m.y & m.z & m.w) != 0xffffffffu) h0[q] = ldg128(s0 + 4 * u);
-                        if ((m.x | m.y | m.z | m.w) != 0u) h1[q] = ldg128(s1 + 4 * u);
-                    }
+        }
+        // E2. bins that hold toggles: the lane owning the bin's first toggle splices its pieces.
+        for (uint32_t i0 = 0; i0 < n_tog; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            if (i >= n_tog) continue;
+            const uint32_t bin = grouped[i] >> (7 + a.piece_shift);
+            const uint32_t b = cnt[bin], e = cnt[bin + 1];
+            if (b != i) continue;
+            const uint32_t u_end = min(a.n_u, (bin + 1) << a.piece_shift);
+            for (uint32_t u = bin << a.piece_shift; u < u_end; ++u) {
+                const uint32_t base = u << 7;
+                uint32_t m0, m1, m2, m3;
+                m0 = m1 = m2 = m3 = (b & 1u) ? 0xffffffffu : 0u;
+                for (uint32_t j = b; j < e; ++j) {
+                    const uint32_t t = grouped[j];
+                    if (t >= base + 128) continue;
+                    const int o = t > base ? (int) (t - base) : 0;      // flip bits [o, 128)
+                    m0 ^= shl_clamp(0xffffffffu, max(o, 0));
+                    m1 ^= shl_clamp(0xffffffffu, max(o - 32, 0));
+                    m2 ^= shl_clamp(0xffffffffu, max(o - 64, 0));
+                    m3 ^= shl_clamp(0xffffffffu, max(o - 96, 0));
                 }
-#pragma unroll
-                for (int q = 0; q < kUnroll; ++q) {
-                    const uint32_t u = u0 + q * 32 + lane;
-                    if (u < a.n_u) {
-                        const uint4 m = mask[q];
-                        uint4 r;
-                        r.x = (h0[q].x & ~m.x) | (h1[q].x & m.x);
-                        r.y = (h0[q].y & ~m.y) | (h1[q].y & m.y);
-                        r.z = (h0[q].z & ~m.z) | (h1[q].z & m.z);
-                        r.w = (h0[q].w & ~m.w) | (h1[q].w & m.w);
-                        uint32_t* out = dst + (uint64_t) (gam * a.planes + p) * a.plane_words + 4 * u;
-                        *reinterpret_cast<uint4*>(out) = r;
-                        if (a.doubled) *reinterpret_cast<uint4*>(out + hap_stride) = r;
-                    }
+                for (uint32_t p = 0; p < a.planes; ++p) {
+                    const uint32_t* s0 = src + (uint64_t) p * a.plane_words + 4 * u;
+                    const uint4 h0 = ldg128(s0), h1 = ldg128(s0 + hap_stride);
+                    uint4 r;
+                    r.x = (h0.x & ~m0) | (h1.x & m0);
+                    r.y = (h0.y & ~m1) | (h1.y & m1);
+                    r.z = (h0.z & ~m2) | (h1.z & m2);
+                    r.w = (h0.w & ~m3) | (h1.w & m3);
+                    uint32_t* out = dst + (uint64_t) (gam * a.planes + p) * a.plane_words + 4 * u;
+                    *reinterpret_cast<uint4*>(out) = r;
+                    if (a.doubled) *reinterpret_cast<uint4*>(out + hap_stride) = r;
                 }
             }
         }

@@ -245,7 +245,8 @@ def test_empty_and_invalid_requests():
     g = s.make_random_crosses(1, 1203, name_offspring=True, name_prefix="x")
     names = s.group_names(g)
     ids = s.export_group(g, genotypes=False)["ids"]
-    assert names[0] == "x7" and names[1202] == "x1209" and ids.tolist() == list(range(7, 1210))
+    # the retain=False cross above still consumed ids 7..9 (core.c:8174-8178 runs before the drop)
+    assert names[0] == "x10" and names[1202] == "x1212" and ids.tolist() == list(range(10, 1213))
     s.delete_group(1)
     assert s.n_genotypes == 1203 and s.group_indexes(g).tolist() == list(range(1203))
     s.close()
