@@ -79,11 +79,10 @@ struct MeiosisArgs {
     MapView map[2];
     DrawView draws;
     // fast-kernel plan geometry
-    uint32_t n_u;              // uint4 pieces per plane
-    uint32_t piece_shift;      // pieces per bin = 1 << piece_shift
-    uint32_t n_bins;
-    uint32_t cnt_words;        // >= n_bins + 1, multiple of 4
-    uint32_t xcap, tcap, list_words;
+    uint32_t n_u;              // 128-marker pieces (uint4) per plane
+    uint32_t parity_words;     // ceil(n_u / 32)
+    uint32_t chr_words;        // ceil(max n_chr / 32)
+    uint32_t xcap, tcap;       // crossovers / toggles one gamete's plan can hold
     uint32_t warp_smem_words;
     int* flag;
 };
@@ -183,17 +182,8 @@ __device__ __forceinline__ uint64_t entry_index(const DrawView& d, uint64_t unit
 
 // ------------------------------------------------------------------ fast kernel
 
-constexpr uint32_t kSlotBits = 6, kPosBits = 32 - kSlotBits;
 constexpr int kUnroll = 4;
-
-__device__ __forceinline__ void emit_toggle(uint32_t t, const MeiosisArgs& a, uint32_t* cnt, uint32_t* list, uint32_t* n_list,
-                                            uint32_t& overflow) {
-    if (t >= a.n_markers) return;                  // nothing lies beyond the last marker
-    const uint32_t slot = atomicAdd(&cnt[t >> (7 + a.piece_shift)], 1u);
-    const uint32_t idx = atomicAdd(n_list, 1u);
-    if (idx < a.tcap && slot < (1u << kSlotBits)) list[idx] = (slot << kPosBits) | t;
-    else overflow = 1;
-}
+constexpr uint32_t kNoToggle = 0xffffffffu;
 
 // x << n with n in [0, 32]: PTX shl.b32 clamps shift amounts above 31, giving 0 at n = 32
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t x, int n) {
@@ -204,43 +194,60 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t x, int n) {
 
 __device__ __forceinline__ uint4 ldg128(const uint32_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+// Append the toggles the lanes hold (kNoToggle = none) to the warp's list, and flip the parity
+// bit of the 128-marker piece each one falls in.
+__device__ __forceinline__ void emit_toggles(uint32_t t, uint32_t lane, const MeiosisArgs& a, uint32_t* piece_parity,
+                                             uint32_t* list, uint32_t& n_list) {
+    const bool has = t < a.n_markers;              // nothing lies beyond the last marker
+    const uint32_t ballot = __ballot_sync(0xffffffffu, has);
+    if (has) {
+        const uint32_t idx = n_list + __popc(ballot & ((1u << lane) - 1u));
+        if (idx < a.tcap) list[idx] = t;
+        atomicXor(&piece_parity[t >> 12], 1u << ((t >> 7) & 31));
+    }
+    n_list += __popc(ballot);
+}
+
+// One warp per gamete.  Shared memory per warp:
+//   piece_parity[n_u/32 + 1]  bit u: parity of the toggles inside piece u, then (after the scan)
+//                             parity of the toggles BEFORE piece u = the strand piece u starts on
+//   chr_flip[n_chr/32 + 1]    bit c: parity of the crossovers that take effect in chromosome c
+//   chr_start[n_chr/32 + 1]   bit c: start strand of chromosome c
+//   list[tcap]                the toggles (marker positions), unordered
+//   xinfo[xcap]               crossover -> (chromosome, index within chromosome)
 __global__ void __launch_bounds__(256, 4) splice_flat_kernel(const MeiosisArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* cnt = smem + (size_t) warp * a.warp_smem_words;
-    uint32_t* list = cnt + a.cnt_words;            // toggles as emitted: slot << 26 | marker
-    uint32_t* grouped = list + a.tcap;             // toggles binned (aliases xinfo: dead by then)
-    uint2* xinfo = reinterpret_cast<uint2*>(grouped);   // crossover -> (chromosome, index in chromosome)
-    uint32_t* n_list = grouped + a.list_words;
+    uint2* xinfo = reinterpret_cast<uint2*>(smem + (size_t) warp * a.warp_smem_words);
+    uint32_t* list = reinterpret_cast<uint32_t*>(xinfo + a.xcap);
+    uint32_t* piece_parity = list + a.tcap;
+    uint32_t* chr_flip = piece_parity + a.parity_words;
+    uint32_t* chr_start = chr_flip + a.chr_words;
 
-    const uint64_t n_gametes = (uint64_t) a.n_units * a.gametes_per_unit;
-    for (uint64_t g = (uint64_t) blockIdx.x * warps + warp; g < n_gametes; g += (uint64_t) gridDim.x * warps) {
-        const uint32_t unit_local = (uint32_t) (g / a.gametes_per_unit);
-        const uint32_t gam = (uint32_t) (g % a.gametes_per_unit);
+    const uint32_t n_gametes = a.n_units * a.gametes_per_unit;      // host keeps this below 2^32
+    for (uint32_t g = blockIdx.x * warps + warp; g < n_gametes; g += gridDim.x * warps) {
+        const uint32_t unit_local = a.gametes_per_unit == 2 ? g >> 1 : g;
+        const uint32_t gam = a.gametes_per_unit == 2 ? g & 1u : 0u;
         const uint64_t unit = a.draws.first_unit + unit_local;
         const MapView& mv = a.map[gam];
+        const uint64_t entry0 = (uint64_t) unit_local * a.draws.unit_stride + a.draws.base_offset + (gam ? a.map[0].n_chr : 0);
 
-        // A. clear the bins
-        for (uint32_t i = lane * 4; i < a.cnt_words; i += 128) *reinterpret_cast<uint4*>(cnt + i) = make_uint4(0, 0, 0, 0);
-        if (lane == 0) *n_list = 0;
+        for (uint32_t i = lane; i < a.parity_words + 2 * a.chr_words; i += 32) piece_parity[i] = 0;
         __syncwarp();
 
         // B. lane per chromosome: crossover count and start strand
-        uint32_t overflow = 0, n_x = 0;
+        uint32_t n_x = 0;
         for (uint32_t c0 = 0; c0 < mv.n_chr; c0 += 32) {
             const uint32_t c = c0 + lane;
-            uint32_t k = 0;
+            uint32_t k = 0, strand = 0;
             if (c < mv.n_chr) {
                 const ChrInfo ci = mv.chr[c];
-                uint32_t strand;
-                draw_header(a.draws, ci, unit, gam, c, entry_index(a.draws, unit_local, gam, a.map[0].n_chr, c), k, strand);
-                if (ci.len == 0) { k = 0; strand = 0; }
-                if (strand) {
-                    emit_toggle(ci.first, a, cnt, list, n_list, overflow);
-                    emit_toggle(ci.first + ci.len, a, cnt, list, n_list, overflow);
-                }
-                if (!ci.searchable) k = 0;         // the positions are drawn but can never be passed
+                draw_header(a.draws, ci, unit, gam, c, entry0 + c, k, strand);
+                if (ci.len == 0) strand = 0;
+                if (ci.len == 0 || !ci.searchable) k = 0;   // such positions are drawn but can never be passed
             }
+            const uint32_t sb = __ballot_sync(0xffffffffu, strand != 0);
+            if (lane == 0) chr_start[c0 >> 5] = sb;
             uint32_t incl = k;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -252,58 +259,71 @@ __global__ void __launch_bounds__(256, 4) splice_flat_kernel(const MeiosisArgs a
                 if (off + j < a.xcap) xinfo[off + j] = make_uint2(c, j);
             n_x += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (n_x > a.xcap) overflow = 1;
         __syncwarp();
-
-        // C. lane per crossover: position -> marker where the strand flips
-        if (n_x <= a.xcap) {
-            for (uint32_t i0 = 0; i0 < n_x; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                uint32_t t0 = 0xffffffffu, t1 = 0xffffffffu;
-                if (i < n_x) {
-                    const uint2 xi = xinfo[i];
-                    const ChrInfo ci = mv.chr[xi.x];
-                    const double x = draw_position(a.draws, unit, gam, xi.x,
-                                                   entry_index(a.draws, unit_local, gam, a.map[0].n_chr, xi.x), xi.y);
-                    const uint32_t ub = first_marker_past(ci, mv, x);
-                    if (ub < ci.len) { t0 = ci.first + ub; t1 = ci.first + ci.len; }
-                }
-                emit_toggle(t0, a, cnt, list, n_list, overflow);
-                emit_toggle(t1, a, cnt, list, n_list, overflow);
-            }
-        }
-        overflow = __any_sync(0xffffffffu, overflow);
-        __syncwarp();
-        if (overflow) {                            // host re-runs the batch on the general kernel
+        if (n_x > a.xcap) {                        // host re-runs the batch on the general kernel
             if (lane == 0) atomicExch(a.flag, 1);
             continue;
         }
 
-        // D. exclusive prefix sum of the bins -> bin b holds grouped[cnt[b] .. cnt[b+1])
-        {
-            const uint32_t n_scan = a.n_bins + 1;
-            const uint32_t per = (n_scan + 31) / 32;
-            const uint32_t lo = min(lane * per, n_scan), hi = min(lo + per, n_scan);
-            uint32_t sum = 0;
-            for (uint32_t i = lo; i < hi; ++i) sum += cnt[i];
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((int) lane >= o) incl += v;
+        // C. lane per crossover: position -> the marker from which the strand is flipped
+        uint32_t n_list = 0;
+        for (uint32_t i0 = 0; i0 < n_x; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t t = kNoToggle;
+            if (i < n_x) {
+                const uint2 xi = xinfo[i];
+                const ChrInfo ci = mv.chr[xi.x];
+                const double x = draw_position(a.draws, unit, gam, xi.x, entry0 + xi.x, xi.y);
+                const uint32_t ub = first_marker_past(ci, mv, x);
+                if (ub < ci.len) {
+                    t = ci.first + ub;
+                    atomicXor(&chr_flip[xi.x >> 5], 1u << (xi.x & 31));
+                }
             }
-            uint32_t run = incl - sum;
-            for (uint32_t i = lo; i < hi; ++i) { const uint32_t v = cnt[i]; cnt[i] = run; run += v; }
+            emit_toggles(t, lane, a, piece_parity, list, n_list);
         }
         __syncwarp();
-        const uint32_t n_tog = *n_list;
-        for (uint32_t i = lane; i < n_tog; i += 32) {
-            const uint32_t e = list[i], t = e & ((1u << kPosBits) - 1);
-            grouped[cnt[t >> (7 + a.piece_shift)] + (e >> kPosBits)] = t;
+        // chromosome boundaries: enter on the start strand, leave back on strand 0
+        for (uint32_t c0 = 0; c0 < mv.n_chr; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            uint32_t t_in = kNoToggle, t_out = kNoToggle;
+            if (c < mv.n_chr) {
+                const uint32_t s_c = (chr_start[c0 >> 5] >> lane) & 1u;
+                const uint32_t e_c = s_c ^ ((chr_flip[c0 >> 5] >> lane) & 1u);
+                const ChrInfo ci = mv.chr[c];
+                if (s_c) t_in = ci.first;
+                if (e_c) t_out = ci.first + ci.len;
+            }
+            emit_toggles(t_in, lane, a, piece_parity, list, n_list);
+            emit_toggles(t_out, lane, a, piece_parity, list, n_list);
+        }
+        __syncwarp();
+        if (n_list > a.tcap) {
+            if (lane == 0) atomicExch(a.flag, 1);
+            continue;
+        }
+
+        // D. exclusive prefix XOR over the piece parities: bit u = strand piece u starts on
+        {
+            uint32_t carry = 0;
+            for (uint32_t w0 = 0; w0 < a.parity_words; w0 += 32) {
+                const uint32_t w = w0 + lane;
+                uint32_t x = w < a.parity_words ? piece_parity[w] : 0u;
+                uint32_t incl = x;
+                incl ^= incl << 1; incl ^= incl << 2; incl ^= incl << 4; incl ^= incl << 8; incl ^= incl << 16;
+                uint32_t word_par = incl >> 31, pre = word_par;      // parity of the whole word
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, pre, o);
+                    if ((int) lane >= o) pre ^= v;
+                }
+                const uint32_t before = carry ^ pre ^ word_par;      // parity of all earlier words
+                if (w < a.parity_words) piece_parity[w] = (incl << 1) ^ (before ? 0xffffffffu : 0u);
+                carry ^= __shfl_sync(0xffffffffu, pre, 31);
+            }
         }
         __syncwarp();
 
-        // E. stream the plane(s)
         const uint32_t src_row = gam ? (a.src_rows1 ? a.src_rows1[unit_local] : unit_local)
                                      : (a.src_rows0 ? a.src_rows0[unit_local] : unit_local);
         const uint32_t dst_row = a.dst_rows ? a.dst_rows[unit_local] : unit_local;
@@ -311,67 +331,54 @@ __global__ void __launch_bounds__(256, 4) splice_flat_kernel(const MeiosisArgs a
         uint32_t* dst = a.dst_base + (uint64_t) dst_row * a.row_words;
         const uint32_t hap_stride = a.planes * a.plane_words;
 
-        // E1. pieces whose bin holds no toggle inherit one strand whole: a plain 128-bit copy
-        //     from the strand the parity of the toggles before the bin selects.
+        // E1. every piece, whole, from the strand it starts on: plain 128-bit copies
         for (uint32_t p = 0; p < a.planes; ++p) {
-            const uint32_t* s0 = src + (uint64_t) p * a.plane_words;
-            uint32_t* out = dst + (uint64_t) (gam * a.planes + p) * a.plane_words;
+            const uint32_t* s0 = src + p * a.plane_words;
+            uint32_t* out = dst + (gam * a.planes + p) * a.plane_words;
             for (uint32_t u0 = 0; u0 < a.n_u; u0 += 32 * kUnroll) {
                 uint4 v[kUnroll];
-                bool plain[kUnroll];
 #pragma unroll
                 for (int q = 0; q < kUnroll; ++q) {
                     const uint32_t u = u0 + q * 32 + lane;
-                    plain[q] = false;
                     if (u < a.n_u) {
-                        const uint32_t bin = u >> a.piece_shift;
-                        const uint32_t b = cnt[bin], e = cnt[bin + 1];
-                        plain[q] = (b == e);
-                        if (plain[q]) v[q] = ldg128(s0 + ((b & 1u) ? hap_stride : 0u) + 4 * u);
+                        const uint32_t on1 = (piece_parity[(u0 >> 5) + q] >> lane) & 1u;
+                        v[q] = ldg128(s0 + (on1 ? hap_stride : 0u) + 4 * u);
                     }
                 }
 #pragma unroll
                 for (int q = 0; q < kUnroll; ++q) {
-                    if (plain[q]) {
-                        const uint32_t u = u0 + q * 32 + lane;
+                    const uint32_t u = u0 + q * 32 + lane;
+                    if (u < a.n_u) {
                         *reinterpret_cast<uint4*>(out + 4 * u) = v[q];
                         if (a.doubled) *reinterpret_cast<uint4*>(out + hap_stride + 4 * u) = v[q];
                     }
                 }
             }
         }
-        // E2. bins that hold toggles: the lane owning the bin's first toggle splices its pieces.
-        for (uint32_t i0 = 0; i0 < n_tog; i0 += 32) {
+        __syncwarp();      // orders the plain stores before the fix-ups below (same warp)
+
+        // E2. lane per toggle: flipping the strand from bit o of its piece on means XOR-ing
+        //     (strand0 ^ strand1) & (ones from bit o) into what E1 wrote; XOR fix-ups of several
+        //     toggles in one piece commute, so they are applied with 64-bit atomic XORs.
+        for (uint32_t i0 = 0; i0 < n_list; i0 += 32) {
             const uint32_t i = i0 + lane;
-            if (i >= n_tog) continue;
-            const uint32_t bin = grouped[i] >> (7 + a.piece_shift);
-            const uint32_t b = cnt[bin], e = cnt[bin + 1];
-            if (b != i) continue;
-            const uint32_t u_end = min(a.n_u, (bin + 1) << a.piece_shift);
-            for (uint32_t u = bin << a.piece_shift; u < u_end; ++u) {
-                const uint32_t base = u << 7;
-                uint32_t m0, m1, m2, m3;
-                m0 = m1 = m2 = m3 = (b & 1u) ? 0xffffffffu : 0u;
-                for (uint32_t j = b; j < e; ++j) {
-                    const uint32_t t = grouped[j];
-                    if (t >= base + 128) continue;
-                    const int o = t > base ? (int) (t - base) : 0;      // flip bits [o, 128)
-                    m0 ^= shl_clamp(0xffffffffu, max(o, 0));
-                    m1 ^= shl_clamp(0xffffffffu, max(o - 32, 0));
-                    m2 ^= shl_clamp(0xffffffffu, max(o - 64, 0));
-                    m3 ^= shl_clamp(0xffffffffu, max(o - 96, 0));
-                }
-                for (uint32_t p = 0; p < a.planes; ++p) {
-                    const uint32_t* s0 = src + (uint64_t) p * a.plane_words + 4 * u;
-                    const uint4 h0 = ldg128(s0), h1 = ldg128(s0 + hap_stride);
-                    uint4 r;
-                    r.x = (h0.x & ~m0) | (h1.x & m0);
-                    r.y = (h0.y & ~m1) | (h1.y & m1);
-                    r.z = (h0.z & ~m2) | (h1.z & m2);
-                    r.w = (h0.w & ~m3) | (h1.w & m3);
-                    uint32_t* out = dst + (uint64_t) (gam * a.planes + p) * a.plane_words + 4 * u;
-                    *reinterpret_cast<uint4*>(out) = r;
-                    if (a.doubled) *reinterpret_cast<uint4*>(out + hap_stride) = r;
+            if (i >= n_list) continue;
+            const uint32_t t = list[i], u = t >> 7;
+            const int o = (int) (t & 127u);
+            const uint32_t m0 = shl_clamp(0xffffffffu, o), m1 = shl_clamp(0xffffffffu, max(o - 32, 0));
+            const uint32_t m2 = shl_clamp(0xffffffffu, max(o - 64, 0)), m3 = shl_clamp(0xffffffffu, max(o - 96, 0));
+            for (uint32_t p = 0; p < a.planes; ++p) {
+                const uint32_t* s0 = src + p * a.plane_words + 4 * u;
+                const uint4 h0 = ldg128(s0), h1 = ldg128(s0 + hap_stride);
+                const unsigned long long lo = ((unsigned long long) ((h0.y ^ h1.y) & m1) << 32) | ((h0.x ^ h1.x) & m0);
+                const unsigned long long hi = ((unsigned long long) ((h0.w ^ h1.w) & m3) << 32) | ((h0.z ^ h1.z) & m2);
+                unsigned long long* out = reinterpret_cast<unsigned long long*>(dst + (gam * a.planes + p) * a.plane_words + 4 * u);
+                if (lo) atomicXor(out, lo);
+                if (hi) atomicXor(out + 1, hi);
+                if (a.doubled) {
+                    unsigned long long* out2 = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint32_t*>(out) + hap_stride);
+                    if (lo) atomicXor(out2, lo);
+                    if (hi) atomicXor(out2 + 1, hi);
                 }
             }
         }
@@ -625,24 +632,21 @@ int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
     // plan geometry of the fast kernel
     bool fast = maps[0]->flat && maps[1]->flat;
     a.n_u = ctx->plane_words / 4;
-    a.piece_shift = 0;
-    while ((a.n_u >> a.piece_shift) > 2040) ++a.piece_shift;
-    a.n_bins = (a.n_u + (1u << a.piece_shift) - 1) >> a.piece_shift;
-    a.cnt_words = (a.n_bins + 1 + 3) / 4 * 4;
-    uint32_t xcap, n_chr_max = std::max(maps[0]->n_chr, maps[1]->n_chr);
+    a.parity_words = (a.n_u + 31) / 32;
+    const uint32_t n_chr_max = std::max(maps[0]->n_chr, maps[1]->n_chr);
+    a.chr_words = (n_chr_max + 31) / 32;
+    uint32_t xcap;
     if (b.draws.mode == GSB200_DRAWS_TAPE) {
         xcap = b.tape_xcap;
     } else {
         const double ls = std::max(maps[0]->lambda_sum, maps[1]->lambda_sum);
         xcap = (uint32_t) std::ceil(ls + 8.0 * std::sqrt(ls) + 16.0);
-        if (std::max(maps[0]->lambda_max, maps[1]->lambda_max) > 16.0) fast = false;   // slot field of a toggle
     }
     xcap = std::max<uint32_t>((xcap + 31) / 32 * 32, 32);
     a.xcap = xcap;
-    a.tcap = 2 * xcap + 2 * n_chr_max;
-    a.list_words = std::max(a.tcap, 2 * xcap);
-    a.warp_smem_words = (a.cnt_words + a.tcap + a.list_words + 4 + 3) / 4 * 4;
-    if (ctx->n_markers >= (1u << kPosBits)) fast = false;
+    a.tcap = (xcap + 2 * n_chr_max + 1) / 2 * 2;
+    a.warp_smem_words = (a.parity_words + 2 * a.chr_words + a.tcap + 2 * a.xcap + 3) / 4 * 4;
+    if ((uint64_t) b.n_units * b.gametes_per_unit >= (1ull << 32)) fast = false;
     uint32_t warps = 8;
     const size_t smem_limit = 200 * 1024;
     while (warps > 1 && (size_t) warps * a.warp_smem_words * 4 > smem_limit / 2) warps >>= 1;
