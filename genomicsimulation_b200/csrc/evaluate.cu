@@ -36,64 +36,109 @@ namespace {
 // recombined in fp64 at the end.  Integer accumulation is exact and order-free, so marker
 // segments can be summed with integer atomics and the result is still deterministic.
 constexpr int kGebvWarps = 4;                  // warps per block, 16 individuals each
-constexpr uint32_t kGebvMaxMarkers = 1u << 22; // 2 strands * M * 128 must stay below 2^31
+constexpr uint32_t kGebvMaxMarkers = 1u << 26;
+constexpr uint32_t kChunkWords = 32;           // 1024 markers = 8 mma tiles of 128 = one 128-byte line per strand
+constexpr uint32_t kRowStride = 36;            // words: 128 B + 16 B pad -> the 8 row reads of an LDS.128 hit 32 distinct banks
+constexpr uint32_t kBufWords = 32 * kRowStride;   // 16 individuals x 2 strands
+constexpr uint32_t kGebvMaxSegChunks = 32;     // 32768 markers * 2 strands * 128 * 128 < 2^31
 
 __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// bfrag[w * 32 + lane] = the two B registers of `lane` for marker word w (see build_digit_fragments)
+__device__ __forceinline__ void cp_async16(uint32_t* smem_dst, const uint32_t* gmem_src) {
+    const uint32_t d = (uint32_t) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// One warp = 16 individuals x one segment of marker chunks.  The warp streams its 32 strand rows
+// through shared memory with 16-byte cp.async (each row contributes one full 128-byte line per
+// chunk, so global reads are whole lines), double-buffered; lanes then pick their mma A words
+// with conflict-free LDS.128.  A byte is `word & (0x01010101 << s)`: bit 8j+s of the word,
+// left at weight 2^s (s = c for register a0/a1, c+4 for a2/a3) — one LOP3 per register; the
+// weight is divided out of the digits on the host (ensure_effect_tables).
+// bfrag[(w * 32 + lane)] = the two B registers of `lane` for marker word w.
 __global__ void __launch_bounds__(kGebvWarps * 32) gebv_digits_kernel(
         const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
         const uint32_t* __restrict__ rows, uint32_t n, const uint2* __restrict__ bfrag,
-        uint32_t n_segments, uint32_t seg_len /* uint4 steps per segment */, int* __restrict__ digit_sums) {
-    const uint32_t warp_global = blockIdx.x * kGebvWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+        uint32_t n_segments, uint32_t seg_chunks, unsigned long long* __restrict__ digit_sums) {
+    __shared__ __align__(16) uint32_t s_buf[kGebvWarps][2][kBufWords];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp_global = blockIdx.x * kGebvWarps + warp;
     const uint32_t n_groups = (n + 15) / 16;
     if (warp_global >= n_groups * n_segments) return;
     const uint32_t group = warp_global % n_groups, seg = warp_global / n_groups;   // neighbours share B
     const uint32_t g = lane >> 2, c = lane & 3;
-    const uint32_t ia = group * 16 + g, ib = ia + 8;
-    const uint32_t* ra = store + (uint64_t) rows[min(ia, n - 1)] * row_words;
-    const uint32_t* rb = store + (uint64_t) rows[min(ib, n - 1)] * row_words;
-    const uint32_t step_lo = seg * seg_len, step_hi = min(step_lo + seg_len, plane_words / 4);
-    int acc[4] = { 0, 0, 0, 0 };
-    constexpr uint32_t K = 0x01010101u;
-#pragma unroll 1
-    for (uint32_t st = step_lo; st < step_hi; ++st) {
-        const uint4 xa0 = __ldg(reinterpret_cast<const uint4*>(ra) + st);
-        const uint4 xb0 = __ldg(reinterpret_cast<const uint4*>(rb) + st);
-        const uint4 xa1 = __ldg(reinterpret_cast<const uint4*>(ra + plane_words) + st);
-        const uint4 xb1 = __ldg(reinterpret_cast<const uint4*>(rb + plane_words) + st);
-        const uint32_t wa0[4] = { xa0.x, xa0.y, xa0.z, xa0.w }, wb0[4] = { xb0.x, xb0.y, xb0.z, xb0.w };
-        const uint32_t wa1[4] = { xa1.x, xa1.y, xa1.z, xa1.w }, wb1[4] = { xb1.x, xb1.y, xb1.z, xb1.w };
+    const uint32_t ch_lo = seg * seg_chunks, ch_hi = min(ch_lo + seg_chunks, plane_words / kChunkWords);
+    if (ch_lo >= ch_hi) return;
+
+    // staging role: copy `it` moves 16 bytes of strand row r = it*4 + lane/8 (individual r & 15, strand r >> 4)
+    const uint32_t my_row = rows[min(group * 16 + (lane & 15), n - 1)];
+    const uint32_t* stage_src[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint2 b = __ldg(bfrag + ((size_t) (st * 4 + k) * 32 + lane));
-            uint32_t ta = wa0[k] >> c, tb = wb0[k] >> c;
-            mma_u8s8(acc, ta & K, tb & K, (ta >> 4) & K, (tb >> 4) & K, b.x, b.y);
-            ta = wa1[k] >> c; tb = wb1[k] >> c;
-            mma_u8s8(acc, ta & K, tb & K, (ta >> 4) & K, (tb >> 4) & K, b.x, b.y);
+    for (int it = 0; it < 8; ++it) {
+        const uint32_t r = it * 4 + (lane >> 3);
+        const uint32_t row = __shfl_sync(0xffffffffu, my_row, r & 15);
+        stage_src[it] = store + (uint64_t) row * row_words + (r >> 4) * plane_words + (lane & 7) * 4;
+    }
+    auto stage = [&](uint32_t ch, uint32_t* buf) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+            cp_async16(buf + (it * 4 + (lane >> 3)) * kRowStride + (lane & 7) * 4, stage_src[it] + (size_t) ch * kChunkWords);
+        cp_async_commit();
+    };
+
+    const uint32_t k_lo = 0x01010101u << c, k_hi = k_lo << 4;
+    int acc0[4] = { 0, 0, 0, 0 }, acc1[4] = { 0, 0, 0, 0 };
+    stage(ch_lo, s_buf[warp][0]);
+    for (uint32_t ch = ch_lo; ch < ch_hi; ++ch) {
+        const uint32_t* buf = s_buf[warp][(ch - ch_lo) & 1];
+        if (ch + 1 < ch_hi) { stage(ch + 1, s_buf[warp][(ch - ch_lo + 1) & 1]); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp();
+        const uint2* f = bfrag + (size_t) ch * (kChunkWords * 32) + lane;
+#pragma unroll 2
+        for (uint32_t t = 0; t < 8; ++t) {
+            const uint4 xa0 = *reinterpret_cast<const uint4*>(buf + g * kRowStride + t * 4);
+            const uint4 xb0 = *reinterpret_cast<const uint4*>(buf + (g + 8) * kRowStride + t * 4);
+            const uint4 xa1 = *reinterpret_cast<const uint4*>(buf + (16 + g) * kRowStride + t * 4);
+            const uint4 xb1 = *reinterpret_cast<const uint4*>(buf + (24 + g) * kRowStride + t * 4);
+            const uint2 f0 = __ldg(f + (t * 4 + 0) * 32), f1 = __ldg(f + (t * 4 + 1) * 32);
+            const uint2 f2 = __ldg(f + (t * 4 + 2) * 32), f3 = __ldg(f + (t * 4 + 3) * 32);
+            mma_u8s8(acc0, xa0.x & k_lo, xb0.x & k_lo, xa0.x & k_hi, xb0.x & k_hi, f0.x, f0.y);
+            mma_u8s8(acc1, xa1.x & k_lo, xb1.x & k_lo, xa1.x & k_hi, xb1.x & k_hi, f0.x, f0.y);
+            mma_u8s8(acc0, xa0.y & k_lo, xb0.y & k_lo, xa0.y & k_hi, xb0.y & k_hi, f1.x, f1.y);
+            mma_u8s8(acc1, xa1.y & k_lo, xb1.y & k_lo, xa1.y & k_hi, xb1.y & k_hi, f1.x, f1.y);
+            mma_u8s8(acc0, xa0.z & k_lo, xb0.z & k_lo, xa0.z & k_hi, xb0.z & k_hi, f2.x, f2.y);
+            mma_u8s8(acc1, xa1.z & k_lo, xb1.z & k_lo, xa1.z & k_hi, xb1.z & k_hi, f2.x, f2.y);
+            mma_u8s8(acc0, xa0.w & k_lo, xb0.w & k_lo, xa0.w & k_hi, xb0.w & k_hi, f3.x, f3.y);
+            mma_u8s8(acc1, xa1.w & k_lo, xb1.w & k_lo, xa1.w & k_hi, xb1.w & k_hi, f3.x, f3.y);
         }
+        __syncwarp();      // everyone is done with `buf` before the next iteration overwrites it
     }
     // acc[0],acc[1]: individual ia, digits 2c, 2c+1;  acc[2],acc[3]: individual ib
-    if (ia < n) { atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c], acc[0]); atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c + 1], acc[1]); }
-    if (ib < n) { atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c], acc[2]); atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c + 1], acc[3]); }
+    const uint32_t ia = group * 16 + g, ib = ia + 8;
+    if (ia < n) {
+        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c], (unsigned long long) (long long) (acc0[0] + acc1[0]));
+        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[1] + acc1[1]));
+    }
+    if (ib < n) {
+        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c], (unsigned long long) (long long) (acc0[2] + acc1[2]));
+        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[3] + acc1[3]));
+    }
 }
 
 // BV_i = offset + scale * sum_j digit_sums[i][j] * 256^j, most significant digit first
-__global__ void gebv_finish_kernel(const int* __restrict__ digit_sums, uint32_t n, double scale, double offset, double* __restrict__ out) {
+__global__ void gebv_finish_kernel(const long long* __restrict__ digit_sums, uint32_t n, double scale, double offset, double* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int4 lo = reinterpret_cast<const int4*>(digit_sums)[2 * (size_t) i], hi = reinterpret_cast<const int4*>(digit_sums)[2 * (size_t) i + 1];
-    double v = (double) hi.w;
-    v = v * 256.0 + (double) hi.z;
-    v = v * 256.0 + (double) hi.y;
-    v = v * 256.0 + (double) hi.x;
-    v = v * 256.0 + (double) lo.w;
-    v = v * 256.0 + (double) lo.z;
-    v = v * 256.0 + (double) lo.y;
-    v = v * 256.0 + (double) lo.x;
+    const long long* d = digit_sums + (size_t) i * 8;
+    double v = (double) d[7];
+#pragma unroll
+    for (int j = 6; j >= 0; --j) v = v * 256.0 + (double) d[j];
     out[i] = offset + v * scale;
 }
 
@@ -249,12 +294,14 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
         for (uint32_t m = 0; m < M; ++m) maxabs = std::max(maxabs, std::fabs(delta[m]));
         int exp2 = 0;
         if (maxabs > 0.0 && std::isfinite(maxabs)) exp2 = 61 - std::ilogb(maxabs);
+        // the kernel leaves the genotype bit of marker (8j + sft) of a word at weight 2^sft, so the
+        // digits are those of round(delta * 2^(exp2 - sft)): 55..62 significant bits
         e.digit_scale = std::ldexp(1.0, -exp2);
         const uint32_t words = ctx->plane_words;
         std::vector<uint32_t> frag((size_t) words * 64, 0u);
         for (uint32_t m = 0; m < M; ++m) {
-            long long q = std::isfinite(delta[m]) ? std::llrint(std::ldexp(delta[m], exp2)) : 0;
             const uint32_t w = m >> 5, bit = m & 31, j = bit >> 3, sft = bit & 7, cc = sft & 3, half = sft >> 2;
+            long long q = std::isfinite(delta[m]) ? std::llrint(std::ldexp(delta[m], exp2 - (int) sft)) : 0;
             for (uint32_t dg = 0; dg < 8; ++dg) {
                 const long long d8 = ((q + 128) & 255) - 128;
                 q = (q - d8) >> 8;
@@ -278,22 +325,22 @@ int gebv_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t ef
     GSB_TRY(get_effects(ctx, eff_index, &e, what));
     const double centre_sum = e->has_centre ? e->centre_sum : 0.0;
     if (ctx->planes == 1 && ctx->n_markers <= kGebvMaxMarkers) {
-        GSB_TRY(ctx->s_eval[2].ensure((size_t) n * 8 * sizeof(int)));
-        int* d_digits = (int*) ctx->s_eval[2].ptr;
-        GSB_CUDA_TRY(cudaMemsetAsync(d_digits, 0, (size_t) n * 8 * sizeof(int), ctx->stream));
-        const uint32_t steps = ctx->plane_words / 4, n_groups = (n + 15) / 16;
-        // enough marker segments to fill the machine a few times over, at least 16 steps each
-        uint32_t n_segments = (uint32_t) std::min<uint64_t>(std::max<uint32_t>(steps / 16, 1),
-                                                            ((uint64_t) ctx->sm_count * 64 * 4 + n_groups - 1) / n_groups);
-        n_segments = std::max<uint32_t>(n_segments, 1);
-        const uint32_t seg_len = (steps + n_segments - 1) / n_segments;
-        n_segments = (steps + seg_len - 1) / seg_len;
+        GSB_TRY(ctx->s_eval[2].ensure((size_t) n * 8 * sizeof(long long)));
+        unsigned long long* d_digits = (unsigned long long*) ctx->s_eval[2].ptr;
+        GSB_CUDA_TRY(cudaMemsetAsync(d_digits, 0, (size_t) n * 8 * sizeof(long long), ctx->stream));
+        const uint32_t chunks = ctx->plane_words / kChunkWords, n_groups = (n + 15) / 16;
+        // enough marker segments to fill the machine a few times over
+        uint32_t n_segments = (uint32_t) std::min<uint64_t>(chunks, ((uint64_t) ctx->sm_count * 64 * 4 + n_groups - 1) / n_groups);
+        n_segments = std::max<uint32_t>(n_segments, (chunks + kGebvMaxSegChunks - 1) / kGebvMaxSegChunks);
+        const uint32_t seg_chunks = (chunks + n_segments - 1) / n_segments;
+        n_segments = (chunks + seg_chunks - 1) / seg_chunks;
         const uint64_t warps = (uint64_t) n_groups * n_segments;
         gebv_digits_kernel<<<(unsigned) ((warps + kGebvWarps - 1) / kGebvWarps), kGebvWarps * 32, 0, ctx->stream>>>(
-            ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, (const uint2*) e->d_digit_frag, n_segments, seg_len, d_digits);
+            ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, (const uint2*) e->d_digit_frag, n_segments, seg_chunks, d_digits);
         ++ctx->launches;
         GSB_CUDA_TRY(cudaGetLastError());
-        gebv_finish_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_digits, n, e->digit_scale, e->base_all - centre_sum, d_out);
+        gebv_finish_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const long long*) d_digits, n, e->digit_scale,
+                                                                    e->base_all - centre_sum, d_out);
     } else {
         const uint64_t threads = (uint64_t) n * 32;
         gebv_generic_kernel<<<(unsigned) ((threads + 127) / 128), 128, 0, ctx->stream>>>(
