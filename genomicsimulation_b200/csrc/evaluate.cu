@@ -57,8 +57,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // One warp = 16 individuals x one segment of marker chunks.  The warp streams its 32 strand rows
 // through shared memory with 16-byte cp.async (each row contributes one full 128-byte line per
 // chunk, so global reads are whole lines), double-buffered; lanes then pick their mma A words
-// with conflict-free LDS.128.  A byte is `word & (0x01010101 << s)`: bit 8j+s of the word,
-// left at weight 2^s (s = c for register a0/a1, c+4 for a2/a3) — one LOP3 per register; the
+// with conflict-free LDS.128.  An A byte is `(strand0 & mask) + (strand1 & mask)`: the allele
+// count of marker 8j+s of the word, left at the weight the mask's bit position gives it; the
 // weight is divided out of the digits on the host (ensure_effect_tables).
 // bfrag[(w * 32 + lane)] = the two B registers of `lane` for marker word w.
 __global__ void __launch_bounds__(kGebvWarps * 32) gebv_digits_kernel(
@@ -77,21 +77,27 @@ __global__ void __launch_bounds__(kGebvWarps * 32) gebv_digits_kernel(
 
     // staging role: copy `it` moves 16 bytes of strand row r = it*4 + lane/8 (individual r & 15, strand r >> 4)
     const uint32_t my_row = rows[min(group * 16 + (lane & 15), n - 1)];
-    const uint32_t* stage_src[8];
+    uint32_t stage_row[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const uint32_t r = it * 4 + (lane >> 3);
-        const uint32_t row = __shfl_sync(0xffffffffu, my_row, r & 15);
-        stage_src[it] = store + (uint64_t) row * row_words + (r >> 4) * plane_words + (lane & 7) * 4;
-    }
+    for (int it = 0; it < 8; ++it) stage_row[it] = __shfl_sync(0xffffffffu, my_row, (it * 4 + (lane >> 3)) & 15);
+    const uint32_t* stage_base = store + (lane & 7) * 4;
     auto stage = [&](uint32_t ch, uint32_t* buf) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it)
-            cp_async16(buf + (it * 4 + (lane >> 3)) * kRowStride + (lane & 7) * 4, stage_src[it] + (size_t) ch * kChunkWords);
+        for (int it = 0; it < 8; ++it) {
+            const uint32_t r = it * 4 + (lane >> 3);
+            cp_async16(buf + r * kRowStride + (lane & 7) * 4,
+                       stage_base + (uint64_t) stage_row[it] * row_words + (r >> 4) * plane_words + ch * kChunkWords);
+        }
         cp_async_commit();
     };
 
-    const uint32_t k_lo = 0x01010101u << c, k_hi = k_lo << 4;
+    // byte j of an A register = allele count of marker 8j + s of the word (both strands added),
+    // at weight 2^c for s = c (a0/a1) and 2^(c+3) for s = c + 4 (a2/a3): at most 2 * 2^6 = 128
+    const uint32_t k_lo = 0x01010101u << c, k_hi = k_lo << 3;
+    auto word = [&](int (&acc)[4], uint32_t a_s0, uint32_t a_s1, uint32_t b_s0, uint32_t b_s1, const uint2& f) {
+        mma_u8s8(acc, (a_s0 & k_lo) + (a_s1 & k_lo), (b_s0 & k_lo) + (b_s1 & k_lo),
+                 ((a_s0 >> 1) & k_hi) + ((a_s1 >> 1) & k_hi), ((b_s0 >> 1) & k_hi) + ((b_s1 >> 1) & k_hi), f.x, f.y);
+    };
     int acc0[4] = { 0, 0, 0, 0 }, acc1[4] = { 0, 0, 0, 0 };
     stage(ch_lo, s_buf[warp][0]);
     for (uint32_t ch = ch_lo; ch < ch_hi; ++ch) {
@@ -108,14 +114,10 @@ __global__ void __launch_bounds__(kGebvWarps * 32) gebv_digits_kernel(
             const uint4 xb1 = *reinterpret_cast<const uint4*>(buf + (24 + g) * kRowStride + t * 4);
             const uint2 f0 = __ldg(f + (t * 4 + 0) * 32), f1 = __ldg(f + (t * 4 + 1) * 32);
             const uint2 f2 = __ldg(f + (t * 4 + 2) * 32), f3 = __ldg(f + (t * 4 + 3) * 32);
-            mma_u8s8(acc0, xa0.x & k_lo, xb0.x & k_lo, xa0.x & k_hi, xb0.x & k_hi, f0.x, f0.y);
-            mma_u8s8(acc1, xa1.x & k_lo, xb1.x & k_lo, xa1.x & k_hi, xb1.x & k_hi, f0.x, f0.y);
-            mma_u8s8(acc0, xa0.y & k_lo, xb0.y & k_lo, xa0.y & k_hi, xb0.y & k_hi, f1.x, f1.y);
-            mma_u8s8(acc1, xa1.y & k_lo, xb1.y & k_lo, xa1.y & k_hi, xb1.y & k_hi, f1.x, f1.y);
-            mma_u8s8(acc0, xa0.z & k_lo, xb0.z & k_lo, xa0.z & k_hi, xb0.z & k_hi, f2.x, f2.y);
-            mma_u8s8(acc1, xa1.z & k_lo, xb1.z & k_lo, xa1.z & k_hi, xb1.z & k_hi, f2.x, f2.y);
-            mma_u8s8(acc0, xa0.w & k_lo, xb0.w & k_lo, xa0.w & k_hi, xb0.w & k_hi, f3.x, f3.y);
-            mma_u8s8(acc1, xa1.w & k_lo, xb1.w & k_lo, xa1.w & k_hi, xb1.w & k_hi, f3.x, f3.y);
+            word(acc0, xa0.x, xa1.x, xb0.x, xb1.x, f0);
+            word(acc1, xa0.y, xa1.y, xb0.y, xb1.y, f1);
+            word(acc0, xa0.z, xa1.z, xb0.z, xb1.z, f2);
+            word(acc1, xa0.w, xa1.w, xb0.w, xb1.w, f3);
         }
         __syncwarp();      // everyone is done with `buf` before the next iteration overwrites it
     }
@@ -294,14 +296,16 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
         for (uint32_t m = 0; m < M; ++m) maxabs = std::max(maxabs, std::fabs(delta[m]));
         int exp2 = 0;
         if (maxabs > 0.0 && std::isfinite(maxabs)) exp2 = 61 - std::ilogb(maxabs);
-        // the kernel leaves the genotype bit of marker (8j + sft) of a word at weight 2^sft, so the
-        // digits are those of round(delta * 2^(exp2 - sft)): 55..62 significant bits
+        // the kernel leaves the allele count of marker (8j + sft) of a word at weight 2^wexp,
+        // wexp = sft for sft < 4 and sft - 1 above, so the digits are those of
+        // round(delta * 2^(exp2 - wexp)): 56..62 significant bits
         e.digit_scale = std::ldexp(1.0, -exp2);
         const uint32_t words = ctx->plane_words;
         std::vector<uint32_t> frag((size_t) words * 64, 0u);
         for (uint32_t m = 0; m < M; ++m) {
             const uint32_t w = m >> 5, bit = m & 31, j = bit >> 3, sft = bit & 7, cc = sft & 3, half = sft >> 2;
-            long long q = std::isfinite(delta[m]) ? std::llrint(std::ldexp(delta[m], exp2 - (int) sft)) : 0;
+            const int wexp = half ? (int) sft - 1 : (int) sft;
+            long long q = std::isfinite(delta[m]) ? std::llrint(std::ldexp(delta[m], exp2 - wexp)) : 0;
             for (uint32_t dg = 0; dg < 8; ++dg) {
                 const long long d8 = ((q + 128) & 255) - 128;
                 q = (q - d8) >> 8;
