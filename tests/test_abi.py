@@ -1,0 +1,62 @@
+"""CPU-side checks of the boundary: the C-ABI libraries load and export every symbol the headers
+declare, and the product refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header, prefix):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(%s\w+)\s*\(" % prefix, txt)))
+
+
+def test_engine_exports_every_declared_symbol():
+    import genomicsimulation_b200 as g
+    lib = C.CDLL(g.LIB_ENGINE)
+    names = declared("gsb200.h", "gsb200_")
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "libgsb200.so does not export %s" % n
+    assert set(names) == set(g._lib.ENGINE_SYMBOLS), "ctypes table out of step with include/gsb200.h"
+    assert g.engine().gsb200_abi_version() == 1
+
+
+def test_host_mirror_exports_every_declared_symbol():
+    import genomicsimulation_b200 as g
+    g.engine()
+    lib = C.CDLL(g.LIB_HOST)
+    names = declared("gsb200_gsc.h", "gsb_")
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "libgsb200_gsc.so does not export %s" % n
+    assert set(names) == set(g._lib.HOST_SYMBOLS)
+    opt = g.GenOptions.in_dll(lib, "GSB_BASIC_OPT")          # GSC_BASIC_OPT, sim-operations.c:11-23
+    assert opt.family_size == 1 and opt.will_allocate_ids and opt.will_save_to_simdata and not opt.will_track_pedigree
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import genomicsimulation_b200 as g
+    E = g.engine()
+    ctx = C.c_void_p()
+    st = E.gsb200_create(C.byref(ctx), 0, 100)
+    assert st == 1 and not ctx.value                          # GSB200_ERR_CUDA
+    assert b"no CPU fallback" in E.gsb200_last_error()
+    with pytest.raises(g.EngineError):
+        g.SimData(100)
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "genomicsimulation_b200")):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
+                assert "gs_oracle" not in txt and "libgsoracle" not in txt, f
