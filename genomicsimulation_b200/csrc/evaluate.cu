@@ -37,10 +37,12 @@ namespace {
 // segments can be summed with integer atomics and the result is still deterministic.
 constexpr int kGebvWarps = 4;                  // warps per block, 16 individuals each
 constexpr uint32_t kGebvMaxMarkers = 1u << 26;
-constexpr uint32_t kChunkWords = 32;           // 1024 markers = 8 mma tiles of 128 = one 128-byte line per strand
-constexpr uint32_t kRowStride = 36;            // words: 128 B + 16 B pad -> the 8 row reads of an LDS.128 hit 32 distinct banks
-constexpr uint32_t kBufWords = 32 * kRowStride;   // 16 individuals x 2 strands
-constexpr uint32_t kGebvMaxSegChunks = 32;     // 32768 markers * 2 strands * 128 * 128 < 2^31
+constexpr uint32_t kChunkWords = 16;           // 512 markers = 4 mma tiles of 128 = 64 bytes per strand row
+constexpr uint32_t kChunkTiles = kChunkWords / 4;
+constexpr uint32_t kRowStride = 20;            // words: 64 B + 16 B pad -> the 8 row reads of an LDS.128 hit 32 distinct banks
+constexpr uint32_t kBufWords = 32 * kRowStride;   // 16 individuals x 2 strands; small on purpose: what shared
+                                                  // memory does not take stays L1 for the B fragments
+constexpr uint32_t kGebvMaxSegChunks = 64;     // 32768 markers * 128 * 128 < 2^31
 
 __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -55,11 +57,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 // One warp = 16 individuals x one segment of marker chunks.  The warp streams its 32 strand rows
-// through shared memory with 16-byte cp.async (each row contributes one full 128-byte line per
-// chunk, so global reads are whole lines), double-buffered; lanes then pick their mma A words
-// with conflict-free LDS.128.  An A byte is `(strand0 & mask) + (strand1 & mask)`: the allele
-// count of marker 8j+s of the word, left at the weight the mask's bit position gives it; the
-// weight is divided out of the digits on the host (ensure_effect_tables).
+// through shared memory with 16-byte cp.async (64 contiguous bytes per row and chunk),
+// double-buffered; lanes then pick their mma A words
+// with conflict-free LDS.128.  An A byte is `strand_word & mask`: bit 8j+s of the word, left at
+// the weight 2^s its position gives it; the weight is divided out of the digits on the host
+// (ensure_effect_tables).
 // bfrag[(w * 32 + lane)] = the two B registers of `lane` for marker word w.
 __global__ void __launch_bounds__(kGebvWarps * 32) gebv_digits_kernel(
         const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
@@ -75,30 +77,33 @@ __global__ void __launch_bounds__(kGebvWarps * 32) gebv_digits_kernel(
     const uint32_t ch_lo = seg * seg_chunks, ch_hi = min(ch_lo + seg_chunks, plane_words / kChunkWords);
     if (ch_lo >= ch_hi) return;
 
-    // staging role: copy `it` moves 16 bytes of strand row r = it*4 + lane/8 (individual r & 15, strand r >> 4)
+    // staging role: copy `it` moves 16 bytes of strand row r = it*8 + lane/4 (individual r & 15, strand r >> 4)
     const uint32_t my_row = rows[min(group * 16 + (lane & 15), n - 1)];
-    uint32_t stage_row[8];
+    uint32_t stage_row[4];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) stage_row[it] = __shfl_sync(0xffffffffu, my_row, (it * 4 + (lane >> 3)) & 15);
-    const uint32_t* stage_base = store + (lane & 7) * 4;
+    for (int it = 0; it < 4; ++it) stage_row[it] = __shfl_sync(0xffffffffu, my_row, (it * 8 + (lane >> 2)) & 15);
+    const uint32_t* stage_base = store + (lane & 3) * 4;
     auto stage = [&](uint32_t ch, uint32_t* buf) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const uint32_t r = it * 4 + (lane >> 3);
-            cp_async16(buf + r * kRowStride + (lane & 7) * 4,
+        for (int it = 0; it < 4; ++it) {
+            const uint32_t r = it * 8 + (lane >> 2);
+            cp_async16(buf + r * kRowStride + (lane & 3) * 4,
                        stage_base + (uint64_t) stage_row[it] * row_words + (r >> 4) * plane_words + ch * kChunkWords);
         }
         cp_async_commit();
     };
 
-    // byte j of an A register = allele count of marker 8j + s of the word (both strands added),
-    // at weight 2^c for s = c (a0/a1) and 2^(c+3) for s = c + 4 (a2/a3): at most 2 * 2^6 = 128
-    const uint32_t k_lo = 0x01010101u << c, k_hi = k_lo << 3;
-    auto word = [&](int (&acc)[4], uint32_t a_s0, uint32_t a_s1, uint32_t b_s0, uint32_t b_s1, const uint2& f) {
-        mma_u8s8(acc, (a_s0 & k_lo) + (a_s1 & k_lo), (b_s0 & k_lo) + (b_s1 & k_lo),
-                 ((a_s0 >> 1) & k_hi) + ((a_s1 >> 1) & k_hi), ((b_s0 >> 1) & k_hi) + ((b_s1 >> 1) & k_hi), f.x, f.y);
-    };
     int acc0[4] = { 0, 0, 0, 0 }, acc1[4] = { 0, 0, 0, 0 };
+    // A rows are STRANDS: row g = strand 0 of an individual, row g + 8 = its strand 1, so a register
+    // is one LOP3: byte j = bit 8j + s of the strand's word, left at weight 2^s (s = c for a0/a1,
+    // c + 4 for a2/a3).  One mma covers 8 individuals; the warp issues two per marker word
+    // (individuals g and g + 8 of its 16) on the same B registers.  The expansion runs on the ALU
+    // pipe (one LOP3 per 2 cycles per scheduler), which is what bounds this kernel.
+    const uint32_t k_lo = 0x01010101u << c, k_hi = k_lo << 4;
+    auto word = [&](uint32_t a_s0, uint32_t a_s1, uint32_t b_s0, uint32_t b_s1, const uint2& f) {
+        mma_u8s8(acc0, a_s0 & k_lo, a_s1 & k_lo, a_s0 & k_hi, a_s1 & k_hi, f.x, f.y);
+        mma_u8s8(acc1, b_s0 & k_lo, b_s1 & k_lo, b_s0 & k_hi, b_s1 & k_hi, f.x, f.y);
+    };
     stage(ch_lo, s_buf[warp][0]);
     for (uint32_t ch = ch_lo; ch < ch_hi; ++ch) {
         const uint32_t* buf = s_buf[warp][(ch - ch_lo) & 1];
@@ -107,29 +112,29 @@ __global__ void __launch_bounds__(kGebvWarps * 32) gebv_digits_kernel(
         __syncwarp();
         const uint2* f = bfrag + (size_t) ch * (kChunkWords * 32) + lane;
 #pragma unroll 2
-        for (uint32_t t = 0; t < 8; ++t) {
+        for (uint32_t t = 0; t < kChunkTiles; ++t) {
             const uint4 xa0 = *reinterpret_cast<const uint4*>(buf + g * kRowStride + t * 4);
             const uint4 xb0 = *reinterpret_cast<const uint4*>(buf + (g + 8) * kRowStride + t * 4);
             const uint4 xa1 = *reinterpret_cast<const uint4*>(buf + (16 + g) * kRowStride + t * 4);
             const uint4 xb1 = *reinterpret_cast<const uint4*>(buf + (24 + g) * kRowStride + t * 4);
             const uint2 f0 = __ldg(f + (t * 4 + 0) * 32), f1 = __ldg(f + (t * 4 + 1) * 32);
             const uint2 f2 = __ldg(f + (t * 4 + 2) * 32), f3 = __ldg(f + (t * 4 + 3) * 32);
-            word(acc0, xa0.x, xa1.x, xb0.x, xb1.x, f0);
-            word(acc1, xa0.y, xa1.y, xb0.y, xb1.y, f1);
-            word(acc0, xa0.z, xa1.z, xb0.z, xb1.z, f2);
-            word(acc1, xa0.w, xa1.w, xb0.w, xb1.w, f3);
+            word(xa0.x, xa1.x, xb0.x, xb1.x, f0);
+            word(xa0.y, xa1.y, xb0.y, xb1.y, f1);
+            word(xa0.z, xa1.z, xb0.z, xb1.z, f2);
+            word(xa0.w, xa1.w, xb0.w, xb1.w, f3);
         }
         __syncwarp();      // everyone is done with `buf` before the next iteration overwrites it
     }
-    // acc[0],acc[1]: individual ia, digits 2c, 2c+1;  acc[2],acc[3]: individual ib
+    // acc0: individual ia (rows g, g+8 = its two strands), digits 2c, 2c+1;  acc1: individual ib
     const uint32_t ia = group * 16 + g, ib = ia + 8;
     if (ia < n) {
-        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c], (unsigned long long) (long long) (acc0[0] + acc1[0]));
-        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[1] + acc1[1]));
+        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c], (unsigned long long) (long long) (acc0[0] + acc0[2]));
+        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[1] + acc0[3]));
     }
     if (ib < n) {
-        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c], (unsigned long long) (long long) (acc0[2] + acc1[2]));
-        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[3] + acc1[3]));
+        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c], (unsigned long long) (long long) (acc1[0] + acc1[2]));
+        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c + 1], (unsigned long long) (long long) (acc1[1] + acc1[3]));
     }
 }
 
@@ -296,16 +301,14 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
         for (uint32_t m = 0; m < M; ++m) maxabs = std::max(maxabs, std::fabs(delta[m]));
         int exp2 = 0;
         if (maxabs > 0.0 && std::isfinite(maxabs)) exp2 = 61 - std::ilogb(maxabs);
-        // the kernel leaves the allele count of marker (8j + sft) of a word at weight 2^wexp,
-        // wexp = sft for sft < 4 and sft - 1 above, so the digits are those of
-        // round(delta * 2^(exp2 - wexp)): 56..62 significant bits
+        // the kernel leaves the strand bit of marker (8j + sft) of a word at weight 2^sft, so the
+        // digits are those of round(delta * 2^(exp2 - sft)): 55..62 significant bits
         e.digit_scale = std::ldexp(1.0, -exp2);
         const uint32_t words = ctx->plane_words;
         std::vector<uint32_t> frag((size_t) words * 64, 0u);
         for (uint32_t m = 0; m < M; ++m) {
             const uint32_t w = m >> 5, bit = m & 31, j = bit >> 3, sft = bit & 7, cc = sft & 3, half = sft >> 2;
-            const int wexp = half ? (int) sft - 1 : (int) sft;
-            long long q = std::isfinite(delta[m]) ? std::llrint(std::ldexp(delta[m], exp2 - wexp)) : 0;
+            long long q = std::isfinite(delta[m]) ? std::llrint(std::ldexp(delta[m], exp2 - (int) sft)) : 0;
             for (uint32_t dg = 0; dg < 8; ++dg) {
                 const long long d8 = ((q + 128) & 255) - 128;
                 q = (q - d8) >> 8;
