@@ -204,7 +204,6 @@ def engine_arm(a):
     d_bv = torch.empty(n, dtype=torch.float64, device="cuda")
     pool = torch.empty(F * row_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
     all_bv = torch.empty(world * n, dtype=torch.float64, device="cuda") if world > 1 else None
-    founder_rows = np.arange(F, dtype=np.uint32)
     torch.cuda.synchronize()
 
     def check(st):
@@ -214,25 +213,29 @@ def engine_arm(a):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kernel_ms = {"cross": [], "gebv": []}
 
+    d_founder_rows = torch.arange(0, F, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+
     def step(i, timed):
-        if world > 1:
-            # generation boundary: rank 0's parent pool to everyone over NVLink, GEBVs gathered for selection
-            if rank == 0:
-                check(E.gsb200_store_gather_rows_dev(ctx, F, founder_rows.ctypes.data, pool.data_ptr()))
-            dist.broadcast(pool, 0)
-            torch.cuda.current_stream().synchronize()
-            if rank != 0:
-                check(E.gsb200_store_scatter_rows_dev(ctx, F, founder_rows.ctypes.data, pool.data_ptr()))
-        dr = Draws(mode=0, seed=20261019, stream=i, first_unit=rank * n)
-        e0, e1, e2 = ev(), ev(), ev()
-        e0.record(ext)
-        check(E.gsb200_cross_dev(ctx, n, d_p1.data_ptr(), d_p2.data_ptr(), 0, 0, d_out.data_ptr(), C.byref(dr)))
-        e1.record(ext)
-        check(E.gsb200_gebv_dev(ctx, n, d_out.data_ptr(), 0, d_bv.data_ptr()))
-        e2.record(ext)
-        if world > 1:
-            ext.synchronize()
-            dist.all_gather_into_tensor(all_bv, d_bv)
+        # everything is enqueued on the engine's stream (torch's current stream inside this call):
+        # NCCL orders itself against it with events, so the step has no host synchronisation
+        with torch.cuda.stream(ext):
+            if world > 1:
+                # generation boundary: rank 0's parent pool to everyone over NVLink
+                if rank == 0:
+                    check(E.gsb200_store_gather_rows_dev(ctx, F, d_founder_rows.data_ptr(), pool.data_ptr()))
+                dist.broadcast(pool, 0)
+                if rank != 0:
+                    check(E.gsb200_store_scatter_rows_dev(ctx, F, d_founder_rows.data_ptr(), pool.data_ptr()))
+            dr = Draws(mode=0, seed=20261019, stream=i, first_unit=rank * n)
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record(ext)
+            check(E.gsb200_cross_dev(ctx, n, d_p1.data_ptr(), d_p2.data_ptr(), 0, 0, d_out.data_ptr(), C.byref(dr)))
+            e1.record(ext)
+            check(E.gsb200_gebv_dev(ctx, n, d_out.data_ptr(), 0, d_bv.data_ptr()))
+            e2.record(ext)
+            if world > 1:
+                dist.all_gather_into_tensor(all_bv, d_bv)      # GEBVs for replicated selection
         if timed:
             kernel_ms["_ev"].append((e0, e1, e2))
 
@@ -277,11 +280,16 @@ def engine_arm(a):
             dist.barrier()
         t = time.perf_counter()
         grp = sim.make_random_crosses(g_f, n, 0, 1)
+        ta = time.perf_counter()
         bv = sim.calculate_bvs(grp, 1)
+        tb = time.perf_counter()
         sim.delete_group(grp)
         if world > 1:
             dist.barrier()
         e2e_t.append(time.perf_counter() - t)
+        if os.environ.get("GSB200_BENCH_VERBOSE") and rank == 0:
+            print("e2e step: cross %.3f ms, gebv %.3f ms, delete %.3f ms" % ((ta - t) * 1e3, (tb - ta) * 1e3,
+                  (time.perf_counter() - tb) * 1e3), file=sys.stderr)
         assert bv.shape[0] == n
     e2e_sec = float(np.mean(e2e_t[2:]))
     te = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")

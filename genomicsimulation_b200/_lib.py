@@ -82,6 +82,8 @@ ENGINE_SYMBOLS = {
     "gsb200_gebv": (I32, [VP, U32, VP, U32, VP]),
     "gsb200_gebv_dev": (I32, [VP, U32, VP, U32, VP]),
     "gsb200_local_gebv": (I32, [VP, U32, VP, U32, VP, VP, U32, VP]),
+    "gsb200_local_gebv_multi": (I32, [VP, U32, VP, U32, VP, VP, U32, VP, VP]),
+    "gsb200_local_gebv_multi_dev": (I32, [VP, U32, VP, U32, VP, VP, U32, VP, VP]),
     "gsb200_allele_counts": (I32, [VP, U32, VP, C.c_char, I32, VP]),
     "gsb200_top_n": (I32, [VP, U32, VP, U32, I32, VP]),
     "gsb200_kernel_launches": (U64, [VP]),

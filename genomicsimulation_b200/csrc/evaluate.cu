@@ -207,6 +207,112 @@ __global__ void local_gebv_kernel(const uint32_t* __restrict__ store, uint64_t r
     }
 }
 
+// ------------------------------------------------------------------ local GEBV, tensor path
+// Blocks that are contiguous, ascending, non-overlapping marker ranges (what
+// gsc_create_evenlength_blocks_each_chr produces on a map in marker order) on a one-plane store:
+// the same exact digit contraction as gebv_digits_kernel, with the accumulators flushed at every
+// block boundary.  A rows are the 16 strands of 8 individuals; a "step" is one 32-marker word of
+// one block, with B digits zeroed outside the block (a word straddling two blocks is two steps).
+// kSets effect sets share each A register — with many effect sets this is the dense
+// (strands x markers) x (markers x 8*sets) contraction of BASELINE.json configs[4].
+constexpr uint32_t kLocalRowStride = 20;
+constexpr uint32_t kLocalBufWords = 16 * kLocalRowStride;
+constexpr int kLocalWarps = 4;
+constexpr int kLocalMaxSets = 4;
+
+struct LocalSetParams {
+    const uint2* bfrag[kLocalMaxSets];     // [n_steps][32]
+    const double* base[kLocalMaxSets];     // [n_blocks]
+    double* out[kLocalMaxSets];            // [(2n) x n_blocks]
+    double scale[kLocalMaxSets];
+};
+
+template <int kSets>
+__global__ void __launch_bounds__(kLocalWarps * 32) local_gebv_digits_kernel(
+        const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
+        const uint32_t* __restrict__ rows, uint32_t n, uint32_t n_blocks,
+        const uint2* __restrict__ steps /* (word, block) */, const uint32_t* __restrict__ range_lo, uint32_t n_ranges,
+        const LocalSetParams sp) {
+    __shared__ __align__(16) uint32_t s_buf[kLocalWarps][2][kLocalBufWords];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp_global = blockIdx.x * kLocalWarps + warp;
+    const uint32_t n_groups = (n + 7) / 8;
+    if (warp_global >= n_groups * n_ranges) return;
+    const uint32_t group = warp_global % n_groups, range = warp_global / n_groups;
+    const uint32_t g = lane >> 2, c = lane & 3;
+    const uint32_t s_lo = range_lo[range], s_hi = range_lo[range + 1];
+    if (s_lo >= s_hi) return;
+
+    // staging: 16 strand rows x 64 bytes per chunk; copy `it` moves 16 bytes of row it*8 + lane/4
+    // (individual r & 7, strand r >> 3)
+    const uint32_t my_row = rows[min(group * 8 + (lane & 7), n - 1)];
+    uint32_t stage_row[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) stage_row[it] = __shfl_sync(0xffffffffu, my_row, (it * 8 + (lane >> 2)) & 7);
+    const uint32_t* stage_base = store + (lane & 3) * 4;
+    auto stage = [&](uint32_t chunk, uint32_t* buf) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const uint32_t r = it * 8 + (lane >> 2);
+            cp_async16(buf + r * kLocalRowStride + (lane & 3) * 4,
+                       stage_base + (uint64_t) stage_row[it] * row_words + (r >> 3) * plane_words + chunk * kChunkWords);
+        }
+        cp_async_commit();
+    };
+
+    const uint32_t k_lo = 0x01010101u << c, k_hi = k_lo << 4;
+    const uint32_t n_chunks = plane_words / kChunkWords;
+    int acc[kSets][4];
+#pragma unroll
+    for (int q = 0; q < kSets; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0;
+
+    const uint32_t ia = group * 8 + g;
+    auto flush = [&](uint32_t block) {
+#pragma unroll
+        for (int q = 0; q < kSets; ++q) {
+            // row g = strand 0 of individual ia, row g + 8 = strand 1; this lane: digits 2c, 2c+1
+            const double w = exp2((double) (16 * c));
+            double v0 = ((double) acc[q][0] + 256.0 * (double) acc[q][1]) * w;
+            double v1 = ((double) acc[q][2] + 256.0 * (double) acc[q][3]) * w;
+            v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+            v0 += __shfl_xor_sync(0xffffffffu, v0, 2); v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+            if (c == 0 && ia < n) {
+                const double b = sp.base[q][block];
+                sp.out[q][(size_t) (2 * (size_t) ia) * n_blocks + block] = b + v0 * sp.scale[q];
+                sp.out[q][(size_t) (2 * (size_t) ia + 1) * n_blocks + block] = b + v1 * sp.scale[q];
+            }
+            acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0;
+        }
+    };
+
+    uint32_t cur_block = steps[s_lo].y, cur_chunk = 0xffffffffu, staged_next = 0xffffffffu, parity = 0;
+    for (uint32_t s = s_lo; s < s_hi; ++s) {
+        const uint2 st = __ldg(steps + s);
+        if (st.y != cur_block) { flush(cur_block); cur_block = st.y; }
+        const uint32_t chunk = st.x / kChunkWords;
+        if (chunk != cur_chunk) {
+            __syncwarp();                                   // everyone is done with the old buffers
+            if (staged_next == chunk) { parity ^= 1; }
+            else { cp_async_wait<0>(); parity = 0; stage(chunk, s_buf[warp][0]); }
+            cur_chunk = chunk;
+            if (chunk + 1 < n_chunks) { stage(chunk + 1, s_buf[warp][parity ^ 1]); staged_next = chunk + 1; cp_async_wait<1>(); }
+            else { staged_next = 0xffffffffu; cp_async_wait<0>(); }
+            __syncwarp();
+        }
+        const uint32_t* buf = s_buf[warp][parity];
+        const uint32_t x0 = buf[g * kLocalRowStride + (st.x % kChunkWords)];
+        const uint32_t x1 = buf[(8 + g) * kLocalRowStride + (st.x % kChunkWords)];
+        const uint32_t a0 = x0 & k_lo, a1 = x1 & k_lo, a2 = x0 & k_hi, a3 = x1 & k_hi;
+#pragma unroll
+        for (int q = 0; q < kSets; ++q) {
+            const uint2 f = __ldg(sp.bfrag[q] + (size_t) s * 32 + lane);
+            mma_u8s8(acc[q], a0, a1, a2, a3, f.x, f.y);
+        }
+    }
+    flush(cur_block);
+    cp_async_wait<0>();
+}
+
 // ------------------------------------------------------------------ allele counts
 template <typename T>
 __global__ void allele_count_kernel(const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
@@ -284,6 +390,7 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
     cudaStreamSynchronize(ctx->stream);
     GSB_TRY(to_device_vec(all, &e.d_value_all));
     GSB_TRY(to_device_vec(first, &e.d_value_first));
+    e.h_value_first = first;
     if (e.has_centre) GSB_TRY(to_device_vec(e.centre, &e.d_centre));
     if (planes == 1) {
         std::vector<double> delta(M);
@@ -386,28 +493,27 @@ int gsb200_gebv(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t eff_
     return GSB200_OK;
 }
 
-int gsb200_local_gebv(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t n_blocks,
-                      const uint32_t* block_offsets, const uint32_t* block_markers,
-                      uint32_t eff_index, double* out) {
-    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
-    const char* what = "gsb200_local_gebv";
-    if (n == 0 || n_blocks == 0) return GSB200_OK;
-    GSB_REQUIRE(block_offsets && out, GSB200_ERR_ARG, "%s: null array", what);
-    GSB_TRY(check_rows(ctx, n, rows, what));
-    GSB_REQUIRE(block_offsets[0] == 0, GSB200_ERR_ARG, "%s: block_offsets[0] must be 0", what);
-    for (uint32_t b = 0; b < n_blocks; ++b)
-        GSB_REQUIRE(block_offsets[b] <= block_offsets[b + 1], GSB200_ERR_ARG, "%s: block_offsets not ascending", what);
-    const uint32_t total = block_offsets[n_blocks];
-    GSB_REQUIRE(total == 0 || block_markers, GSB200_ERR_ARG, "%s: null marker list", what);
-    for (uint32_t q = 0; q < total; ++q)
-        GSB_REQUIRE(block_markers[q] < ctx->n_markers, GSB200_ERR_ARG, "%s: marker index %u out of range", what, block_markers[q]);
-    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
-    DeviceEffects* e;
-    GSB_TRY(get_effects(ctx, eff_index, &e, what));
-    uint32_t *d_rows, *d_off, *d_mk;
-    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], rows, n, &d_rows));
-    GSB_TRY(upload_u32(ctx, ctx->s_rows[1], block_offsets, (size_t) n_blocks + 1, &d_off));
-    GSB_TRY(upload_u32(ctx, ctx->s_rows[2], block_markers, total, &d_mk));
+// Build the step schedule of the tensor path; false if the blocks do not qualify.
+static bool local_schedule(const gsb200_ctx* ctx, uint32_t n_blocks, const uint32_t* off, const uint32_t* mk,
+                           std::vector<uint2>& steps, std::vector<uint32_t>& step_block_first) {
+    if (ctx->planes != 1) return false;
+    uint32_t prev_end = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        const uint32_t lo = off[b], hi = off[b + 1];
+        if (lo == hi) continue;
+        const uint32_t m0 = mk[lo], len = hi - lo;
+        if (len > 32768 || m0 < prev_end) return false;
+        for (uint32_t q = 1; q < len; ++q) if (mk[lo + q] != m0 + q) return false;
+        prev_end = m0 + len;
+        step_block_first.push_back((uint32_t) steps.size());
+        for (uint32_t w = m0 >> 5; w <= (m0 + len - 1) >> 5; ++w) steps.push_back(make_uint2(w, b));
+    }
+    step_block_first.push_back((uint32_t) steps.size());
+    return !steps.empty();
+}
+
+static int local_gebv_generic(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t n_blocks, const uint32_t* d_off,
+                              const uint32_t* d_mk, DeviceEffects* e, double* out) {
     // output in slabs of individuals so that the device buffer stays bounded
     const size_t row_out = 2 * (size_t) n_blocks * sizeof(double);
     const uint32_t slab = (uint32_t) std::max<size_t>(1, std::min<size_t>(n, ((size_t) 1 << 30) / row_out));
@@ -425,6 +531,172 @@ int gsb200_local_gebv(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_
         GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
     return GSB200_OK;
+}
+
+static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t n_blocks,
+                                 const uint32_t* block_offsets, const uint32_t* block_markers,
+                                 uint32_t n_effect_sets, const uint32_t* eff_indexes, double* const* outs, bool device_out) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    const char* what = device_out ? "gsb200_local_gebv_multi_dev" : "gsb200_local_gebv";
+    if (n == 0 || n_blocks == 0 || n_effect_sets == 0) return GSB200_OK;
+    GSB_REQUIRE(block_offsets && outs && eff_indexes, GSB200_ERR_ARG, "%s: null array", what);
+    GSB_TRY(check_rows(ctx, n, rows, what));
+    GSB_REQUIRE(block_offsets[0] == 0, GSB200_ERR_ARG, "%s: block_offsets[0] must be 0", what);
+    for (uint32_t b = 0; b < n_blocks; ++b)
+        GSB_REQUIRE(block_offsets[b] <= block_offsets[b + 1], GSB200_ERR_ARG, "%s: block_offsets not ascending", what);
+    const uint32_t total = block_offsets[n_blocks];
+    GSB_REQUIRE(total == 0 || block_markers, GSB200_ERR_ARG, "%s: null marker list", what);
+    for (uint32_t q = 0; q < total; ++q)
+        GSB_REQUIRE(block_markers[q] < ctx->n_markers, GSB200_ERR_ARG, "%s: marker index %u out of range", what, block_markers[q]);
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    std::vector<DeviceEffects*> effs(n_effect_sets);
+    for (uint32_t q = 0; q < n_effect_sets; ++q) {
+        GSB_REQUIRE(outs[q] != nullptr, GSB200_ERR_ARG, "%s: null output", what);
+        GSB_TRY(get_effects(ctx, eff_indexes[q], &effs[q], what));
+    }
+    uint32_t* d_rows;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], rows, n, &d_rows));
+
+    std::vector<uint2> steps;
+    std::vector<uint32_t> block_first;
+    if (!local_schedule(ctx, n_blocks, block_offsets, block_markers, steps, block_first)) {
+        GSB_REQUIRE(!device_out, GSB200_ERR_UNSUPPORTED,
+                    "%s: device output needs blocks that are contiguous, ascending, non-overlapping marker ranges on a one-plane store", what);
+        uint32_t *d_off, *d_mk;
+        GSB_TRY(upload_u32(ctx, ctx->s_rows[1], block_offsets, (size_t) n_blocks + 1, &d_off));
+        GSB_TRY(upload_u32(ctx, ctx->s_rows[2], block_markers, total, &d_mk));
+        for (uint32_t q = 0; q < n_effect_sets; ++q)
+            GSB_TRY(local_gebv_generic(ctx, n, d_rows, n_blocks, d_off, d_mk, effs[q], outs[q]));
+        return GSB200_OK;
+    }
+
+    // ---- tensor path
+    const uint32_t M = ctx->n_markers, n_steps = (uint32_t) steps.size();
+    // block ranges: tasks = (8 individuals) x (range of whole blocks), a few waves over the machine
+    const uint32_t n_groups = (n + 7) / 8;
+    uint32_t want_ranges = (uint32_t) std::max<uint64_t>(1, ((uint64_t) ctx->sm_count * 48 * 4 + n_groups - 1) / n_groups);
+    want_ranges = std::min<uint32_t>(want_ranges, (uint32_t) block_first.size() - 1);
+    std::vector<uint32_t> range_lo(1, 0);
+    for (uint32_t r = 1; r < want_ranges; ++r) {
+        const uint32_t target = (uint32_t) ((uint64_t) n_steps * r / want_ranges);
+        auto it = std::lower_bound(block_first.begin(), block_first.end(), target);
+        if (it != block_first.end() && *it > range_lo.back() && *it < n_steps) range_lo.push_back(*it);
+    }
+    range_lo.push_back(n_steps);
+    const uint32_t n_ranges = (uint32_t) range_lo.size() - 1;
+
+    // per-pass device buffers: steps | ranges | per set: fragments, block bases
+    const size_t out_elems = (size_t) 2 * n * n_blocks;
+    const size_t slab_rows = std::max<size_t>(8, std::min<size_t>(n, (((size_t) 1 << 30) / (2 * (size_t) n_blocks * sizeof(double))) / 8 * 8));
+    (void) out_elems;
+    for (uint32_t q0 = 0; q0 < n_effect_sets; q0 += kLocalMaxSets) {
+        const uint32_t sets = std::min<uint32_t>(kLocalMaxSets, n_effect_sets - q0);
+        const size_t frag_bytes = (size_t) n_steps * 32 * sizeof(uint2);
+        const size_t base_bytes = (size_t) n_blocks * sizeof(double);
+        const size_t hdr = ((size_t) n_steps * sizeof(uint2) + (n_ranges + 1) * sizeof(uint32_t) + 255) / 256 * 256;
+        const size_t per_set = (frag_bytes + base_bytes + 255) / 256 * 256;
+        GSB_TRY(ctx->s_eval[3].ensure(hdr + per_set * sets));
+        char* dbase = (char*) ctx->s_eval[3].ptr;
+        GSB_CUDA_TRY(cudaMemcpyAsync(dbase, steps.data(), (size_t) n_steps * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+        GSB_CUDA_TRY(cudaMemcpyAsync(dbase + (size_t) n_steps * sizeof(uint2), range_lo.data(), (n_ranges + 1) * sizeof(uint32_t),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        LocalSetParams sp;
+        memset(&sp, 0, sizeof sp);
+        std::vector<std::vector<uint32_t>> frags(sets);
+        std::vector<std::vector<double>> bases(sets);
+        for (uint32_t q = 0; q < sets; ++q) {
+            DeviceEffects* e = effs[q0 + q];
+            const std::vector<double>& vf = e->h_value_first;      // [M << 1]
+            double maxabs = 0.0;
+            for (uint32_t m = 0; m < M; ++m) maxabs = std::max(maxabs, std::fabs(vf[2 * (size_t) m + 1] - vf[2 * (size_t) m]));
+            int exp2v = 0;
+            if (maxabs > 0.0 && std::isfinite(maxabs)) exp2v = 61 - std::ilogb(maxabs);
+            sp.scale[q] = std::ldexp(1.0, -exp2v);
+            frags[q].assign((size_t) n_steps * 64, 0u);
+            bases[q].assign(n_blocks, 0.0);
+            for (uint32_t st = 0; st < n_steps; ++st) {
+                const uint32_t w = steps[st].x, b = steps[st].y;
+                const uint32_t m_lo = block_markers[block_offsets[b]], m_hi = m_lo + (block_offsets[b + 1] - block_offsets[b]);
+                for (uint32_t bit = 0; bit < 32; ++bit) {
+                    const uint32_t m = w * 32 + bit;
+                    if (m < m_lo || m >= m_hi) continue;
+                    const double d = vf[2 * (size_t) m + 1] - vf[2 * (size_t) m];
+                    const uint32_t j = bit >> 3, sft = bit & 7, cc = sft & 3, half = sft >> 2;
+                    long long qv = std::isfinite(d) ? std::llrint(std::ldexp(d, exp2v - (int) sft)) : 0;
+                    for (uint32_t dg = 0; dg < 8; ++dg) {
+                        const long long d8 = ((qv + 128) & 255) - 128;
+                        qv = (qv - d8) >> 8;
+                        frags[q][((size_t) st * 32 + 4 * dg + cc) * 2 + half] |= ((uint32_t) (uint8_t) (int8_t) d8) << (8 * j);
+                    }
+                }
+            }
+            for (uint32_t b = 0; b < n_blocks; ++b) {
+                double acc = 0.0;
+                for (uint32_t x = block_offsets[b]; x < block_offsets[b + 1]; ++x) {
+                    const uint32_t m = block_markers[x];
+                    acc += vf[2 * (size_t) m] - (e->has_centre ? e->centre[m] : 0.0);
+                }
+                bases[q][b] = acc;
+            }
+            char* p = dbase + hdr + per_set * q;
+            GSB_CUDA_TRY(cudaMemcpyAsync(p, frags[q].data(), frag_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            GSB_CUDA_TRY(cudaMemcpyAsync(p + frag_bytes, bases[q].data(), base_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            sp.bfrag[q] = (const uint2*) p;
+            sp.base[q] = (const double*) (p + frag_bytes);
+        }
+        // individuals in slabs: the device output of `sets` matrices stays bounded
+        const size_t slab = device_out ? (size_t) n : std::max<size_t>(8, slab_rows / sets / 8 * 8);
+        const size_t slab_bytes = slab * 2 * (size_t) n_blocks * sizeof(double);
+        if (!device_out) GSB_TRY(ctx->s_eval[1].ensure(slab_bytes * sets));
+        for (uint32_t done = 0; done < n; done += (uint32_t) slab) {
+            const uint32_t cnt = (uint32_t) std::min<size_t>(slab, n - done);
+            for (uint32_t q = 0; q < sets; ++q) {
+                sp.out[q] = device_out ? outs[q0 + q] : (double*) ((char*) ctx->s_eval[1].ptr + slab_bytes * q);
+                GSB_CUDA_TRY(cudaMemsetAsync(sp.out[q], 0, (size_t) cnt * 2 * n_blocks * sizeof(double), ctx->stream));   // empty blocks read 0
+            }
+            const uint64_t warps = (uint64_t) ((cnt + 7) / 8) * n_ranges;
+            const unsigned grid = (unsigned) ((warps + kLocalWarps - 1) / kLocalWarps);
+            const uint2* d_steps = (const uint2*) dbase;
+            const uint32_t* d_ranges = (const uint32_t*) (dbase + (size_t) n_steps * sizeof(uint2));
+#define GSB_LOCAL_LAUNCH(S) local_gebv_digits_kernel<S><<<grid, kLocalWarps * 32, 0, ctx->stream>>>( \
+                ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows + done, cnt, n_blocks, d_steps, d_ranges, n_ranges, sp)
+            switch (sets) {
+                case 1: GSB_LOCAL_LAUNCH(1); break;
+                case 2: GSB_LOCAL_LAUNCH(2); break;
+                case 3: GSB_LOCAL_LAUNCH(3); break;
+                default: GSB_LOCAL_LAUNCH(4); break;
+            }
+#undef GSB_LOCAL_LAUNCH
+            ++ctx->launches;
+            GSB_CUDA_TRY(cudaGetLastError());
+            if (!device_out)
+                for (uint32_t q = 0; q < sets; ++q)
+                    GSB_CUDA_TRY(cudaMemcpyAsync(outs[q0 + q] + (size_t) done * 2 * n_blocks, sp.out[q],
+                                                 (size_t) cnt * 2 * n_blocks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+        GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));     // frags/bases go out of scope
+    }
+    return GSB200_OK;
+}
+
+int gsb200_local_gebv_multi(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t n_blocks,
+                            const uint32_t* block_offsets, const uint32_t* block_markers,
+                            uint32_t n_effect_sets, const uint32_t* eff_indexes, double* const* outs) {
+    return local_gebv_multi_impl(ctx, n, rows, n_blocks, block_offsets, block_markers, n_effect_sets, eff_indexes, outs, false);
+}
+
+int gsb200_local_gebv_multi_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t n_blocks,
+                                const uint32_t* block_offsets, const uint32_t* block_markers,
+                                uint32_t n_effect_sets, const uint32_t* eff_indexes, double* const* d_outs) {
+    return local_gebv_multi_impl(ctx, n, rows, n_blocks, block_offsets, block_markers, n_effect_sets, eff_indexes, d_outs, true);
+}
+
+int gsb200_local_gebv(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t n_blocks,
+                      const uint32_t* block_offsets, const uint32_t* block_markers,
+                      uint32_t eff_index, double* out) {
+    double* outs[1] = { out };
+    return local_gebv_multi_impl(ctx, n, rows, n_blocks, block_offsets, block_markers, 1, &eff_index, outs, false);
 }
 
 int gsb200_allele_counts(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, char allele, int out_kind, void* out) {

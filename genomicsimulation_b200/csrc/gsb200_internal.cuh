@@ -104,6 +104,7 @@ struct DeviceEffects {
     double  base_all = 0.0;           // planes == 1: sum_m 2 * value_all[m][0]
     uint32_t* d_digit_frag = nullptr; // planes == 1: fixed-point digits of delta as mma B fragments
     double  digit_scale = 1.0;        // value of one fixed-point unit
+    std::vector<double> h_value_first; // host copy of d_value_first (local-GEBV digit fragments are per call)
     void release();
 };
 

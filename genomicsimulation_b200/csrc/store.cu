@@ -104,21 +104,17 @@ __global__ void move_rows_kernel(uint32_t* store, uint32_t* dense, const uint32_
     if (to_store) *a = *b; else *b = *a;
 }
 
-int move_rows(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, void* dense, int to_store, const char* what) {
+int move_rows(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, void* dense, int to_store, const char* what) {
     GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
     if (n == 0) return GSB200_OK;
-    GSB_REQUIRE(dense != nullptr, GSB200_ERR_ARG, "%s: null device buffer", what);
+    GSB_REQUIRE(dense != nullptr && d_rows != nullptr, GSB200_ERR_ARG, "%s: null device buffer", what);
     GSB_REQUIRE(((uintptr_t) dense & 15) == 0, GSB200_ERR_ARG, "%s: device buffer must be 16-byte aligned", what);
-    GSB_TRY(check_rows(ctx, n, rows, what));
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
-    uint32_t* d_rows = nullptr;
-    GSB_TRY(upload_u32(ctx, ctx->s_rows[3], rows, n, &d_rows));
     const uint64_t threads = (uint64_t) n * (ctx->row_words() / 4);
     move_rows_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_store, (uint32_t*) dense, d_rows, n,
                                                                                   ctx->row_words(), to_store);
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
-    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return GSB200_OK;
 }
 
@@ -219,11 +215,35 @@ int gsb200_store_upload_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows,
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
     const uint32_t M = ctx->n_markers;
 
-    // 1. extend the dictionary with any symbol not seen before at its marker
+    // 1. extend the dictionary with any symbol not seen before at its marker.  Rows whose symbols
+    //    are all known (every row but the first few) are cleared by a vectorisable pass against
+    //    the two commonest symbols per marker; only rows that fail it take the slow scan.
     uint32_t planes = ctx->planes;
     bool changed = false;
+    std::vector<uint8_t> e0(2 * (size_t) M), e1(2 * (size_t) M);
+    auto refresh_expanded = [&]() {
+        for (uint32_t m = 0; m < M; ++m) {
+            const uint8_t* sym = &ctx->dict_sym[(size_t) m << ctx->planes];
+            const uint32_t nc = ctx->dict_n[m];
+            // a marker nobody uploaded yet matches nothing: both slots hold a value the row
+            // cannot equal in both... so force the slow scan by using two different sentinels
+            const uint8_t a0 = nc > 0 ? sym[0] : 0, a1 = nc > 1 ? sym[1] : a0;
+            e0[2 * (size_t) m] = e0[2 * (size_t) m + 1] = a0;
+            e1[2 * (size_t) m] = e1[2 * (size_t) m + 1] = a1;
+        }
+    };
+    refresh_expanded();
+    bool any_empty = false;
+    for (uint32_t m = 0; m < M && !any_empty; ++m) any_empty = ctx->dict_n[m] == 0;
     for (uint32_t i = 0; i < n; ++i) {
         const uint8_t* g = (const uint8_t*) chars + (size_t) i * 2 * M;
+        if (!any_empty) {
+            uint8_t bad = 0;
+            const size_t len = 2 * (size_t) M;
+            for (size_t j = 0; j < len; ++j) bad |= (uint8_t) ((g[j] != e0[j]) & (g[j] != e1[j]));
+            if (!bad) continue;
+        }
+        bool row_changed = false;
         for (uint32_t m = 0; m < M; ++m) {
             for (uint32_t h = 0; h < 2; ++h) {
                 const uint8_t a = g[2 * (size_t) m + h];
@@ -239,8 +259,14 @@ int gsb200_store_upload_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows,
                 }
                 ctx->dict_sym[((size_t) m << planes) + nc] = a;
                 ctx->dict_n[m] = (uint16_t) (nc + 1);
-                changed = true;
+                row_changed = true;
             }
+        }
+        if (row_changed) {
+            changed = true;
+            refresh_expanded();
+            any_empty = false;
+            for (uint32_t m = 0; m < M && !any_empty; ++m) any_empty = ctx->dict_n[m] == 0;
         }
     }
     if (changed) { ctx->dict_dirty = true; ++ctx->dict_version; }
@@ -297,12 +323,12 @@ int gsb200_store_download_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* row
     return GSB200_OK;
 }
 
-int gsb200_store_gather_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, void* d_dense) {
-    return move_rows(ctx, n, rows, d_dense, 0, "gsb200_store_gather_rows_dev");
+int gsb200_store_gather_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, void* d_dense) {
+    return move_rows(ctx, n, d_rows, d_dense, 0, "gsb200_store_gather_rows_dev");
 }
 
-int gsb200_store_scatter_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const void* d_dense) {
-    return move_rows(ctx, n, rows, (void*) d_dense, 1, "gsb200_store_scatter_rows_dev");
+int gsb200_store_scatter_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, const void* d_dense) {
+    return move_rows(ctx, n, d_rows, (void*) d_dense, 1, "gsb200_store_scatter_rows_dev");
 }
 
 int gsb200_store_change_symbol(gsb200_ctx* ctx, uint32_t marker, char from, char to) {

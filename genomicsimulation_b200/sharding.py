@@ -148,7 +148,10 @@ class EngineBackend:
         rows = np.ascontiguousarray(rows, dtype=np.uint32)
         t = torch.empty((len(rows), self.row_bytes), dtype=torch.uint8, device="cuda")
         if len(rows):
-            self._check(self.E.gsb200_store_gather_rows_dev(self.ctx, len(rows), rows.ctypes.data, t.data_ptr()))
+            d_rows = torch.from_numpy(rows.astype(np.int32)).cuda()
+            torch.cuda.current_stream().synchronize()
+            self._check(self.E.gsb200_store_gather_rows_dev(self.ctx, len(rows), d_rows.data_ptr(), t.data_ptr()))
+            self._check(self.E.gsb200_synchronize(self.ctx))
         return t
 
     def adopt_rows(self, packed):
@@ -156,7 +159,10 @@ class EngineBackend:
         torch.cuda.current_stream().synchronize()
         rows = self._take(packed.shape[0])
         if len(rows):
-            self._check(self.E.gsb200_store_scatter_rows_dev(self.ctx, len(rows), rows.ctypes.data, packed.data_ptr()))
+            d_rows = torch.from_numpy(rows.astype(np.int32)).cuda()
+            torch.cuda.current_stream().synchronize()
+            self._check(self.E.gsb200_store_scatter_rows_dev(self.ctx, len(rows), d_rows.data_ptr(), packed.data_ptr()))
+            self._check(self.E.gsb200_synchronize(self.ctx))
         return rows
 
     def cross(self, p1_rows, p2_rows, map_index, seed, stream, first_unit):

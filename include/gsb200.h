@@ -80,9 +80,10 @@ int  gsb200_store_upload_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows
 int  gsb200_store_download_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, char* chars);
 /* Packed rows <-> a dense DEVICE buffer of n x gsb200_store_row_bytes() bytes (16-byte aligned):
  * the send/receive side of the per-generation parent-pool broadcast over NCCL (no reference
- * counterpart: the reference is single-process). Synchronous on the context stream. */
-int  gsb200_store_gather_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, void* d_dense);
-int  gsb200_store_scatter_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const void* d_dense);
+ * counterpart: the reference is single-process). `d_rows` is a DEVICE array; asynchronous on the
+ * context stream, so that a collective enqueued on that stream needs no host synchronisation. */
+int  gsb200_store_gather_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, void* d_dense);
+int  gsb200_store_scatter_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, const void* d_dense);
 /* gsc_change_allele_symbol (core.c:1029-1100) for one marker (marker == UINT32_MAX: all). */
 int  gsb200_store_change_symbol(gsb200_ctx* ctx, uint32_t marker, char from, char to);
 /* dictionary of one marker: up to 2^planes symbols, returns how many are defined */
@@ -175,6 +176,18 @@ int  gsb200_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32
 int  gsb200_local_gebv(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t n_blocks,
                        const uint32_t* block_offsets, const uint32_t* block_markers,
                        uint32_t eff_index, double* out);
+/* The same for several effect sets in one pass over the genotypes (the reference computes one set
+ * per call, core.c:9943-9961; see.local.GEBVs called once per set maps onto one call here):
+ * outs[s] receives the matrix of eff_indexes[s]. */
+int  gsb200_local_gebv_multi(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t n_blocks,
+                             const uint32_t* block_offsets, const uint32_t* block_markers,
+                             uint32_t n_effect_sets, const uint32_t* eff_indexes, double* const* outs);
+/* ... with the output matrices left on the DEVICE (d_outs[s]: (2n) x n_blocks doubles each), for
+ * consumers that keep working there; only for blocks that are contiguous, ascending,
+ * non-overlapping marker ranges on a one-plane store (GSB200_ERR_UNSUPPORTED otherwise). */
+int  gsb200_local_gebv_multi_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t n_blocks,
+                                 const uint32_t* block_offsets, const uint32_t* block_markers,
+                                 uint32_t n_effect_sets, const uint32_t* eff_indexes, double* const* d_outs);
 
 /* gsc_calculate_allele_counts (core.c:9636-9667). out is row-major n x n_markers. */
 enum { GSB200_COUNTS_F64 = 0, GSB200_COUNTS_I32 = 1, GSB200_COUNTS_U8 = 2 };

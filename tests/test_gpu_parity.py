@@ -250,3 +250,31 @@ def test_empty_and_invalid_requests():
     s.delete_group(1)
     assert s.n_genotypes == 1203 and s.group_indexes(g).tolist() == list(range(1203))
     s.close()
+
+
+def test_local_gebv_many_effect_sets_in_one_pass():
+    """gsb200_local_gebv_multi (several effect sets per pass over the genotypes, the dense-contraction
+    path of BASELINE.json configs[4]) against the oracle's one-set-at-a-time calls, with centres."""
+    n_sets = 6
+    ds = datasets.synthetic(40, 3000, 6, 130.0, seed=17, spacing="random", n_effect_sets=n_sets)
+    rng = np.random.default_rng(3)
+    ds["effects"][2]["centre"] = rng.standard_normal(3000) * 0.1
+    p = port.PortSim.from_dataset(ds)
+    s = engine_from(ds)
+    off, mk = p.blocks_evenlength(7, 0, n_chr=6)
+    rows = np.arange(40, dtype=np.uint32)
+    nb = len(off) - 1
+    outs = [np.zeros((80, nb)) for _ in range(n_sets)]
+    ptrs = (C.c_void_p * n_sets)(*[o.ctypes.data for o in outs])
+    effs = np.arange(n_sets, dtype=np.uint32)
+    off32, mk32 = off.astype(np.uint32), mk.astype(np.uint32)
+    st = s.E.gsb200_local_gebv_multi(s.ctx, 40, rows.ctypes.data, nb, off32.ctypes.data, mk32.ctypes.data,
+                                     n_sets, effs.ctypes.data, ptrs)
+    assert st == 0, s.E.gsb200_last_error()
+    for e in range(n_sets):
+        want = p.calculate_local_bvs(1, off, mk, e)
+        bv_close(outs[e], want, scale=np.abs(want).mean())
+        single = s.calculate_local_bvs(1, off, mk, e + 1)
+        np.testing.assert_array_equal(single, outs[e])
+    p.close()
+    s.close()
