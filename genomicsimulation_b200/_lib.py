@@ -73,6 +73,7 @@ ENGINE_SYMBOLS = {
     "gsb200_effects_set": (I32, [VP, U32, VP, VP, VP, VP]),
     "gsb200_effects_delete": (I32, [VP, U32]),
     "gsb200_cross": (I32, [VP, U32, VP, VP, U32, U32, VP, C.POINTER(Draws)]),
+    "gsb200_cross_random_pairs": (I32, [VP, U32, U32, VP, U32, VP, U32, U32, U32, VP, U32, C.POINTER(Draws), VP, VP]),
     "gsb200_cross_dev": (I32, [VP, U32, VP, VP, U32, U32, VP, C.POINTER(Draws)]),
     "gsb200_cross_dev_status": (I32, [VP]),
     "gsb200_self_n_times": (I32, [VP, U32, VP, U32, U32, VP, C.POINTER(Draws)]),
@@ -124,6 +125,7 @@ HOST_SYMBOLS = {
     "gsb_make_clones": (UINT, [VP, UINT, C.c_bool, GenOptions]),
     "gsb_make_all_unidirectional_crosses": (UINT, [VP, UINT, UINT, GenOptions]),
     "gsb_calculate_bvs": (DecimalMatrix, [VP, UINT, UINT]),
+    "gsb_get_group_bvs": (UINT, [VP, UINT, UINT, UINT, VP]),
     "gsb_calculate_allele_counts": (DecimalMatrix, [VP, UINT, C.c_char]),
     "gsb_calculate_local_bvs": (DecimalMatrix, [VP, UINT, MarkerBlocks, UINT]),
     "gsb_create_evenlength_blocks_each_chr": (MarkerBlocks, [VP, UINT, UINT]),

@@ -482,6 +482,35 @@ __global__ void export_positions_kernel(const MeiosisArgs a, const uint32_t* k_a
     for (uint32_t j = 0; j < k; ++j) dst[j] = draw_position(a.draws, a.draws.first_unit + unit_local, gam, c, 0, j);
 }
 
+// ------------------------------------------------------------------ random parent pairs on the device
+// gsc_helper_parentchooser_cross_randomly / _between with no usage cap (core.c:8364-8402,
+// 8594-8631): parent a = round(u * (n1 - 1)); parent b likewise over its group, redrawn while
+// it collides with a when both come from the same group (gsc_randomdraw_replacementrules,
+// core.c:8556-8581).  Draws: the native stream with chromosome index 0xffffffff, indexed by cross.
+__global__ void random_pairs_kernel(uint32_t n_crosses, uint32_t family_size, const uint32_t* __restrict__ members1, uint32_t n1,
+                                    const uint32_t* __restrict__ members2, uint32_t n2, uint32_t distinct, DrawView draws,
+                                    uint32_t first_out_row, uint32_t* __restrict__ p1_rows, uint32_t* __restrict__ p2_rows,
+                                    uint32_t* __restrict__ picked1, uint32_t* __restrict__ picked2, uint32_t* __restrict__ out_rows) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_crosses) return;
+    const uint64_t unit = draws.first_unit + i;
+    uint4 r = draw_block(draws, unit, 0, 0xffffffffu, 0);
+    const uint32_t a = (uint32_t) rint(u01(r.x, r.y) * (double) (n1 - 1));
+    uint32_t b = (uint32_t) rint(u01(r.z, r.w) * (double) (n2 - 1));
+    for (uint32_t blk = 1; distinct && b == a && blk < 4096; ++blk) {
+        r = draw_block(draws, unit, 0, 0xffffffffu, blk);
+        b = (uint32_t) rint(u01(r.x, r.y) * (double) (n2 - 1));
+        if (b == a) b = (uint32_t) rint(u01(r.z, r.w) * (double) (n2 - 1));
+    }
+    const uint32_t ra = members1[a], rb = members2[b];
+    for (uint32_t f = 0; f < family_size; ++f) {
+        const uint64_t o = (uint64_t) i * family_size + f;
+        p1_rows[o] = ra; p2_rows[o] = rb;
+        picked1[o] = a; picked2[o] = b;
+        if (out_rows) out_rows[o] = first_out_row + (uint32_t) o;
+    }
+}
+
 // ------------------------------------------------------------------ clone
 
 __global__ void copy_rows_kernel(uint32_t* store, const uint32_t* src_rows, const uint32_t* dst_rows, uint32_t n, uint64_t row_words) {
@@ -790,6 +819,48 @@ int gsb200_cross_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1_rows
     GSB_REQUIRE(d_parent1_rows && d_parent2_rows && d_out_rows, GSB200_ERR_ARG, "gsb200_cross_dev: null row array");
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
     return cross_impl(ctx, n, d_parent1_rows, d_parent2_rows, map1, map2, d_out_rows, draws, false, "gsb200_cross_dev");
+}
+
+int gsb200_cross_random_pairs(gsb200_ctx* ctx, uint32_t n_crosses, uint32_t family_size,
+                              const uint32_t* member_rows1, uint32_t n1, const uint32_t* member_rows2, uint32_t n2,
+                              uint32_t map1, uint32_t map2, const uint32_t* out_rows, uint32_t first_out_row,
+                              const gsb200_draws* draws, uint32_t* picked1, uint32_t* picked2) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    const char* what = "gsb200_cross_random_pairs";
+    const uint64_t n64 = (uint64_t) n_crosses * family_size;
+    if (n64 == 0) return GSB200_OK;
+    GSB_REQUIRE(n64 < (1ull << 31), GSB200_ERR_ARG, "%s: too many offspring in one call", what);
+    const uint32_t n = (uint32_t) n64;
+    GSB_REQUIRE(draws && draws->mode == GSB200_DRAWS_PHILOX, GSB200_ERR_ARG, "%s: needs PHILOX draws", what);
+    const bool same = member_rows2 == nullptr;
+    GSB_REQUIRE(member_rows1 && n1 >= 1 && (same ? n1 >= 2 : n2 >= 1), GSB200_ERR_ARG, "%s: not enough candidate parents", what);
+    GSB_TRY(check_rows(ctx, n1, member_rows1, what));
+    if (!same) GSB_TRY(check_rows(ctx, n2, member_rows2, what));
+    if (out_rows) GSB_TRY(check_rows(ctx, n, out_rows, what));
+    else GSB_REQUIRE((uint64_t) first_out_row + n <= ctx->capacity, GSB200_ERR_ARG, "%s: offspring rows beyond the store capacity", what);
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint32_t *d_m1, *d_m2, *d_out = nullptr;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], member_rows1, n1, &d_m1));
+    if (same) d_m2 = d_m1; else GSB_TRY(upload_u32(ctx, ctx->s_rows[1], member_rows2, n2, &d_m2));
+    if (out_rows) GSB_TRY(upload_u32(ctx, ctx->s_rows[2], out_rows, n, &d_out));
+    else { GSB_TRY(ctx->s_rows[2].ensure((size_t) n * sizeof(uint32_t))); d_out = (uint32_t*) ctx->s_rows[2].ptr; }
+    GSB_TRY(ctx->s_rows[3].ensure((size_t) 4 * n * sizeof(uint32_t)));
+    uint32_t* d_p1 = (uint32_t*) ctx->s_rows[3].ptr;
+    uint32_t *d_p2 = d_p1 + n, *d_k1 = d_p2 + n, *d_k2 = d_k1 + n;
+    DrawView dv;
+    GSB_TRY(make_draw_view(draws, &dv, what));
+    random_pairs_kernel<<<grid_for(n_crosses, 256), 256, 0, ctx->stream>>>(n_crosses, family_size, d_m1, n1, d_m2, same ? n1 : n2,
+        same ? 1u : 0u, dv, first_out_row, d_p1, d_p2, d_k1, d_k2, out_rows ? nullptr : d_out);
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    // the offspring of cross i are units i*family_size .. of the same stream
+    gsb200_draws per_offspring = *draws;
+    per_offspring.first_unit = draws->first_unit * family_size;
+    GSB_TRY(cross_impl(ctx, n, d_p1, d_p2, map1, map2, d_out, &per_offspring, true, what));
+    if (picked1) GSB_CUDA_TRY(cudaMemcpyAsync(picked1, d_k1, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (picked2) GSB_CUDA_TRY(cudaMemcpyAsync(picked2, d_k2, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GSB200_OK;
 }
 
 int gsb200_cross_dev_status(gsb200_ctx* ctx) {

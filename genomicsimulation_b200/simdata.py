@@ -220,6 +220,15 @@ class SimData:
     def calculate_bvs(self, group, eff_id):
         return self._take(self.L.gsb_calculate_bvs(self.d, group, eff_id)).reshape(-1)
 
+    def get_group_bvs(self, group, eff_id, out=None):
+        """gsc_get_group_bvs: GEBVs into a caller-owned array (what see.GEBVs does, r-wrappers.c:795-813)."""
+        n = self.group_size(group)
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        got = self.L.gsb_get_group_bvs(self.d, group, eff_id, min(n, len(out)), _p(out))
+        self._check()
+        return out[:got]
+
     def calculate_allele_counts(self, group, allele):
         a = allele if isinstance(allele, bytes) else allele.encode()
         return self._take(self.L.gsb_calculate_allele_counts(self.d, group, C.c_char(a)))

@@ -146,6 +146,18 @@ int  gsb200_doubled_haploid(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent_
 /* gsc_generate_clone (core.c:8047-8055). */
 int  gsb200_clone(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent_rows, const uint32_t* out_rows);
 
+/* gsc_make_random_crosses / _between with no usage cap, parents chosen ON THE DEVICE
+ * (gsc_helper_parentchooser_cross_randomly core.c:8364-8402, _between 8594-8631, pick rule
+ * round(u * (n - 1)) redrawn on collision, core.c:8556-8581): n_crosses pairs, family_size
+ * offspring each.  member_rows2 == NULL: both parents from group 1 and distinct.  out_rows ==
+ * NULL: offspring go to rows first_out_row, first_out_row + 1, ...  picked1/2 (host, may be NULL)
+ * receive, per offspring, the positions of its parents in member_rows1/2 — what the host needs for
+ * pedigrees.  PHILOX draws only; nothing but the candidate lists and the picks crosses PCIe. */
+int  gsb200_cross_random_pairs(gsb200_ctx* ctx, uint32_t n_crosses, uint32_t family_size,
+                               const uint32_t* member_rows1, uint32_t n1, const uint32_t* member_rows2, uint32_t n2,
+                               uint32_t map1, uint32_t map2, const uint32_t* out_rows, uint32_t first_out_row,
+                               const gsb200_draws* draws, uint32_t* picked1, uint32_t* picked2);
+
 /* Device-pointer variants for callers that keep index arrays resident (benchmarks,
  * multi-GPU generation loops).  PHILOX draws only.  Asynchronous on the context stream. */
 int  gsb200_cross_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1_rows, const uint32_t* d_parent2_rows,

@@ -17,10 +17,12 @@
  *                     Rf_rpois in the package; a replay tape in the parity tests) in exactly
  *                     the reference's order, then shipped to the GPU as a tape.  Results are
  *                     bit-identical to the reference's for the same stream.
- *   GSB_DRAWS_NATIVE  parent picks come from the host source (same order as the reference's
- *                     picks); meiosis draws come from the device Philox stream keyed by
- *                     (seed, call number) and indexed by offspring — nothing but row indexes
- *                     crosses PCIe.
+ *   GSB_DRAWS_NATIVE  meiosis draws come from the device Philox stream keyed by (seed, call
+ *                     number) and indexed by offspring.  Random crosses without a usage cap
+ *                     draw their parent pairs from the same stream on the device (same pick
+ *                     rule as core.c:8556-8581) — only the candidate list goes up and the
+ *                     picked pairs (for pedigrees) come down; capped random crosses pick on
+ *                     the host from the host source, in the reference's order.
  */
 #ifndef GSB200_GSC_H
 #define GSB200_GSC_H
@@ -129,6 +131,7 @@ gsb_GroupNum gsb_make_all_unidirectional_crosses(gsb_SimData* d, gsb_GroupNum fr
 
 /* ---- evaluation (core.c:9463-10090) */
 gsb_DecimalMatrix gsb_calculate_bvs(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID effID);
+unsigned int gsb_get_group_bvs(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID effID, unsigned int group_size, double* output);
 gsb_DecimalMatrix gsb_calculate_allele_counts(gsb_SimData* d, gsb_GroupNum group, char allele);
 gsb_DecimalMatrix gsb_calculate_local_bvs(gsb_SimData* d, gsb_GroupNum group, gsb_MarkerBlocks b, gsb_EffectID effID);
 gsb_MarkerBlocks gsb_create_evenlength_blocks_each_chr(const gsb_SimData* d, gsb_MapID mapid, unsigned int n);

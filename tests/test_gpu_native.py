@@ -179,3 +179,41 @@ def test_native_scheme_through_the_api():
     ga, gb = sim.export_group(a)["genotypes"], sim3.export_group(b)["genotypes"]
     assert ga.shape == gb.shape
     sim.close(); sim2.close(); sim3.close()
+
+
+def test_device_side_parent_choice():
+    """gsb_make_random_crosses(_between) in native mode with no cap draw the pairs on the device
+    (gsb200_cross_random_pairs): pick rule, distinct parents, pedigrees, family members share a pair,
+    uniform use of the candidates (core.c:8556-8581: the end points get half weight)."""
+    ds = datasets.synthetic(30, 800, 4, 100.0, seed=12)
+    sim = make_sim(ds)
+    sim.use_native_draws(5)
+    g = sim.make_random_crosses(1, 20000, family_size=2)
+    x = sim.export_group(g)
+    assert len(x["ids"]) == 40000
+    p1, p2 = x["ped1"].astype(int), x["ped2"].astype(int)
+    assert (p1 != p2).all() and p1.min() >= 1 and p1.max() <= 30
+    assert (p1[0::2] == p1[1::2]).all() and (p2[0::2] == p2[1::2]).all()
+    counts = np.bincount(p1[0::2], minlength=31)[1:]
+    expect = np.full(30, 20000 / 29.0)
+    expect[[0, 29]] /= 2                                   # round(u * 29): half-width end bins
+    assert stats.chisquare(counts, expect * counts.sum() / expect.sum()).pvalue > 1e-4
+    founders = ds["genotypes"]
+    geno = x["genotypes"]
+    for i in range(0, 40000, 997):
+        a, b = founders[p1[i] - 1], founders[p2[i] - 1]
+        assert np.all((geno[i, 0::2] == a[0::2]) | (geno[i, 0::2] == a[1::2]))
+        assert np.all((geno[i, 1::2] == b[0::2]) | (geno[i, 1::2] == b[1::2]))
+    # siblings share parents but not gametes
+    assert (geno[0] != geno[1]).any()
+    # between two groups: parents from the right groups, recycled rows after a delete
+    sim.delete_group(g)
+    h = sim.make_group_from(np.arange(10, 30))
+    b = sim.make_random_crosses_between(1, h, 5000)
+    y = sim.export_group(b, genotypes=False)
+    assert y["ped1"].max() <= 10 and y["ped2"].min() >= 11
+    # no pedigree tracking: no picks come back, ids still handed out
+    c = sim.make_random_crosses(1, 100, track_pedigree=False)
+    z = sim.export_group(c, genotypes=False)
+    assert (z["ped1"] == 0).all() and len(set(z["ids"].tolist())) == 100
+    sim.close()
