@@ -202,7 +202,11 @@ def engine_arm(a):
     d_p2 = torch.from_numpy(p2.astype(np.int32)).cuda()
     d_out = torch.arange(F, F + n, dtype=torch.int32, device="cuda")
     d_bv = torch.empty(n, dtype=torch.float64, device="cuda")
-    pool = torch.empty(F * row_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
+    # the founders occupy rows 0..F-1 of the store, contiguously: the parent pool is broadcast in place
+    class _StoreView:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    pool = torch.as_tensor(_StoreView(E.gsb200_store_device_ptr(ctx), F * row_bytes), device="cuda") if world > 1 else None
     all_bv = torch.empty(world * n, dtype=torch.float64, device="cuda") if world > 1 else None
     torch.cuda.synchronize()
 
@@ -213,7 +217,6 @@ def engine_arm(a):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kernel_ms = {"cross": [], "gebv": []}
 
-    d_founder_rows = torch.arange(0, F, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
 
     def step(i, timed):
@@ -221,12 +224,10 @@ def engine_arm(a):
         # NCCL orders itself against it with events, so the step has no host synchronisation
         with torch.cuda.stream(ext):
             if world > 1:
-                # generation boundary: rank 0's parent pool to everyone over NVLink
-                if rank == 0:
-                    check(E.gsb200_store_gather_rows_dev(ctx, F, d_founder_rows.data_ptr(), pool.data_ptr()))
+                # generation boundary: rank 0's parent pool to everyone over NVLink, straight from
+                # and into the packed stores (scattered pools go through gsb200_store_gather/scatter_rows_dev,
+                # genomicsimulation_b200/sharding.py)
                 dist.broadcast(pool, 0)
-                if rank != 0:
-                    check(E.gsb200_store_scatter_rows_dev(ctx, F, d_founder_rows.data_ptr(), pool.data_ptr()))
             dr = Draws(mode=0, seed=20261019, stream=i, first_unit=rank * n)
             e0, e1, e2 = ev(), ev(), ev()
             e0.record(ext)

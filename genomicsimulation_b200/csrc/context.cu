@@ -40,7 +40,7 @@ void Scratch::release() {
 }
 
 void DeviceMap::release() {
-    void* ptrs[] = { d_chr, d_dists, d_marker_index, d_bucket, d_chunk_chr, d_chunk_start };
+    void* ptrs[] = { d_chr, d_dists, d_marker_index, d_bucket, d_chunk_chr, d_chunk_start, d_uncovered };
     for (void* p : ptrs) if (p) cudaFree(p);
     *this = DeviceMap();
 }
@@ -138,6 +138,7 @@ void gsb200_destroy(gsb200_ctx* ctx) {
     for (auto& s : ctx->s_plan) s.release();
     for (auto& s : ctx->s_eval) s.release();
     for (auto& s : ctx->s_chain) s.release();
+    ctx->s_null.release();
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->d_store) cudaFree(ctx->d_store);
     if (ctx->d_dict_sym) cudaFree(ctx->d_dict_sym);
@@ -248,6 +249,8 @@ int gsb200_map_set(gsb200_ctx* ctx, uint32_t map_index, uint32_t n_chr, const do
     GSB_TRY(to_device(v_bucket, &m.d_bucket));
     GSB_TRY(to_device(v_chunk_chr, &m.d_chunk_chr));
     GSB_TRY(to_device(v_chunk_start, &m.d_chunk_start));
+    for (uint32_t mk = 0; mk < ctx->n_markers; ++mk) if (!covered[mk]) m.h_uncovered.push_back(mk);
+    GSB_TRY(to_device(m.h_uncovered, &m.d_uncovered));
     m.present = true;
     return GSB200_OK;
 }

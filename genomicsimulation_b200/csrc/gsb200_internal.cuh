@@ -82,6 +82,9 @@ struct DeviceMap {
     // general path: chunk k covers positions [chunk_start[k], chunk_start[k]+32) of chromosome chunk_chr[k]
     uint32_t* d_chunk_chr = nullptr;
     uint32_t* d_chunk_start = nullptr;
+    // markers no linkage group covers: gametes leave them at the reference's '\0' (core.c:75)
+    std::vector<uint32_t> h_uncovered;
+    uint32_t* d_uncovered = nullptr;
     void release();
 };
 
@@ -138,12 +141,15 @@ struct gsb200_ctx {
     gsb::Scratch s_plan[8];         // meiosis draw buffers
     gsb::Scratch s_eval[4];
     gsb::Scratch s_chain[2];        // ping-pong rows of chained selfing
+    gsb::Scratch s_null;            // per marker: the code that decodes to '\0' (uncovered markers)
+    uint64_t null_built_for = ~0ull;
 
     uint64_t row_words() const { return (uint64_t) 2 * planes * plane_words; }
 };
 
 namespace gsb {
 int sync_dictionary(gsb200_ctx* ctx);                       // store.cu
+int ensure_symbol(gsb200_ctx* ctx, uint32_t marker, uint8_t symbol, uint32_t* code);   // store.cu
 int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff);    // evaluate.cu
 int upload_u32(gsb200_ctx* ctx, Scratch& s, const uint32_t* host, size_t n, uint32_t** out);
 int check_rows(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const char* what);

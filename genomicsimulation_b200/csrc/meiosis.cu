@@ -452,6 +452,25 @@ __global__ void splice_general_kernel(const MeiosisArgs a, const uint32_t gam) {
     }
 }
 
+// Markers the gamete's map does not cover are never written by the reference and keep the zeroed
+// slot's '\0' (core.c:75): write the code that decodes to '\0' there (rows were zeroed first).
+__global__ void fill_uncovered_kernel(const MeiosisArgs a, const uint32_t gam, const uint32_t* __restrict__ uncovered, uint32_t n_unc,
+                                      const uint8_t* __restrict__ null_code) {
+    const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (uint64_t) a.n_units * n_unc) return;
+    const uint32_t unit_local = (uint32_t) (tid / n_unc), m = uncovered[tid % n_unc];
+    const uint32_t code = null_code[m];
+    if (code == 0) return;
+    const uint32_t dst_row = a.dst_rows ? a.dst_rows[unit_local] : unit_local;
+    uint32_t* dst = a.dst_base + (uint64_t) dst_row * a.row_words;
+    for (uint32_t p = 0; p < a.planes; ++p) {
+        if (!((code >> p) & 1u)) continue;
+        uint32_t* out = dst + (uint64_t) (gam * a.planes + p) * a.plane_words + (m >> 5);
+        atomicOr(out, 1u << (m & 31));
+        if (a.doubled) atomicOr(out + a.planes * a.plane_words, 1u << (m & 31));
+    }
+}
+
 // ------------------------------------------------------------------ native draws -> tape layout
 
 // entry e of unit u: gamete = e >= n_chr0, chromosome = e - (gamete ? n_chr0 : 0)
@@ -554,13 +573,27 @@ int check_flag(gsb200_ctx* ctx, int* value) {
     return GSB200_OK;
 }
 
-// Uncovered markers keep the zero bits of a fresh slot, which must decode to the reference's
-// '\0' (core.c:75): refuse maps with holes unless code 0 is '\0' (or undefined) there.
-int check_coverage(gsb200_ctx* ctx, const DeviceMap& m, const char* what) {
+// A map with holes leaves the uncovered markers of a gamete at '\0' (core.c:75).  Make sure every
+// such marker has a code for '\0' (this may widen the store, so it runs before anything reads the
+// store's geometry) and keep the per-marker code array on the device.
+int prepare_uncovered(gsb200_ctx* ctx, const DeviceMap& m) {
     if (m.covers_all) return GSB200_OK;
-    set_error("%s: the recombination map does not cover every marker; uncovered markers of the offspring would be "
-              "'\\0' in the reference (sim-operations.c:75) and this store cannot represent that yet", what);
-    return GSB200_ERR_UNSUPPORTED;
+    for (uint32_t mk : m.h_uncovered) {
+        uint32_t code;
+        GSB_TRY(ensure_symbol(ctx, mk, 0, &code));
+    }
+    if (ctx->null_built_for != ctx->dict_version || !ctx->s_null.ptr) {
+        std::vector<uint8_t> codes(ctx->n_markers, 0);
+        for (uint32_t mk = 0; mk < ctx->n_markers; ++mk) {
+            const uint8_t* sym = &ctx->dict_sym[(size_t) mk << ctx->planes];
+            for (uint32_t c = 0; c < ctx->dict_n[mk]; ++c) if (sym[c] == 0) { codes[mk] = (uint8_t) c; break; }
+        }
+        GSB_TRY(ctx->s_null.ensure(ctx->n_markers));
+        GSB_CUDA_TRY(cudaMemcpyAsync(ctx->s_null.ptr, codes.data(), ctx->n_markers, cudaMemcpyHostToDevice, ctx->stream));
+        GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->null_built_for = ctx->dict_version;
+    }
+    return GSB200_OK;
 }
 
 struct Batch {
@@ -612,7 +645,7 @@ int materialise_draws(gsb200_ctx* ctx, MeiosisArgs& a, uint64_t* n_positions_out
     return GSB200_OK;
 }
 
-int run_general(gsb200_ctx* ctx, MeiosisArgs a) {
+int run_general(gsb200_ctx* ctx, MeiosisArgs a, const DeviceMap* const* maps) {
     if (a.draws.mode == GSB200_DRAWS_PHILOX) {
         uint64_t n_pos = 0;
         GSB_TRY(materialise_draws(ctx, a, &n_pos));
@@ -622,6 +655,13 @@ int run_general(gsb200_ctx* ctx, MeiosisArgs a) {
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
     for (uint32_t gam = 0; gam < a.gametes_per_unit; ++gam) {
+        const uint32_t n_unc = (uint32_t) maps[gam]->h_uncovered.size();
+        if (n_unc) {
+            fill_uncovered_kernel<<<grid_for((uint64_t) a.n_units * n_unc, 256), 256, 0, ctx->stream>>>(
+                a, gam, maps[gam]->d_uncovered, n_unc, (const uint8_t*) ctx->s_null.ptr);
+            ++ctx->launches;
+            GSB_CUDA_TRY(cudaGetLastError());
+        }
         const uint64_t threads = (uint64_t) a.n_units * a.map[gam].n_chunks;
         if (threads == 0) continue;
         splice_general_kernel<<<grid_for(threads, 128), 128, 0, ctx->stream>>>(a, gam);
@@ -636,8 +676,6 @@ int run_general(gsb200_ctx* ctx, MeiosisArgs a) {
 // call is allowed to wait for that verdict (the `_dev` entry points defer it).
 int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
     if (b.n_units == 0) return GSB200_OK;
-    GSB_TRY(check_coverage(ctx, *b.map0, b.what));
-    if (b.gametes_per_unit > 1) GSB_TRY(check_coverage(ctx, *b.map1, b.what));
     MeiosisArgs a;
     a.src_base = b.src_base; a.src_rows0 = b.d_src0; a.src_rows1 = b.d_src1;
     a.dst_base = b.dst_base; a.dst_rows = b.d_dst;
@@ -698,7 +736,7 @@ int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
         // plan capacity exceeded somewhere in the batch: same draws, general kernel
     }
     GSB_REQUIRE(may_sync || !fast, GSB200_ERR_UNSUPPORTED, "%s: internal: unreachable", b.what);
-    return run_general(ctx, a);
+    return run_general(ctx, a, maps);
 }
 
 struct TapeUpload {
@@ -772,6 +810,8 @@ int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t
     const DeviceMap *m1, *m2;
     GSB_TRY(get_map(ctx, map1, &m1, what));
     GSB_TRY(get_map(ctx, map2, &m2, what));
+    GSB_TRY(prepare_uncovered(ctx, *m1));
+    GSB_TRY(prepare_uncovered(ctx, *m2));
     Batch b;
     b.what = what; b.n_units = n;
     b.src_base = ctx->d_store; b.d_src0 = d_p1; b.d_src1 = d_p2; b.dst_base = ctx->d_store; b.d_dst = d_out;
@@ -883,6 +923,7 @@ int gsb200_doubled_haploid(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent_r
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
     const DeviceMap* m;
     GSB_TRY(get_map(ctx, map, &m, what));
+    GSB_TRY(prepare_uncovered(ctx, *m));
     uint32_t *d1, *dout;
     GSB_TRY(upload_u32(ctx, ctx->s_rows[0], parent_rows, n, &d1));
     GSB_TRY(upload_u32(ctx, ctx->s_rows[2], out_rows, n, &dout));
@@ -916,6 +957,7 @@ int gsb200_self_n_times(gsb200_ctx* ctx, uint32_t n, const uint32_t* parent_rows
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
     const DeviceMap* m;
     GSB_TRY(get_map(ctx, map, &m, what));
+    GSB_TRY(prepare_uncovered(ctx, *m));
     uint32_t *d1, *dout;
     GSB_TRY(upload_u32(ctx, ctx->s_rows[0], parent_rows, n, &d1));
     GSB_TRY(upload_u32(ctx, ctx->s_rows[2], out_rows, n, &dout));

@@ -150,6 +150,24 @@ int widen_store(gsb200_ctx* ctx, uint32_t new_planes) {
 
 namespace gsb {
 
+// code of `symbol` at `marker`, added to the dictionary (widening the store if its codes are
+// used up) when it is not there yet
+int ensure_symbol(gsb200_ctx* ctx, uint32_t marker, uint8_t symbol, uint32_t* code) {
+    const uint32_t nc = ctx->dict_n[marker];
+    const uint8_t* sym = &ctx->dict_sym[(size_t) marker << ctx->planes];
+    for (uint32_t c = 0; c < nc; ++c) if (sym[c] == symbol) { *code = c; return GSB200_OK; }
+    if (nc == (1u << ctx->planes)) {
+        GSB_REQUIRE(ctx->planes < 8, GSB200_ERR_ARG, "store: more than 256 symbols at marker %u", marker);
+        GSB_TRY(widen_store(ctx, ctx->planes * 2));
+    }
+    ctx->dict_sym[((size_t) marker << ctx->planes) + nc] = symbol;
+    ctx->dict_n[marker] = (uint16_t) (nc + 1);
+    ctx->dict_dirty = true;
+    ++ctx->dict_version;
+    *code = nc;
+    return GSB200_OK;
+}
+
 int sync_dictionary(gsb200_ctx* ctx) {
     if (!ctx->dict_dirty && ctx->d_dict_sym) return GSB200_OK;
     const size_t bytes = (size_t) ctx->n_markers << ctx->planes;

@@ -278,3 +278,47 @@ def test_local_gebv_many_effect_sets_in_one_pass():
         np.testing.assert_array_equal(single, outs[e])
     p.close()
     s.close()
+
+
+def test_map_that_leaves_markers_uncovered():
+    """A recombination map loaded for a subset of the markers (core.c:5737-5751): gametes never write
+    the uncovered markers, which keep the zeroed slot's '\\0' (core.c:75) — here the store grows a
+    code for '\\0' at those markers."""
+    M = 300
+    ds = datasets.synthetic(8, M, 1, 100.0, seed=40)
+    idx_a = np.array([m for m in range(0, 100) if not 10 <= m < 20], dtype=np.uint32)
+    idx_b = np.arange(150, 300, dtype=np.uint32)
+    rng = np.random.default_rng(1)
+    da = np.sort(rng.uniform(0, 1, len(idx_a))); da[0], da[-1] = 0.0, 1.0
+    db = np.sort(rng.uniform(0, 1, len(idx_b))); db[0], db[-1] = 0.0, 1.0
+    ds["maps"] = [dict(lam=np.array([1.7, 2.2]), chr_offset=np.array([0, len(idx_a), len(idx_a) + len(idx_b)], dtype=np.uint32),
+                       dists=np.concatenate([da, db]), marker_index=np.concatenate([idx_a, idx_b]),
+                       has_dists=np.ones(2, dtype=np.uint8))]
+    p, s, groups = replay_both(ds, seed=6, small=True)
+    a, b = scenarios.export_state(p), scenarios.export_state(s)
+    scenarios.assert_same_state(a, b)
+    kids = b["genotypes"][8:]
+    assert (kids[:, 2 * 100:2 * 150] == 0).all() and (kids[:, 20:40] == 0).all()      # uncovered -> '\0'
+    want = p.calculate_bvs(0, 0)
+    bv_close(s.calculate_bvs(0, 1), want, scale=np.abs(want).mean())
+    np.testing.assert_array_equal(p.calculate_allele_counts(0, b"\0"), s.calculate_allele_counts(0, b"\0"))
+    p.close(); s.close()
+
+
+def test_change_allele_symbol():
+    """gsc_change_allele_symbol (core.c:1029-1100) is a dictionary edit on the packed store."""
+    ds = datasets.synthetic(6, 200, 2, 100.0, seed=41)
+    s = engine_from(ds)
+    assert s.E.gsb200_store_change_symbol(s.ctx, 0xFFFFFFFF, b"A", b"G") == 0
+    assert s.E.gsb200_store_change_symbol(s.ctx, 7, b"T", b"C") == 0
+    want = ds["genotypes"].copy()
+    want[want == ord("A")] = ord("G")
+    col = want[:, 14:16]
+    col[col == ord("T")] = ord("C")
+    np.testing.assert_array_equal(s.export_group(0)["genotypes"], want)
+    # effects are keyed by symbol: 'A' effects no longer match anything, 'T' still does except at marker 7
+    e = ds["effects"][0]
+    eff = e["eff"].reshape(200, 2)
+    isT = (want[:, 0::2] == ord("T")).astype(float) + (want[:, 1::2] == ord("T"))
+    bv_close(s.calculate_bvs(0, 1), (isT * eff[:, 1]).sum(axis=1), scale=5.0)
+    s.close()
