@@ -124,6 +124,8 @@ HOST_SYMBOLS = {
     "gsb_make_doubled_haploids": (UINT, [VP, UINT, UINT, GenOptions]),
     "gsb_make_clones": (UINT, [VP, UINT, C.c_bool, GenOptions]),
     "gsb_make_all_unidirectional_crosses": (UINT, [VP, UINT, UINT, GenOptions]),
+    "gsb_make_crosses_from_file": (UINT, [VP, C.c_char_p, UINT, UINT, GenOptions]),
+    "gsb_make_double_crosses_from_file": (UINT, [VP, C.c_char_p, UINT, UINT, GenOptions]),
     "gsb_calculate_bvs": (DecimalMatrix, [VP, UINT, UINT]),
     "gsb_get_group_bvs": (UINT, [VP, UINT, UINT, UINT, VP]),
     "gsb_calculate_allele_counts": (DecimalMatrix, [VP, UINT, C.c_char]),

@@ -189,6 +189,16 @@ class SimData:
         self._check()
         return g
 
+    def make_crosses_from_file(self, path, map1=0, map2=0, **kw):
+        g = self.L.gsb_make_crosses_from_file(self.d, path.encode(), map1, map2, _opts(**kw))
+        self._check()
+        return g
+
+    def make_double_crosses_from_file(self, path, map1=0, map2=0, **kw):
+        g = self.L.gsb_make_double_crosses_from_file(self.d, path.encode(), map1, map2, _opts(**kw))
+        self._check()
+        return g
+
     def make_all_unidirectional_crosses(self, group, map_id=0, **kw):
         g = self.L.gsb_make_all_unidirectional_crosses(self.d, group, map_id, _opts(**kw))
         self._check()

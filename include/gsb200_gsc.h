@@ -128,6 +128,9 @@ gsb_GroupNum gsb_self_n_times(gsb_SimData* d, unsigned int n, gsb_GroupNum group
 gsb_GroupNum gsb_make_doubled_haploids(gsb_SimData* d, gsb_GroupNum group, gsb_MapID which_map, gsb_GenOptions g);
 gsb_GroupNum gsb_make_clones(gsb_SimData* d, gsb_GroupNum group, _Bool inherit_names, gsb_GenOptions g);
 gsb_GroupNum gsb_make_all_unidirectional_crosses(gsb_SimData* d, gsb_GroupNum from_group, gsb_MapID map, gsb_GenOptions g);
+/* crossing plans from files of genotype names (core.c:9248-9313, 9347-9444) */
+gsb_GroupNum gsb_make_crosses_from_file(gsb_SimData* d, const char* input_file, gsb_MapID map1, gsb_MapID map2, gsb_GenOptions g);
+gsb_GroupNum gsb_make_double_crosses_from_file(gsb_SimData* d, const char* input_file, gsb_MapID map1, gsb_MapID map2, gsb_GenOptions g);
 
 /* ---- evaluation (core.c:9463-10090) */
 gsb_DecimalMatrix gsb_calculate_bvs(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID effID);

@@ -265,6 +265,14 @@ class RefSim:
         return self.L.refb_make_targeted_crosses(self.d, len(a), _ptr(a, U), _ptr(b, U), map1, map2,
                                                  gen_options(**kw), np_, fp_)
 
+    def make_crosses_from_file(self, path, map1=0, map2=0, **kw):
+        np_, fp_ = self._pfx(kw)
+        return self.L.refb_make_crosses_from_file(self.d, path.encode(), map1, map2, gen_options(**kw), np_, fp_)
+
+    def make_double_crosses_from_file(self, path, map1=0, map2=0, **kw):
+        np_, fp_ = self._pfx(kw)
+        return self.L.refb_make_double_crosses_from_file(self.d, path.encode(), map1, map2, gen_options(**kw), np_, fp_)
+
     def make_all_unidirectional_crosses(self, group, map_id=0, **kw):
         np_, fp_ = self._pfx(kw)
         return self.L.refb_make_all_unidirectional_crosses(self.d, group, map_id, gen_options(**kw), np_, fp_)

@@ -175,6 +175,16 @@ EXPORT unsigned refb_make_all_unidirectional_crosses(void* d, unsigned group, un
     return gsc_make_all_unidirectional_crosses((gsc_SimData*) d, (gsc_GroupNum){.num = group},
                                                (gsc_MapID){.id = map_id}, make_opts(opt, np, fp)).num;
 }
+EXPORT unsigned refb_make_crosses_from_file(void* d, const char* path, unsigned map1, unsigned map2,
+                                            const unsigned opt[8], const char* np, const char* fp) {
+    return gsc_make_crosses_from_file((gsc_SimData*) d, path, (gsc_MapID){.id = map1}, (gsc_MapID){.id = map2},
+                                      make_opts(opt, np, fp)).num;
+}
+EXPORT unsigned refb_make_double_crosses_from_file(void* d, const char* path, unsigned map1, unsigned map2,
+                                                   const unsigned opt[8], const char* np, const char* fp) {
+    return gsc_make_double_crosses_from_file((gsc_SimData*) d, path, (gsc_MapID){.id = map1}, (gsc_MapID){.id = map2},
+                                             make_opts(opt, np, fp)).num;
+}
 EXPORT unsigned refb_self_n_times(void* d, unsigned n, unsigned group, unsigned map_id,
                                   const unsigned opt[8], const char* np, const char* fp) {
     return gsc_self_n_times((gsc_SimData*) d, n, (gsc_GroupNum){.num = group}, (gsc_MapID){.id = map_id},

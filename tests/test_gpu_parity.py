@@ -322,3 +322,73 @@ def test_change_allele_symbol():
     isT = (want[:, 0::2] == ord("T")).astype(float) + (want[:, 1::2] == ord("T"))
     bv_close(s.calculate_bvs(0, 1), (isT * eff[:, 1]).sum(axis=1), scale=5.0)
     s.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not present")
+def test_crossing_plans_from_files_match_the_reference(tmp_path):
+    """gsc_make_crosses_from_file / gsc_make_double_crosses_from_file (core.c:9248-9444) against the
+    UNMODIFIED reference on a replayed tape: unknown names and short rows are skipped, double
+    crosses find the F1s by pedigree."""
+    ds = datasets.synthetic(8, 600, 3, 100.0, seed=44, spacing="random")
+    gf, mf, ef = datasets.write_files(ds, str(tmp_path))
+    r = ref.RefSim()
+    ref.set_print_mode(0)
+    g, m, e = r.load(gf, mf, ef)
+    plan = tmp_path / "plan.txt"
+    plan.write_text("F1\tF2\nF3\tF8\nF9\tF1\nF4\nF5\tF6\tF7\nF2\tF7\n")
+    dplan = tmp_path / "dplan.txt"
+    dplan.write_text("F1\tF2\tF3\tF8\nF5\tF6\tF2\tF7\nF1\tF3\tF2\tF8\nF1\tF2\tF4\tF5\n")
+    ref.seed(5)
+    ref.record_start()
+    g1 = r.make_crosses_from_file(str(plan), m, m, family_size=2)
+    g2 = r.make_double_crosses_from_file(str(dplan), m, m)
+    tape = ref.record_stop().draws_only()
+    loaded = datasets.from_ref(r, g)
+    s = engine_from(loaded)
+    with port.Replay(tape) as rp:
+        h1 = s.make_crosses_from_file(str(plan), 1, 1, family_size=2)
+        h2 = s.make_double_crosses_from_file(str(dplan), 1, 1)
+    assert not rp.error and rp.consumed == len(tape)
+    assert (g1, g2) == (h1, h2) and r.group_size(g1) == s.group_size(h1) == 8
+    assert r.group_size(g2) == s.group_size(h2) and s.group_size(h2) >= 2
+    scenarios.assert_same_state(scenarios.export_state(r), scenarios.export_state(s))
+    r.close(); s.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("shape", [(20, 1000, 3, 100.0), (24, 50000, 21, 150.0)])
+def test_scheme_replay_matches_the_unmodified_reference(shape, tmp_path):
+    """Every crossing entry point, GEBVs, local GEBVs, allele counts and selection against the
+    UNMODIFIED reference core (oracle/_ref) itself: the reference loads its own text files, records
+    the draws it consumes, and the engine replays them."""
+    n, M, Cn, cm = shape
+    ds = datasets.synthetic(n, M, Cn, cm, seed=M + 3, spacing="random")
+    gf, mf, ef = datasets.write_files(ds, str(tmp_path))
+    r = ref.RefSim()
+    ref.set_print_mode(0)
+    g, m, e = r.load(gf, mf, ef)
+    ref.seed(M + 9)
+    ref.record_start()
+    groups_r = scenarios.crossing_scheme(r, g)
+    tape = ref.record_stop().draws_only()
+    s = engine_from(datasets.from_ref(r, g))
+    with port.Replay(tape) as rp:
+        groups_s = scenarios.crossing_scheme(s, 1)
+    assert not rp.error and rp.consumed == len(tape)
+    assert groups_r == groups_s
+    scenarios.assert_same_state(scenarios.export_state(r), scenarios.export_state(s))
+    want = r.calculate_bvs(0, e)
+    bv_close(s.calculate_bvs(0, 1), want, scale=np.abs(want).mean())
+    rb = r.blocks_evenlength(5)
+    off, mk = rb.export()
+    sb = s.blocks_evenlength(5, 1)
+    off_s, mk_s = sb.export()
+    np.testing.assert_array_equal(off, off_s)
+    np.testing.assert_array_equal(mk, mk_s)
+    want = r.calculate_local_bvs(groups_r[3], rb, e)
+    bv_close(s.calculate_local_bvs(groups_s[3], sb, 1), want, scale=np.abs(want).mean())
+    np.testing.assert_array_equal(r.calculate_allele_counts(groups_r[1], "T"), s.calculate_allele_counts(groups_s[1], "T"))
+    gr = r.split_by_bv(groups_r[0], e, 7, True)
+    gs = s.split_by_bv(groups_s[0], 1, 7, True)
+    assert sorted(r.group_indexes(gr).tolist()) == sorted(s.group_indexes(gs).tolist())
+    r.close(); s.close()
