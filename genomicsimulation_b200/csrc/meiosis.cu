@@ -47,6 +47,7 @@ struct MapView {
     const uint32_t* marker_index;
     const uint32_t* chunk_chr;
     const uint32_t* chunk_start;
+    const double* cdf;         // per linkage group: P(K <= j), j = 0..15
     uint32_t n_chr;
     uint32_t n_chunks;
 };
@@ -133,13 +134,27 @@ __device__ __forceinline__ uint32_t poisson_inverse(double u, double lambda, dou
     return k;
 }
 
+// The same from the linkage group's table of P(K <= j), j < 16 (binary search), falling back to
+// the summation for the tail.
+__device__ __forceinline__ uint32_t poisson_table(double u, const ChrInfo& ci, const double* __restrict__ cdf) {
+    if (!(ci.lambda > 0.0)) return 0;
+    const double* t = cdf + ci.cdf_off;
+    if (u > t[15]) return poisson_inverse(u, ci.lambda, ci.exp_neg_lambda);
+    uint32_t lo = 0;
+    if (u > t[7]) lo = 8;
+    if (u > t[lo + 3]) lo += 4;
+    if (u > t[lo + 1]) lo += 2;
+    if (u > t[lo]) lo += 1;
+    return lo;
+}
+
 // (count, start strand) of one gamete-chromosome: the Rf_rpois and `which` draws of
 // core.c:7873 and 7896.
-__device__ __forceinline__ void draw_header(const DrawView& d, const ChrInfo& ci, uint64_t unit, uint32_t gamete,
-                                            uint32_t chr, uint64_t entry, uint32_t& k, uint32_t& strand) {
+__device__ __forceinline__ void draw_header(const DrawView& d, const ChrInfo& ci, const double* __restrict__ cdf, uint64_t unit,
+                                            uint32_t gamete, uint32_t chr, uint64_t entry, uint32_t& k, uint32_t& strand) {
     if (d.mode == GSB200_DRAWS_PHILOX) {
         const uint4 r = draw_block(d, unit, gamete, chr, 0);
-        k = poisson_inverse(u01(r.x, r.y), ci.lambda, ci.exp_neg_lambda);
+        k = poisson_inverse(u01(r.x, r.y), ci.lambda, ci.exp_neg_lambda);   // (poisson_table: dependent loads cost more than the loop)
         strand = r.z >> 31;
     } else {
         k = d.tape_k[entry];
@@ -215,7 +230,7 @@ __device__ __forceinline__ void emit_toggles(uint32_t t, uint32_t lane, const Me
 //   chr_start[n_chr/32 + 1]   bit c: start strand of chromosome c
 //   list[tcap]                the toggles (marker positions), unordered
 //   xinfo[xcap]               crossover -> (chromosome, index within chromosome)
-__global__ void __launch_bounds__(256, 4) splice_flat_kernel(const MeiosisArgs a) {
+__global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint2* xinfo = reinterpret_cast<uint2*>(smem + (size_t) warp * a.warp_smem_words);
@@ -242,7 +257,7 @@ __global__ void __launch_bounds__(256, 4) splice_flat_kernel(const MeiosisArgs a
             uint32_t k = 0, strand = 0;
             if (c < mv.n_chr) {
                 const ChrInfo ci = mv.chr[c];
-                draw_header(a.draws, ci, unit, gam, c, entry0 + c, k, strand);
+                draw_header(a.draws, ci, mv.cdf, unit, gam, c, entry0 + c, k, strand);
                 if (ci.len == 0) strand = 0;
                 if (ci.len == 0 || !ci.searchable) k = 0;   // such positions are drawn but can never be passed
             }
@@ -331,28 +346,32 @@ __global__ void __launch_bounds__(256, 4) splice_flat_kernel(const MeiosisArgs a
         uint32_t* dst = a.dst_base + (uint64_t) dst_row * a.row_words;
         const uint32_t hap_stride = a.planes * a.plane_words;
 
-        // E1. every piece, whole, from the strand it starts on: plain 128-bit copies
+        // E1. every piece, whole, from the strand it starts on: plain 128-bit copies.  Full groups of
+        //     32 * kUnroll pieces run without bounds checks; 32-bit piece offsets from two bases.
+        const uint32_t hap_pieces = hap_stride >> 2;
+        const uint32_t full = a.n_u & ~(32u * kUnroll - 1u);
         for (uint32_t p = 0; p < a.planes; ++p) {
-            const uint32_t* s0 = src + p * a.plane_words;
-            uint32_t* out = dst + (gam * a.planes + p) * a.plane_words;
-            for (uint32_t u0 = 0; u0 < a.n_u; u0 += 32 * kUnroll) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src + p * a.plane_words);
+            uint4* o4 = reinterpret_cast<uint4*>(dst + (gam * a.planes + p) * a.plane_words);
+            uint32_t u = lane;
+            for (; u < full; u += 32 * kUnroll) {
                 uint4 v[kUnroll];
 #pragma unroll
                 for (int q = 0; q < kUnroll; ++q) {
-                    const uint32_t u = u0 + q * 32 + lane;
-                    if (u < a.n_u) {
-                        const uint32_t on1 = (piece_parity[(u0 >> 5) + q] >> lane) & 1u;
-                        v[q] = ldg128(s0 + (on1 ? hap_stride : 0u) + 4 * u);
-                    }
+                    const uint32_t on1 = (piece_parity[(u >> 5) + q] >> lane) & 1u;
+                    v[q] = __ldg(s4 + (u + q * 32 + on1 * hap_pieces));
                 }
 #pragma unroll
                 for (int q = 0; q < kUnroll; ++q) {
-                    const uint32_t u = u0 + q * 32 + lane;
-                    if (u < a.n_u) {
-                        *reinterpret_cast<uint4*>(out + 4 * u) = v[q];
-                        if (a.doubled) *reinterpret_cast<uint4*>(out + hap_stride + 4 * u) = v[q];
-                    }
+                    o4[u + q * 32] = v[q];
+                    if (a.doubled) o4[u + q * 32 + hap_pieces] = v[q];
                 }
+            }
+            for (; u < a.n_u; u += 32) {
+                const uint32_t on1 = (piece_parity[u >> 5] >> lane) & 1u;
+                const uint4 v = __ldg(s4 + (u + on1 * hap_pieces));
+                o4[u] = v;
+                if (a.doubled) o4[u + hap_pieces] = v;
             }
         }
         __syncwarp();      // orders the plain stores before the fix-ups below (same warp)
@@ -483,7 +502,7 @@ __global__ void export_headers_kernel(const MeiosisArgs a, uint32_t* out_k, uint
     const uint32_t c = e - (gam ? a.map[0].n_chr : 0);
     const ChrInfo ci = a.map[gam].chr[c];
     uint32_t k, strand;
-    draw_header(a.draws, ci, a.draws.first_unit + unit_local, gam, c, 0, k, strand);
+    draw_header(a.draws, ci, a.map[gam].cdf, a.draws.first_unit + unit_local, gam, c, 0, k, strand);
     out_k[tid] = k;
     out_s[tid] = (uint8_t) strand;
     out_k64[tid] = k;
@@ -547,7 +566,7 @@ __global__ void copy_rows_kernel(uint32_t* store, const uint32_t* src_rows, cons
 MapView view_of(const DeviceMap& m) {
     MapView v;
     v.chr = m.d_chr; v.dists = m.d_dists; v.bucket = m.d_bucket; v.marker_index = m.d_marker_index;
-    v.chunk_chr = m.d_chunk_chr; v.chunk_start = m.d_chunk_start; v.n_chr = m.n_chr; v.n_chunks = m.n_chunks;
+    v.chunk_chr = m.d_chunk_chr; v.chunk_start = m.d_chunk_start; v.cdf = m.d_cdf; v.n_chr = m.n_chr; v.n_chunks = m.n_chunks;
     return v;
 }
 
