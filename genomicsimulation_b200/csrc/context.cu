@@ -40,7 +40,7 @@ void Scratch::release() {
 }
 
 void DeviceMap::release() {
-    void* ptrs[] = { d_chr, d_dists, d_marker_index, d_bucket, d_chunk_chr, d_chunk_start, d_uncovered, d_cdf };
+    void* ptrs[] = { d_chr, d_dists, d_marker_index, d_bucket, d_chunk_chr, d_chunk_start, d_uncovered };
     for (void* p : ptrs) if (p) cudaFree(p);
     *this = DeviceMap();
 }
@@ -178,7 +178,6 @@ int gsb200_map_set(gsb200_ctx* ctx, uint32_t map_index, uint32_t n_chr, const do
     std::vector<double> v_dists(std::max<uint32_t>(total, 1), 0.0);
     std::vector<uint32_t> v_mix(marker_index, marker_index + total);
     std::vector<uint32_t> v_bucket, v_chunk_chr, v_chunk_start;
-    std::vector<double> v_cdf;
     std::vector<uint8_t> covered(ctx->n_markers, 0);
 
     bool contiguous = true, disjoint = true;
@@ -189,16 +188,6 @@ int gsb200_map_set(gsb200_ctx* ctx, uint32_t map_index, uint32_t n_chr, const do
         ChrInfo& ci = v_chr[c];
         ci.lambda = lambda[c];
         ci.exp_neg_lambda = lambda[c] > 0 ? std::exp(-lambda[c]) : 1.0;
-        ci.cdf_off = c * 16;
-        ci.pad_ = 0;
-        {
-            double p = ci.exp_neg_lambda, cdf = p;
-            for (uint32_t j = 0; j < 16; ++j) {
-                v_cdf.push_back(cdf);
-                p *= lambda[c] > 0 ? lambda[c] / (double) (j + 1) : 0.0;
-                cdf += p;
-            }
-        }
         ci.len = hi - lo;
         ci.first = hi > lo ? marker_index[lo] : 0;
         ci.pos_off = lo;
@@ -258,7 +247,6 @@ int gsb200_map_set(gsb200_ctx* ctx, uint32_t map_index, uint32_t n_chr, const do
     GSB_TRY(to_device(v_dists, &m.d_dists));
     GSB_TRY(to_device(v_mix, &m.d_marker_index));
     GSB_TRY(to_device(v_bucket, &m.d_bucket));
-    GSB_TRY(to_device(v_cdf, &m.d_cdf));
     GSB_TRY(to_device(v_chunk_chr, &m.d_chunk_chr));
     GSB_TRY(to_device(v_chunk_start, &m.d_chunk_start));
     for (uint32_t mk = 0; mk < ctx->n_markers; ++mk) if (!covered[mk]) m.h_uncovered.push_back(mk);

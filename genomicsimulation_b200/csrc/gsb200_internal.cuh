@@ -59,8 +59,6 @@ struct ChrInfo {
     uint32_t bucket_off;      // offset of group in the bucket index
     uint32_t bucket_shift;    // group has 2^shift buckets
     uint32_t searchable;      // 0: never switches strand (no dists, or all-NaN dists)
-    uint32_t cdf_off;         // offset of the group's 16-entry Poisson CDF table
-    uint32_t pad_;
 };
 
 // Recombination map resident on the device (gsc_RecombinationMap, core.h:678-765).
@@ -81,7 +79,6 @@ struct DeviceMap {
     double*   d_dists = nullptr;    // [n_positions] running maximum of the reference's dists (context.cu)
     uint32_t* d_marker_index = nullptr;
     uint32_t* d_bucket = nullptr;   // bucket index accelerating upper_bound(dists, x)
-    double*   d_cdf = nullptr;      // [n_chr][16] P(K <= j) of Poisson(lambda): the native stream's inversion table
     // general path: chunk k covers positions [chunk_start[k], chunk_start[k]+32) of chromosome chunk_chr[k]
     uint32_t* d_chunk_chr = nullptr;
     uint32_t* d_chunk_start = nullptr;

@@ -47,7 +47,6 @@ struct MapView {
     const uint32_t* marker_index;
     const uint32_t* chunk_chr;
     const uint32_t* chunk_start;
-    const double* cdf;         // per linkage group: P(K <= j), j = 0..15
     uint32_t n_chr;
     uint32_t n_chunks;
 };
@@ -134,27 +133,14 @@ __device__ __forceinline__ uint32_t poisson_inverse(double u, double lambda, dou
     return k;
 }
 
-// The same from the linkage group's table of P(K <= j), j < 16 (binary search), falling back to
-// the summation for the tail.
-__device__ __forceinline__ uint32_t poisson_table(double u, const ChrInfo& ci, const double* __restrict__ cdf) {
-    if (!(ci.lambda > 0.0)) return 0;
-    const double* t = cdf + ci.cdf_off;
-    if (u > t[15]) return poisson_inverse(u, ci.lambda, ci.exp_neg_lambda);
-    uint32_t lo = 0;
-    if (u > t[7]) lo = 8;
-    if (u > t[lo + 3]) lo += 4;
-    if (u > t[lo + 1]) lo += 2;
-    if (u > t[lo]) lo += 1;
-    return lo;
-}
-
 // (count, start strand) of one gamete-chromosome: the Rf_rpois and `which` draws of
 // core.c:7873 and 7896.
-__device__ __forceinline__ void draw_header(const DrawView& d, const ChrInfo& ci, const double* __restrict__ cdf, uint64_t unit,
-                                            uint32_t gamete, uint32_t chr, uint64_t entry, uint32_t& k, uint32_t& strand) {
+__device__ __forceinline__ void draw_header(const DrawView& d, const ChrInfo& ci, uint64_t unit, uint32_t gamete,
+                                            uint32_t chr, uint64_t entry, uint32_t& k, uint32_t& strand) {
     if (d.mode == GSB200_DRAWS_PHILOX) {
         const uint4 r = draw_block(d, unit, gamete, chr, 0);
-        k = poisson_inverse(u01(r.x, r.y), ci.lambda, ci.exp_neg_lambda);   // (poisson_table: dependent loads cost more than the loop)
+        // (a 16-entry CDF table searched by bisection was tried: its dependent loads cost more than this short loop)
+        k = poisson_inverse(u01(r.x, r.y), ci.lambda, ci.exp_neg_lambda);
         strand = r.z >> 31;
     } else {
         k = d.tape_k[entry];
@@ -257,7 +243,7 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
             uint32_t k = 0, strand = 0;
             if (c < mv.n_chr) {
                 const ChrInfo ci = mv.chr[c];
-                draw_header(a.draws, ci, mv.cdf, unit, gam, c, entry0 + c, k, strand);
+                draw_header(a.draws, ci, unit, gam, c, entry0 + c, k, strand);
                 if (ci.len == 0) strand = 0;
                 if (ci.len == 0 || !ci.searchable) k = 0;   // such positions are drawn but can never be passed
             }
@@ -502,7 +488,7 @@ __global__ void export_headers_kernel(const MeiosisArgs a, uint32_t* out_k, uint
     const uint32_t c = e - (gam ? a.map[0].n_chr : 0);
     const ChrInfo ci = a.map[gam].chr[c];
     uint32_t k, strand;
-    draw_header(a.draws, ci, a.map[gam].cdf, a.draws.first_unit + unit_local, gam, c, 0, k, strand);
+    draw_header(a.draws, ci, a.draws.first_unit + unit_local, gam, c, 0, k, strand);
     out_k[tid] = k;
     out_s[tid] = (uint8_t) strand;
     out_k64[tid] = k;
@@ -566,7 +552,7 @@ __global__ void copy_rows_kernel(uint32_t* store, const uint32_t* src_rows, cons
 MapView view_of(const DeviceMap& m) {
     MapView v;
     v.chr = m.d_chr; v.dists = m.d_dists; v.bucket = m.d_bucket; v.marker_index = m.d_marker_index;
-    v.chunk_chr = m.d_chunk_chr; v.chunk_start = m.d_chunk_start; v.cdf = m.d_cdf; v.n_chr = m.n_chr; v.n_chunks = m.n_chunks;
+    v.chunk_chr = m.d_chunk_chr; v.chunk_start = m.d_chunk_start; v.n_chr = m.n_chr; v.n_chunks = m.n_chunks;
     return v;
 }
 
