@@ -217,3 +217,49 @@ def test_device_side_parent_choice():
     z = sim.export_group(c, genotypes=False)
     assert (z["ped1"] == 0).all() and len(set(z["ids"].tolist())) == 100
     sim.close()
+
+
+def test_kernels_stay_inside_their_rows_and_keep_padding_zero():
+    """Guard rows: offspring written to every other row must leave the rows in between untouched,
+    and the bits of a plane beyond the last marker must stay 0 (they feed the GEBV contraction)."""
+    import torch
+    F, M = 12, 3001                         # 3001 markers: a ragged last word
+    ds = datasets.synthetic(F, M, 5, 120.0, seed=9, spacing="random")
+    sim = make_sim(ds)
+    n = 500
+    assert sim.E.gsb200_store_reserve(sim.ctx, F + 2 * n + 2) == 0
+    rng = np.random.default_rng(1)
+    guard_chars = ds["genotypes"][rng.integers(0, F, 2 * n + 2)]
+    all_rows = np.arange(F, F + 2 * n + 2, dtype=np.uint32)
+    assert sim.E.gsb200_store_upload_chars(sim.ctx, len(all_rows), _p(all_rows), _p(np.ascontiguousarray(guard_chars))) == 0
+    out = all_rows[1:-1:2][:n].copy()       # odd positions
+    guards = np.setdiff1d(all_rows, out)
+    p1, p2 = rng.integers(0, F, n), rng.integers(0, F, n)
+    row_bytes = sim.E.gsb200_store_row_bytes(sim.ctx)
+
+    def raw(rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        d_rows = torch.from_numpy(rows).cuda()
+        t = torch.empty((len(rows), row_bytes), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        assert sim.E.gsb200_store_gather_rows_dev(sim.ctx, len(rows), d_rows.data_ptr(), t.data_ptr()) == 0
+        assert sim.E.gsb200_synchronize(sim.ctx) == 0
+        return t.cpu().numpy()
+
+    before = raw(guards)
+    cross(sim, p1, p2, out, philox(3))
+    dh_src = np.ascontiguousarray(all_rows[0:2 * 100:2].copy())      # guard rows as parents (read only)
+    dr = philox(4)
+    assert sim.E.gsb200_doubled_haploid(sim.ctx, 100, _p(dh_src), 0, _p(np.ascontiguousarray(out[:100].copy())), C.byref(dr)) == 0
+    cross(sim, p1, p2, out, philox(5))
+    assert sim.E.gsb200_self_n_times(sim.ctx, 20, _p(np.ascontiguousarray(all_rows[:40:2].copy())), 3, 0,
+                                     _p(np.ascontiguousarray(out[:20].copy())), C.byref(philox(6))) == 0
+    np.testing.assert_array_equal(raw(guards), before)
+    # padding: bits >= M of each of the 2 strand planes are zero
+    words = raw(out).view(np.uint32).reshape(n, 2, -1)
+    last = M // 32
+    assert (words[:, :, last] >> (M % 32) == 0).all() and (words[:, :, last + 1:] == 0).all()
+    # and the offspring decode to parental alleles only
+    g = download(sim, out[20:60])
+    assert set(np.unique(g)) <= {ord("A"), ord("T")}
+    sim.close()
