@@ -27,23 +27,41 @@ def offspring_range(n_total, rank, world):
 
 def select_global(bv_all, top_n, low_is_best=False):
     """Positions of the top_n best values, best first, ties by lower position — the same rule as
-    gsb200_top_n, evaluated identically on every rank."""
+    gsb200_top_n, evaluated identically on every rank.  Accepts a numpy array or a torch tensor
+    (a stable sort on whichever device the GEBVs were gathered to)."""
+    if isinstance(bv_all, torch.Tensor):
+        key = bv_all if low_is_best else -bv_all
+        return torch.sort(key, stable=True).indices[:top_n].cpu().numpy()
     bv_all = np.asarray(bv_all, dtype=np.float64)
     key = bv_all if low_is_best else -bv_all
-    order = np.argsort(key, kind="stable")
-    return order[:top_n]
+    return np.argsort(key, kind="stable")[:top_n]
 
 
-def draw_pairs(n_pool, n_offspring, seed):
-    """Random parent pairs (a != b) for a whole generation from one host stream, with the
-    reference's pick rule round(u * (n - 1)) redrawn on collision (sim-operations.c:8556-8581)."""
-    rng = np.random.default_rng(seed)
-    a = np.rint(rng.random(n_offspring) * (n_pool - 1)).astype(np.int64)
-    b = np.rint(rng.random(n_offspring) * (n_pool - 1)).astype(np.int64)
-    clash = a == b
-    while clash.any():
-        b[clash] = np.rint(rng.random(int(clash.sum())) * (n_pool - 1)).astype(np.int64)
-        clash = a == b
+_PAIR_BLOCK = 1 << 16
+
+
+def draw_pairs(n_pool, n_offspring, seed, lo=0, hi=None):
+    """Random parent pairs (a != b) for offspring [lo, hi) of a generation of n_offspring, with the
+    reference's pick rule round(u * (n - 1)) redrawn on collision (sim-operations.c:8556-8581).
+    The host stream is seeded per block of 65 536 offspring, so a rank draws only the blocks that
+    overlap its own range and the pairs do not depend on how the generation is sharded."""
+    hi = n_offspring if hi is None else hi
+    a = np.empty(hi - lo, dtype=np.int64)
+    b = np.empty(hi - lo, dtype=np.int64)
+    for blk in range(lo // _PAIR_BLOCK, (max(hi, lo + 1) - 1) // _PAIR_BLOCK + 1):
+        b_lo, b_hi = blk * _PAIR_BLOCK, min((blk + 1) * _PAIR_BLOCK, n_offspring)
+        if b_hi <= b_lo:
+            continue
+        rng = np.random.default_rng([int(seed) & 0xFFFFFFFFFFFF, blk])
+        aa = np.rint(rng.random(b_hi - b_lo) * (n_pool - 1)).astype(np.int64)
+        bb = np.rint(rng.random(b_hi - b_lo) * (n_pool - 1)).astype(np.int64)
+        clash = aa == bb
+        while clash.any():
+            bb[clash] = np.rint(rng.random(int(clash.sum())) * (n_pool - 1)).astype(np.int64)
+            clash = aa == bb
+        s_lo, s_hi = max(lo, b_lo), min(hi, b_hi)
+        a[s_lo - lo:s_hi - lo] = aa[s_lo - b_lo:s_hi - b_lo]
+        b[s_lo - lo:s_hi - lo] = bb[s_lo - b_lo:s_hi - b_lo]
     return a, b
 
 
@@ -83,33 +101,27 @@ class ShardedPopulation:
     def select_parents(self, eff, top_n, low_is_best=False):
         """Replicated selection + parent-pool exchange. Returns (global indexes selected, rows of the
         pool in THIS rank's store, in selection order)."""
-        bvs = self.gather_bvs(eff).cpu().numpy()
-        chosen = select_global(bvs, top_n, low_is_best)
-        mine = [(k, int(g)) for k, g in enumerate(chosen) if self.lo <= g < self.hi]
-        counts = []
-        for r in range(self.world):
-            l, h = offspring_range(self.n_total, r, self.world)
-            counts.append(int(((chosen >= l) & (chosen < h)).sum()))
-        send_rows = np.array([self.local_rows[g - self.lo] for _, g in mine], dtype=np.uint32)
-        packed = self.backend.gather_rows(send_rows)                          # tensor [len(mine), row_bytes] u8
+        chosen = select_global(self.gather_bvs(eff), top_n, low_is_best)
+        bounds = np.array([offspring_range(self.n_total, r, self.world)[0] for r in range(self.world)] + [self.n_total])
+        owner = np.searchsorted(bounds, chosen, side="right") - 1
+        counts = np.bincount(owner, minlength=self.world).tolist()
+        send_rows = self.local_rows[chosen[owner == self.rank] - self.lo]
+        packed = self.backend.gather_rows(send_rows)                          # tensor [mine, row_bytes] u8
         pool = self._all_gather_ragged(packed, counts)                        # rank-major order
-        # rank-major position -> selection order
-        order = []
-        for r in range(self.world):
-            l, h = offspring_range(self.n_total, r, self.world)
-            order += [k for k, g in enumerate(chosen) if l <= g < h]
-        inv = np.empty(len(order), dtype=np.int64)
-        inv[np.array(order, dtype=np.int64)] = np.arange(len(order))
+        # rank-major position p holds selection number perm[p]; put the pool in selection order
+        perm = np.argsort(owner, kind="stable")
+        inv = np.empty(len(perm), dtype=np.int64)
+        inv[perm] = np.arange(len(perm))
         pool = pool[torch.as_tensor(inv, device=pool.device)]
         pool_rows = self.backend.adopt_rows(pool)                             # rows holding the pool here
         return chosen, pool_rows
 
     def next_generation(self, pool_rows, n_offspring, seed, generation, map_index=0):
         """Every rank makes its own index range of the next generation from the replicated pool."""
-        a, b = draw_pairs(len(pool_rows), n_offspring, seed * 1000003 + generation)
         lo, hi = offspring_range(n_offspring, self.rank, self.world)
-        rows = self.backend.cross(pool_rows[a[lo:hi]], pool_rows[b[lo:hi]], map_index,
-                                  seed=seed, stream=generation, first_unit=lo)
+        a, b = draw_pairs(len(pool_rows), n_offspring, seed * 1000003 + generation, lo, hi)
+        pool_rows = np.asarray(pool_rows)
+        rows = self.backend.cross(pool_rows[a], pool_rows[b], map_index, seed=seed, stream=generation, first_unit=lo)
         return ShardedPopulation(self.backend, n_offspring, rows, self.group)
 
 
@@ -120,35 +132,43 @@ class EngineBackend:
         self.sim, self.E, self.ctx = sim, sim.E, sim.ctx
         self.row_bytes = self.E.gsb200_store_row_bytes(self.ctx)
         self.next_row = int(self.E.gsb200_store_capacity(self.ctx))
-        self.free = []
+        self.free = np.empty(0, dtype=np.uint32)
 
     def _check(self, st):
         if st != 0:
             raise RuntimeError(self.E.gsb200_last_error().decode())
 
     def _take(self, n):
-        rows = [self.free.pop() for _ in range(min(n, len(self.free)))]
-        need = n - len(rows)
+        k = min(n, len(self.free))
+        rows = self.free[len(self.free) - k:]
+        self.free = self.free[:len(self.free) - k]
+        need = n - k
         if need:
             self._check(self.E.gsb200_store_reserve(self.ctx, self.next_row + need))
-            rows += list(range(self.next_row, self.next_row + need))
+            rows = np.concatenate([rows, np.arange(self.next_row, self.next_row + need, dtype=np.uint32)])
             self.next_row += need
-        return np.array(rows, dtype=np.uint32)
+        return np.ascontiguousarray(rows, dtype=np.uint32)
 
     def release(self, rows):
-        self.free += [int(r) for r in rows]
+        self.free = np.concatenate([self.free, np.asarray(rows, dtype=np.uint32)])
+
+    def _dev_rows(self, rows):
+        return torch.from_numpy(np.ascontiguousarray(rows, dtype=np.uint32).view(np.int32)).cuda()
 
     def gebv(self, rows, eff):
-        rows = np.ascontiguousarray(rows, dtype=np.uint32)
-        out = np.zeros(len(rows), dtype=np.float64)
-        self._check(self.E.gsb200_gebv(self.ctx, len(rows), rows.ctypes.data, eff, out.ctypes.data))
-        return torch.from_numpy(out).cuda()
+        """GEBVs of `rows`, left on the device (they go straight into the all-gather)."""
+        d_rows = self._dev_rows(rows)
+        out = torch.empty(len(rows), dtype=torch.float64, device="cuda")
+        torch.cuda.current_stream().synchronize()
+        if len(rows):
+            self._check(self.E.gsb200_gebv_dev(self.ctx, len(rows), d_rows.data_ptr(), eff, out.data_ptr()))
+            self._check(self.E.gsb200_synchronize(self.ctx))
+        return out
 
     def gather_rows(self, rows):
-        rows = np.ascontiguousarray(rows, dtype=np.uint32)
         t = torch.empty((len(rows), self.row_bytes), dtype=torch.uint8, device="cuda")
         if len(rows):
-            d_rows = torch.from_numpy(rows.astype(np.int32)).cuda()
+            d_rows = self._dev_rows(rows)
             torch.cuda.current_stream().synchronize()
             self._check(self.E.gsb200_store_gather_rows_dev(self.ctx, len(rows), d_rows.data_ptr(), t.data_ptr()))
             self._check(self.E.gsb200_synchronize(self.ctx))
@@ -156,10 +176,9 @@ class EngineBackend:
 
     def adopt_rows(self, packed):
         packed = packed.contiguous()
-        torch.cuda.current_stream().synchronize()
         rows = self._take(packed.shape[0])
         if len(rows):
-            d_rows = torch.from_numpy(rows.astype(np.int32)).cuda()
+            d_rows = self._dev_rows(rows)
             torch.cuda.current_stream().synchronize()
             self._check(self.E.gsb200_store_scatter_rows_dev(self.ctx, len(rows), d_rows.data_ptr(), packed.data_ptr()))
             self._check(self.E.gsb200_synchronize(self.ctx))
@@ -167,10 +186,12 @@ class EngineBackend:
 
     def cross(self, p1_rows, p2_rows, map_index, seed, stream, first_unit):
         from ._lib import Draws
-        p1 = np.ascontiguousarray(p1_rows, dtype=np.uint32)
-        p2 = np.ascontiguousarray(p2_rows, dtype=np.uint32)
-        out = self._take(len(p1))
+        n = len(p1_rows)
+        out = self._take(n)
+        d_p1, d_p2, d_out = self._dev_rows(p1_rows), self._dev_rows(p2_rows), self._dev_rows(out)
+        torch.cuda.current_stream().synchronize()
         dr = Draws(mode=0, seed=seed, stream=stream, first_unit=first_unit)
-        self._check(self.E.gsb200_cross(self.ctx, len(out), p1.ctypes.data, p2.ctypes.data, map_index, map_index,
-                                        out.ctypes.data, C.byref(dr)))
+        self._check(self.E.gsb200_cross_dev(self.ctx, n, d_p1.data_ptr(), d_p2.data_ptr(), map_index, map_index,
+                                            d_out.data_ptr(), C.byref(dr)))
+        self._check(self.E.gsb200_cross_dev_status(self.ctx))      # synchronises
         return out

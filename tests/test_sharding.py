@@ -87,6 +87,11 @@ def test_offspring_range_and_selection():
     bv = np.array([1.0, 3.0, 3.0, -2.0, 0.5])
     assert sharding.select_global(bv, 2).tolist() == [1, 2]           # ties by lower index
     assert sharding.select_global(bv, 2, low_is_best=True).tolist() == [3, 4]
+    assert sharding.select_global(torch.from_numpy(bv), 2).tolist() == [1, 2]
+    # pairs do not depend on which slice of the generation a rank draws
+    a, b = sharding.draw_pairs(50, 200000, 9)
+    a2, b2 = sharding.draw_pairs(50, 200000, 9, 70000, 140001)
+    assert (a[70000:140001] == a2).all() and (b[70000:140001] == b2).all()
     a, b = sharding.draw_pairs(5, 1000, 3)
     assert (a != b).all() and a.min() >= 0 and a.max() <= 4
 
