@@ -46,7 +46,7 @@ void DeviceMap::release() {
 }
 
 void DeviceEffects::release() {
-    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag };
+    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag, d_digit_umma };
     for (void* p : ptrs) if (p) cudaFree(p);
     *this = DeviceEffects();
 }
@@ -115,8 +115,8 @@ int gsb200_create(gsb200_ctx** out, int device_ordinal, uint32_t n_markers) {
         delete ctx;
         return GSB200_ERR_CUDA;
     }
-    e = cudaMalloc((void**) &ctx->d_flag, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(ctx->d_flag, 0, sizeof(int));
+    e = cudaMalloc((void**) &ctx->d_flag, 4 * sizeof(int));      // [0] error flag, [1] task counter of persistent kernels
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_flag, 0, 4 * sizeof(int));
     if (e != cudaSuccess) {
         set_error("cudaMalloc(flag) failed: %s", cudaGetErrorString(e));
         cudaStreamDestroy(ctx->stream);

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
 
@@ -424,6 +425,9 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
             }
         }
         GSB_TRY(to_device_vec(frag, &e.d_digit_frag));
+        std::vector<uint32_t> ufrag;
+        build_umma_fragments(delta, M, words, exp2, ufrag);
+        GSB_TRY(to_device_vec(ufrag, &e.d_digit_umma));
     }
     e.built_for_dict_version = ctx->dict_version;
     e.built_for_planes = planes;
@@ -442,6 +446,15 @@ int gebv_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t ef
         GSB_TRY(ctx->s_eval[2].ensure((size_t) n * 8 * sizeof(long long)));
         unsigned long long* d_digits = (unsigned long long*) ctx->s_eval[2].ptr;
         GSB_CUDA_TRY(cudaMemsetAsync(d_digits, 0, (size_t) n * 8 * sizeof(long long), ctx->stream));
+        static const bool use_umma = [] { const char* v = getenv("GSB200_GEBV_PATH"); return v && strcmp(v, "umma") == 0; }();
+        if (use_umma) {
+            GSB_TRY(gebv_umma_launch(ctx, n, d_rows, e->d_digit_umma, d_digits));
+            gebv_finish_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const long long*) d_digits, n, e->digit_scale,
+                                                                        e->base_all - centre_sum, d_out);
+            ++ctx->launches;
+            GSB_CUDA_TRY(cudaGetLastError());
+            return GSB200_OK;
+        }
         const uint32_t chunks = ctx->plane_words / kChunkWords, n_groups = (n + 15) / 16;
         // enough marker segments to fill the machine a few times over
         uint32_t n_segments = (uint32_t) std::min<uint64_t>(chunks, ((uint64_t) ctx->sm_count * 64 * 4 + n_groups - 1) / n_groups);
