@@ -326,7 +326,7 @@ def engine_arm(a):
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f)
         roof["traffic"] = tr.get("splice_flat_kernel")
-        roof_g["traffic"] = tr.get("gebv_plane1_kernel")
+        roof_g["traffic"] = tr.get("gebv_digits_kernel")
     except Exception:
         pass
 

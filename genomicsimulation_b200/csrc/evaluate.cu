@@ -599,9 +599,7 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
     const uint32_t n_ranges = (uint32_t) range_lo.size() - 1;
 
     // per-pass device buffers: steps | ranges | per set: fragments, block bases
-    const size_t out_elems = (size_t) 2 * n * n_blocks;
     const size_t slab_rows = std::max<size_t>(8, std::min<size_t>(n, (((size_t) 1 << 30) / (2 * (size_t) n_blocks * sizeof(double))) / 8 * 8));
-    (void) out_elems;
     for (uint32_t q0 = 0; q0 < n_effect_sets; q0 += kLocalMaxSets) {
         const uint32_t sets = std::min<uint32_t>(kLocalMaxSets, n_effect_sets - q0);
         const size_t frag_bytes = (size_t) n_steps * 32 * sizeof(uint2);

@@ -406,3 +406,33 @@ def test_gebv_tcgen05_path():
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("n=")]
     assert len(lines) == 2 and all("path=umma" in l and l.rstrip().endswith("OK") for l in lines), out.stdout
+
+
+def test_config5_marker_count():
+    """BASELINE.json configs[4] marker count (600 000 SNPs, 21 chr) on a handful of individuals:
+    crossing replay, GEBV, local GEBV by 10 blocks per chromosome with 3 effect sets, allele counts."""
+    ds = datasets.synthetic(6, 600000, 21, 180.0, seed=50, spacing="random", n_effect_sets=3)
+    p = port.PortSim.from_dataset(ds)
+    port.seed(77)
+    port.record_start()
+    gp = [p.make_random_crosses(1, 12, family_size=2), ]
+    gp.append(p.self_n_times(2, gp[0]))
+    gp.append(p.make_doubled_haploids(gp[1]))
+    tape = port.record_stop().draws_only()
+    s = engine_from(ds)
+    with port.Replay(tape) as rp:
+        gs = [s.make_random_crosses(1, 12, 0, 1, family_size=2), ]
+        gs.append(s.self_n_times(2, gs[0], 1))
+        gs.append(s.make_doubled_haploids(gs[1], 1))
+    assert not rp.error and rp.consumed == len(tape) and gp == gs
+    scenarios.assert_same_state(scenarios.export_state(p), scenarios.export_state(s))
+    for e in range(3):
+        want = p.calculate_bvs(0, e)
+        bv_close(s.calculate_bvs(0, e + 1), want, scale=np.abs(want).mean())
+    off, mk = p.blocks_evenlength(10, 0, n_chr=21)
+    b = s.blocks_evenlength(10, 1)
+    for e in range(3):
+        want = p.calculate_local_bvs(gp[2], off, mk, e)
+        bv_close(s.calculate_local_bvs(gs[2], b, e + 1), want, scale=np.abs(want).mean())
+    np.testing.assert_array_equal(p.calculate_allele_counts(gp[0], "A"), s.calculate_allele_counts(gs[0], "A"))
+    p.close(); s.close()
