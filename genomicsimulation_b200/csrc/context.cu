@@ -46,7 +46,7 @@ void DeviceMap::release() {
 }
 
 void DeviceEffects::release() {
-    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag, d_digit_umma };
+    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag, d_digit_umma, d_local };
     for (void* p : ptrs) if (p) cudaFree(p);
     *this = DeviceEffects();
 }
@@ -139,6 +139,7 @@ void gsb200_destroy(gsb200_ctx* ctx) {
     for (auto& s : ctx->s_eval) s.release();
     for (auto& s : ctx->s_chain) s.release();
     ctx->s_null.release();
+    ctx->local_sched.d_steps.release();
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->d_store) cudaFree(ctx->d_store);
     if (ctx->d_dict_sym) cudaFree(ctx->d_dict_sym);

@@ -570,9 +570,30 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
     uint32_t* d_rows;
     GSB_TRY(upload_u32(ctx, ctx->s_rows[0], rows, n, &d_rows));
 
-    std::vector<uint2> steps;
-    std::vector<uint32_t> block_first;
-    if (!local_schedule(ctx, n_blocks, block_offsets, block_markers, steps, block_first)) {
+    // The step schedule and each effect set's digit fragments depend only on the blocks (and the
+    // dictionary): they are cached on the device under a hash of the block definition, so that a
+    // breeding scheme evaluating the same blocks every generation pays for them once.
+    uint64_t key = 1469598103934665603ull;
+    auto mix = [&](const uint32_t* p, size_t cnt) { for (size_t i = 0; i < cnt; ++i) { key ^= p[i]; key *= 1099511628211ull; } };
+    mix(&n_blocks, 1);
+    mix(block_offsets, (size_t) n_blocks + 1);
+    mix(block_markers, total);
+    key ^= ctx->dict_version * 0x9E3779B97F4A7C15ull;
+    key ^= (uint64_t) ctx->planes << 56;
+    LocalSchedule& sc = ctx->local_sched;
+    if (sc.key != key || !sc.valid) {
+        sc.steps.clear();
+        sc.block_first.clear();
+        sc.usable = local_schedule(ctx, n_blocks, block_offsets, block_markers, sc.steps, sc.block_first);
+        if (sc.usable) {
+            GSB_TRY(sc.d_steps.ensure(sc.steps.size() * sizeof(uint2)));
+            GSB_CUDA_TRY(cudaMemcpyAsync(sc.d_steps.ptr, sc.steps.data(), sc.steps.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+            GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+        sc.key = key;
+        sc.valid = true;
+    }
+    if (!sc.usable) {
         GSB_REQUIRE(!device_out, GSB200_ERR_UNSUPPORTED,
                     "%s: device output needs blocks that are contiguous, ascending, non-overlapping marker ranges on a one-plane store", what);
         uint32_t *d_off, *d_mk;
@@ -584,6 +605,8 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
     }
 
     // ---- tensor path
+    const std::vector<uint2>& steps = sc.steps;
+    const std::vector<uint32_t>& block_first = sc.block_first;
     const uint32_t M = ctx->n_markers, n_steps = (uint32_t) steps.size();
     // block ranges: tasks = (8 individuals) x (range of whole blocks), a few waves over the machine
     const uint32_t n_groups = (n + 7) / 8;
@@ -597,63 +620,61 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
     }
     range_lo.push_back(n_steps);
     const uint32_t n_ranges = (uint32_t) range_lo.size() - 1;
+    uint32_t* d_ranges;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[1], range_lo.data(), range_lo.size(), &d_ranges));
+    const uint2* d_steps = (const uint2*) sc.d_steps.ptr;
+    const size_t frag_bytes = (size_t) n_steps * 32 * sizeof(uint2);
 
-    // per-pass device buffers: steps | ranges | per set: fragments, block bases
+    // fragments + block bases of every effect set asked for (cached per set)
+    for (uint32_t q = 0; q < n_effect_sets; ++q) {
+        DeviceEffects* e = effs[q];
+        if (e->local_key == key && e->d_local) continue;
+        const std::vector<double>& vf = e->h_value_first;      // [M << 1]
+        double maxabs = 0.0;
+        for (uint32_t m = 0; m < M; ++m) maxabs = std::max(maxabs, std::fabs(vf[2 * (size_t) m + 1] - vf[2 * (size_t) m]));
+        int exp2v = 0;
+        if (maxabs > 0.0 && std::isfinite(maxabs)) exp2v = 61 - std::ilogb(maxabs);
+        e->local_scale = std::ldexp(1.0, -exp2v);
+        std::vector<uint32_t> frag((size_t) n_steps * 64 + 2 * (size_t) n_blocks, 0u);
+        double* base = reinterpret_cast<double*>(frag.data() + (size_t) n_steps * 64);
+        for (uint32_t st = 0; st < n_steps; ++st) {
+            const uint32_t w = steps[st].x, b = steps[st].y;
+            const uint32_t m_lo = block_markers[block_offsets[b]], m_hi = m_lo + (block_offsets[b + 1] - block_offsets[b]);
+            for (uint32_t bit = 0; bit < 32; ++bit) {
+                const uint32_t m = w * 32 + bit;
+                if (m < m_lo || m >= m_hi) continue;
+                const double d = vf[2 * (size_t) m + 1] - vf[2 * (size_t) m];
+                const uint32_t j = bit >> 3, sft = bit & 7, cc = sft & 3, half = sft >> 2;
+                long long qv = std::isfinite(d) ? std::llrint(std::ldexp(d, exp2v - (int) sft)) : 0;
+                for (uint32_t dg = 0; dg < 8; ++dg) {
+                    const long long d8 = ((qv + 128) & 255) - 128;
+                    qv = (qv - d8) >> 8;
+                    frag[((size_t) st * 32 + 4 * dg + cc) * 2 + half] |= ((uint32_t) (uint8_t) (int8_t) d8) << (8 * j);
+                }
+            }
+        }
+        for (uint32_t b = 0; b < n_blocks; ++b) {
+            double acc = 0.0;
+            for (uint32_t x = block_offsets[b]; x < block_offsets[b + 1]; ++x) {
+                const uint32_t m = block_markers[x];
+                acc += vf[2 * (size_t) m] - (e->has_centre ? e->centre[m] : 0.0);
+            }
+            base[b] = acc;
+        }
+        GSB_TRY(to_device_vec(frag, &e->d_local));
+        e->local_key = key;
+    }
+
     const size_t slab_rows = std::max<size_t>(8, std::min<size_t>(n, (((size_t) 1 << 30) / (2 * (size_t) n_blocks * sizeof(double))) / 8 * 8));
     for (uint32_t q0 = 0; q0 < n_effect_sets; q0 += kLocalMaxSets) {
         const uint32_t sets = std::min<uint32_t>(kLocalMaxSets, n_effect_sets - q0);
-        const size_t frag_bytes = (size_t) n_steps * 32 * sizeof(uint2);
-        const size_t base_bytes = (size_t) n_blocks * sizeof(double);
-        const size_t hdr = ((size_t) n_steps * sizeof(uint2) + (n_ranges + 1) * sizeof(uint32_t) + 255) / 256 * 256;
-        const size_t per_set = (frag_bytes + base_bytes + 255) / 256 * 256;
-        GSB_TRY(ctx->s_eval[3].ensure(hdr + per_set * sets));
-        char* dbase = (char*) ctx->s_eval[3].ptr;
-        GSB_CUDA_TRY(cudaMemcpyAsync(dbase, steps.data(), (size_t) n_steps * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-        GSB_CUDA_TRY(cudaMemcpyAsync(dbase + (size_t) n_steps * sizeof(uint2), range_lo.data(), (n_ranges + 1) * sizeof(uint32_t),
-                                     cudaMemcpyHostToDevice, ctx->stream));
         LocalSetParams sp;
         memset(&sp, 0, sizeof sp);
-        std::vector<std::vector<uint32_t>> frags(sets);
-        std::vector<std::vector<double>> bases(sets);
         for (uint32_t q = 0; q < sets; ++q) {
             DeviceEffects* e = effs[q0 + q];
-            const std::vector<double>& vf = e->h_value_first;      // [M << 1]
-            double maxabs = 0.0;
-            for (uint32_t m = 0; m < M; ++m) maxabs = std::max(maxabs, std::fabs(vf[2 * (size_t) m + 1] - vf[2 * (size_t) m]));
-            int exp2v = 0;
-            if (maxabs > 0.0 && std::isfinite(maxabs)) exp2v = 61 - std::ilogb(maxabs);
-            sp.scale[q] = std::ldexp(1.0, -exp2v);
-            frags[q].assign((size_t) n_steps * 64, 0u);
-            bases[q].assign(n_blocks, 0.0);
-            for (uint32_t st = 0; st < n_steps; ++st) {
-                const uint32_t w = steps[st].x, b = steps[st].y;
-                const uint32_t m_lo = block_markers[block_offsets[b]], m_hi = m_lo + (block_offsets[b + 1] - block_offsets[b]);
-                for (uint32_t bit = 0; bit < 32; ++bit) {
-                    const uint32_t m = w * 32 + bit;
-                    if (m < m_lo || m >= m_hi) continue;
-                    const double d = vf[2 * (size_t) m + 1] - vf[2 * (size_t) m];
-                    const uint32_t j = bit >> 3, sft = bit & 7, cc = sft & 3, half = sft >> 2;
-                    long long qv = std::isfinite(d) ? std::llrint(std::ldexp(d, exp2v - (int) sft)) : 0;
-                    for (uint32_t dg = 0; dg < 8; ++dg) {
-                        const long long d8 = ((qv + 128) & 255) - 128;
-                        qv = (qv - d8) >> 8;
-                        frags[q][((size_t) st * 32 + 4 * dg + cc) * 2 + half] |= ((uint32_t) (uint8_t) (int8_t) d8) << (8 * j);
-                    }
-                }
-            }
-            for (uint32_t b = 0; b < n_blocks; ++b) {
-                double acc = 0.0;
-                for (uint32_t x = block_offsets[b]; x < block_offsets[b + 1]; ++x) {
-                    const uint32_t m = block_markers[x];
-                    acc += vf[2 * (size_t) m] - (e->has_centre ? e->centre[m] : 0.0);
-                }
-                bases[q][b] = acc;
-            }
-            char* p = dbase + hdr + per_set * q;
-            GSB_CUDA_TRY(cudaMemcpyAsync(p, frags[q].data(), frag_bytes, cudaMemcpyHostToDevice, ctx->stream));
-            GSB_CUDA_TRY(cudaMemcpyAsync(p + frag_bytes, bases[q].data(), base_bytes, cudaMemcpyHostToDevice, ctx->stream));
-            sp.bfrag[q] = (const uint2*) p;
-            sp.base[q] = (const double*) (p + frag_bytes);
+            sp.bfrag[q] = (const uint2*) e->d_local;
+            sp.base[q] = (const double*) ((const char*) e->d_local + frag_bytes);
+            sp.scale[q] = e->local_scale;
         }
         // individuals in slabs: the device output of `sets` matrices stays bounded
         const size_t slab = device_out ? (size_t) n : std::max<size_t>(8, slab_rows / sets / 8 * 8);
@@ -667,8 +688,6 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
             }
             const uint64_t warps = (uint64_t) ((cnt + 7) / 8) * n_ranges;
             const unsigned grid = (unsigned) ((warps + kLocalWarps - 1) / kLocalWarps);
-            const uint2* d_steps = (const uint2*) dbase;
-            const uint32_t* d_ranges = (const uint32_t*) (dbase + (size_t) n_steps * sizeof(uint2));
 #define GSB_LOCAL_LAUNCH(S) local_gebv_digits_kernel<S><<<grid, kLocalWarps * 32, 0, ctx->stream>>>( \
                 ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows + done, cnt, n_blocks, d_steps, d_ranges, n_ranges, sp)
             switch (sets) {
@@ -686,7 +705,6 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
                                                  (size_t) cnt * 2 * n_blocks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         }
-        GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));     // frags/bases go out of scope
     }
     return GSB200_OK;
 }

@@ -108,8 +108,20 @@ struct DeviceEffects {
     uint32_t* d_digit_frag = nullptr; // planes == 1: fixed-point digits of delta as mma B fragments
     uint32_t* d_digit_umma = nullptr; // ... in the shared-memory layout of the tcgen05 path
     double  digit_scale = 1.0;        // value of one fixed-point unit
-    std::vector<double> h_value_first; // host copy of d_value_first (local-GEBV digit fragments are per call)
+    std::vector<double> h_value_first; // host copy of d_value_first (source of the local-GEBV digit fragments)
+    uint64_t  local_key = 0;           // block definition d_local was built for
+    uint32_t* d_local = nullptr;       // local GEBV: per-step digit fragments, then the per-block bases (fp64)
+    double    local_scale = 1.0;
     void release();
+};
+
+// Step schedule of the tensor-path local GEBV for the block definition last used.
+struct LocalSchedule {
+    bool valid = false, usable = false;
+    uint64_t key = 0;
+    std::vector<uint2> steps;           // (marker word, block)
+    std::vector<uint32_t> block_first;  // first step of each non-empty block, then n_steps
+    Scratch d_steps;
 };
 
 }  // namespace gsb
@@ -142,6 +154,7 @@ struct gsb200_ctx {
     gsb::Scratch s_plan[8];         // meiosis draw buffers
     gsb::Scratch s_eval[4];
     gsb::Scratch s_chain[2];        // ping-pong rows of chained selfing
+    gsb::LocalSchedule local_sched;
     gsb::Scratch s_null;            // per marker: the code that decodes to '\0' (uncovered markers)
     uint64_t null_built_for = ~0ull;
 

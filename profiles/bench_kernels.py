@@ -73,7 +73,7 @@ def main():
     for sets in (1, 4, 10):
         t = timeit(lambda: chk(E.gsb200_local_gebv_multi_dev(ctx, n_loc, ptr(out), len(off) - 1, ptr(off), ptr(mk), sets, ptr(effs), dptrs)), reps=3)
         line("gsb200_local_gebv_multi_dev 20k x 50k, 210 blk, %2d sets" % sets, t, (n_loc * M * sets, "marker.ind.set"),
-             n_loc * (M / 4 + sets * 2 * 210 * 8), "(device output; host builds + uploads digit fragments)")
+             n_loc * (M / 4 + sets * 2 * 210 * 8), "(device output; schedule + digit fragments cached on the device)")
     n_cnt = 4000
     cnt = np.zeros((n_cnt, M), dtype=np.uint8)
     t = timeit(lambda: chk(E.gsb200_allele_counts(ctx, n_cnt, ptr(out), b"T", 2, ptr(cnt))), reps=3)
