@@ -263,3 +263,40 @@ def test_kernels_stay_inside_their_rows_and_keep_padding_zero():
     g = download(sim, out[20:60])
     assert set(np.unique(g)) <= {ord("A"), ord("T")}
     sim.close()
+
+
+def test_store_round_trips_random_alphabets():
+    """chars -> packed planes -> chars over random marker counts, alphabets (1..9 symbols incl. '\\0')
+    and upload orders; allele counts and symbol edits against numpy on the same bytes."""
+    from genomicsimulation_b200 import SimData
+    rng = np.random.default_rng(123)
+    for trial in range(12):
+        M = int(rng.integers(1, 300))
+        n_sym = int(rng.integers(1, 10))
+        alphabet = rng.choice(np.arange(0, 128), size=n_sym, replace=False).astype(np.uint8)
+        if trial % 3 == 0:
+            alphabet[0] = 0
+        n = int(rng.integers(1, 40))
+        g = alphabet[rng.integers(0, n_sym, (n, 2 * M))]
+        sim = SimData(M)
+        # two uploads: the second may introduce symbols the first did not have (store widens in place)
+        half = max(1, n // 2)
+        assert sim.add_genotypes(g[:half]) == 1
+        if half < n:
+            g[half:, 0] = alphabet[-1]
+            assert sim.add_genotypes(g[half:]) == 2
+        got = sim.export_group(0)["genotypes"]
+        np.testing.assert_array_equal(got, g)
+        planes = sim.E.gsb200_store_planes(sim.ctx)
+        assert (1 << planes) >= min(n_sym, len(np.unique(g)))
+        a = int(alphabet[rng.integers(0, n_sym)])
+        cnt = sim.calculate_allele_counts(0, bytes([a]))
+        want = (g[:, 0::2] == a).astype(float) + (g[:, 1::2] == a)
+        np.testing.assert_array_equal(cnt, want)
+        if n_sym >= 2:
+            frm, to = int(alphabet[0]), int(alphabet[1])
+            assert sim.E.gsb200_store_change_symbol(sim.ctx, 0xFFFFFFFF, bytes([frm]), bytes([to])) == 0
+            g2 = g.copy()
+            g2[g2 == frm] = to
+            np.testing.assert_array_equal(sim.export_group(0)["genotypes"], g2)
+        sim.close()
