@@ -52,7 +52,7 @@ __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, 
 
 __device__ __forceinline__ void cp_async16(uint32_t* smem_dst, const uint32_t* gmem_src) {
     const uint32_t d = (uint32_t) __cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
