@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kThreads) gebv_umma_kernel(
         const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
         const uint32_t* __restrict__ rows, uint32_t n, const uint32_t* __restrict__ bfrag /* 64 words per marker word */,
         uint32_t n_segments, uint32_t seg_chunks, unsigned long long* __restrict__ digit_sums, int* __restrict__ flag,
-        unsigned int* __restrict__ task_counter, uint32_t dbg) {
+        unsigned int* __restrict__ task_counter) {
     extern __shared__ __align__(128) uint32_t s_dyn[];
     uint32_t (*s_b)[kBChunkWords] = reinterpret_cast<uint32_t (*)[kBChunkWords]>(s_dyn);
     uint32_t (*s_packed)[kPackedWords] = reinterpret_cast<uint32_t (*)[kPackedWords]>(s_dyn + kBBufs * kBChunkWords);
@@ -215,12 +215,10 @@ __global__ void __launch_bounds__(kThreads) gebv_umma_kernel(
             // A warp's operand registers are in TMEM: count it in; the LAST of the 4 warps to arrive issues
             // the four tcgen05.mma of the tile (no thread ever sleeps waiting for "all rows written").
             auto publish = [&](uint32_t stg, uint32_t tl) {
-                if (!(dbg & 8)) {
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    tc_fence_before();
-                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
                 __syncwarp();
-                if ((tid & 31) == 0 && !(dbg & 4)) {
+                if ((tid & 31) == 0) {
                     uint32_t old;
                     asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt_a + 4 * stg) : "memory");
                     if (old == kProducers / 32 - 1) {
@@ -244,7 +242,7 @@ __global__ void __launch_bounds__(kThreads) gebv_umma_kernel(
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(bar_packed_full + 8 * pb);  // ... this warp's
                 mbar_wait(bar_packed_full + 8 * pb, (cc / kPackedBufs) & 1, ok);   // ... everyone's
-                if (!(dbg & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // B bytes -> visible to the tensor core's proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // B bytes -> visible to the tensor core's proxy
                 const uint32_t* packed = s_packed[pb] + tid * kRowStride;
 #pragma unroll 1
                 for (uint32_t t = 0; t < 4; ++t, ++tile) {
@@ -254,13 +252,13 @@ __global__ void __launch_bounds__(kThreads) gebv_umma_kernel(
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) r[k * 8 + j] = (dbg & 2) ? w[k] : (w[k] & (0x01010101u << j));   // byte i = bit 8i + j, weight 2^j
+                        for (int j = 0; j < 8; ++j) r[k * 8 + j] = w[k] & (0x01010101u << j);   // byte i = bit 8i + j, weight 2^j
                     if (pending) publish(pending_stage, pending_tile);   // its store has had this tile's expansion to complete
-                    if (tiles_done + tile >= kAStages && !(dbg & 4)) {       // the mma that read this stage kAStages tiles ago
+                    if (tiles_done + tile >= kAStages) {                     // the mma that read this stage kAStages tiles ago
                         mbar_wait(bar_a_empty + 8 * st_stage, st_phase ^ 1, ok);
                         tc_fence_after();
                     }
-                    if (!(dbg & 1)) asm volatile(
+                    asm volatile(
                         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
                         "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
                         :: "r"(tmem + ((warp * 32) << 16) + 8 + 32 * st_stage),
@@ -284,7 +282,7 @@ __global__ void __launch_bounds__(kThreads) gebv_umma_kernel(
 #pragma unroll
                 for (uint32_t sg = 0; sg < kAStages; ++sg) {
                     const uint32_t uses = total > sg ? (total - sg + kAStages - 1) / kAStages : 0;
-                    if (uses && !(dbg & 4)) mbar_wait(bar_a_empty + 8 * sg, (uses - 1) & 1, ok);
+                    if (uses) mbar_wait(bar_a_empty + 8 * sg, (uses - 1) & 1, ok);
                 }
             }
             tc_fence_after();
@@ -345,7 +343,7 @@ int gebv_umma_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, const 
     const uint32_t grid = std::min<uint32_t>(ctas, n_groups * n_segments);
     GSB_CUDA_TRY(cudaFuncSetAttribute(gebv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes));
     gebv_umma_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(
-        ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, d_frag, n_segments, seg_chunks, d_digits, ctx->d_flag, d_counter, getenv("GSB200_DBG") ? (uint32_t) atoi(getenv("GSB200_DBG")) : 0u);
+        ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, d_frag, n_segments, seg_chunks, d_digits, ctx->d_flag, d_counter);
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
     return GSB200_OK;
