@@ -66,6 +66,7 @@ ENGINE_SYMBOLS = {
     "gsb200_store_gather_rows_dev": (I32, [VP, U32, VP, VP]),
     "gsb200_store_scatter_rows_dev": (I32, [VP, U32, VP, VP]),
     "gsb200_store_change_symbol": (I32, [VP, U32, C.c_char, C.c_char]),
+    "gsb200_store_dictionary": (I32, [VP, VP, VP]),
     "gsb200_store_symbols": (I32, [VP, U32, VP, U32]),
     "gsb200_map_set": (I32, [VP, U32, U32, VP, VP, VP, VP, VP]),
     "gsb200_map_delete": (I32, [VP, U32]),
@@ -86,6 +87,7 @@ ENGINE_SYMBOLS = {
     "gsb200_local_gebv_multi": (I32, [VP, U32, VP, U32, VP, VP, U32, VP, VP]),
     "gsb200_local_gebv_multi_dev": (I32, [VP, U32, VP, U32, VP, VP, U32, VP, VP]),
     "gsb200_allele_counts": (I32, [VP, U32, VP, C.c_char, I32, VP]),
+    "gsb200_allele_presence": (I32, [VP, U32, VP, VP]),
     "gsb200_top_n": (I32, [VP, U32, VP, U32, I32, VP]),
     "gsb200_kernel_launches": (U64, [VP]),
 }
@@ -131,6 +133,11 @@ HOST_SYMBOLS = {
     "gsb_calculate_allele_counts": (DecimalMatrix, [VP, UINT, C.c_char]),
     "gsb_calculate_local_bvs": (DecimalMatrix, [VP, UINT, MarkerBlocks, UINT]),
     "gsb_create_evenlength_blocks_each_chr": (MarkerBlocks, [VP, UINT, UINT]),
+    "gsb_calculate_optimal_haplotype": (None, [VP, UINT, C.c_char, VP]),
+    "gsb_calculate_optimal_bv": (C.c_double, [VP, UINT]),
+    "gsb_calculate_minimal_bv": (C.c_double, [VP, UINT]),
+    "gsb_calculate_optimal_possible_haplotype": (None, [VP, UINT, UINT, C.c_char, VP]),
+    "gsb_calculate_optimal_possible_bv": (C.c_double, [VP, UINT, UINT]),
     "gsb_split_by_bv": (UINT, [VP, UINT, UINT, UINT, C.c_bool]),
     "gsb_delete_dmatrix": (None, [C.POINTER(DecimalMatrix)]),
     "gsb_delete_markerblocks": (None, [C.POINTER(MarkerBlocks)]),

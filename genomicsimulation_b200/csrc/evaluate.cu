@@ -332,6 +332,34 @@ __global__ void allele_count_kernel(const uint32_t* __restrict__ store, uint64_t
     out[tid] = (T) ((sym[c0] == allele ? 1 : 0) + (sym[c1] == allele ? 1 : 0));
 }
 
+// ------------------------------------------------------------------ allele presence
+// present[code][word] |= markers of `word` at which some strand of some row carries `code`: the
+// OR-reduction behind gsc_calculate_optimal_possible_haplotype / _bv (core.c:10171-10222,
+// 10285-10346), which scan every genotype's chars for the alleles a group contains.
+__global__ void presence_kernel(const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words, uint32_t planes,
+                                const uint32_t* __restrict__ rows, uint32_t n, uint32_t rows_per_slab, uint32_t* __restrict__ present) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= plane_words) return;
+    const uint32_t lo = blockIdx.y * rows_per_slab, hi = min(lo + rows_per_slab, n);
+    const uint32_t codes = 1u << planes;
+    for (uint32_t c = 0; c < codes; ++c) {
+        uint32_t acc = 0;
+        for (uint32_t i = lo; i < hi; ++i) {
+            const uint32_t* row = store + (uint64_t) rows[i] * row_words + w;
+#pragma unroll 1
+            for (uint32_t h = 0; h < 2; ++h) {
+                uint32_t m = 0xffffffffu;
+                for (uint32_t p = 0; p < planes; ++p) {
+                    const uint32_t x = row[(uint64_t) (h * planes + p) * plane_words];
+                    m &= ((c >> p) & 1u) ? x : ~x;
+                }
+                acc |= m;
+            }
+        }
+        if (acc) atomicOr(&present[(size_t) c * plane_words + w], acc);
+    }
+}
+
 // ------------------------------------------------------------------ ranking
 // order-preserving map of fp64 to u64, inverted when the highest value is the best, so that an
 // ascending STABLE sort yields best-first with ties in input order.
@@ -763,6 +791,35 @@ int gsb200_allele_counts(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, char
                                      cudaMemcpyDeviceToHost, ctx->stream));
         GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
+    return GSB200_OK;
+}
+
+int gsb200_allele_presence(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint8_t* present) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    const char* what = "gsb200_allele_presence";
+    GSB_REQUIRE(present != nullptr, GSB200_ERR_ARG, "%s: null output", what);
+    const uint32_t M = ctx->n_markers, planes = ctx->planes, codes = 1u << planes;
+    memset(present, 0, (size_t) M << planes);
+    if (n == 0) return GSB200_OK;
+    GSB_TRY(check_rows(ctx, n, rows, what));
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint32_t* d_rows;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], rows, n, &d_rows));
+    const size_t bytes = (size_t) codes * ctx->plane_words * sizeof(uint32_t);
+    GSB_TRY(ctx->s_eval[1].ensure(bytes));
+    GSB_CUDA_TRY(cudaMemsetAsync(ctx->s_eval[1].ptr, 0, bytes, ctx->stream));
+    const uint32_t rows_per_slab = 256;
+    dim3 grid((ctx->plane_words + 127) / 128, (n + rows_per_slab - 1) / rows_per_slab);
+    presence_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->d_store, ctx->row_words(), ctx->plane_words, planes, d_rows, n, rows_per_slab,
+                                                   (uint32_t*) ctx->s_eval[1].ptr);
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    std::vector<uint32_t> masks((size_t) codes * ctx->plane_words);
+    GSB_CUDA_TRY(cudaMemcpyAsync(masks.data(), ctx->s_eval[1].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t c = 0; c < codes; ++c)
+        for (uint32_t m = 0; m < M; ++m)
+            present[((size_t) m << planes) + c] = (masks[(size_t) c * ctx->plane_words + (m >> 5)] >> (m & 31)) & 1u;
     return GSB200_OK;
 }
 

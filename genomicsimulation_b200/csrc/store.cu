@@ -366,6 +366,13 @@ int gsb200_store_change_symbol(gsb200_ctx* ctx, uint32_t marker, char from, char
     return GSB200_OK;
 }
 
+int gsb200_store_dictionary(const gsb200_ctx* ctx, char* symbols, uint16_t* n_codes) {
+    GSB_REQUIRE(ctx != nullptr && symbols != nullptr && n_codes != nullptr, GSB200_ERR_ARG, "gsb200_store_dictionary: null argument");
+    memcpy(symbols, ctx->dict_sym.data(), ctx->dict_sym.size());
+    memcpy(n_codes, ctx->dict_n.data(), ctx->dict_n.size() * sizeof(uint16_t));
+    return GSB200_OK;
+}
+
 int gsb200_store_symbols(const gsb200_ctx* ctx, uint32_t marker, char* out, uint32_t cap) {
     if (!ctx || marker >= ctx->n_markers) return 0;
     const uint32_t nc = ctx->dict_n[marker];

@@ -254,6 +254,28 @@ class SimData:
     def blocks_evenlength(self, n, map_id=0, n_chr=None):
         return Blocks(self.L, self.L.gsb_create_evenlength_blocks_each_chr(self.d, map_id, n))
 
+    def optimal_haplotype(self, eff_id, na=b"-"):
+        buf = C.create_string_buffer(self.M + 1)
+        self.L.gsb_calculate_optimal_haplotype(self.d, eff_id, C.c_char(na), buf)
+        return buf.raw[:self.M]
+
+    def optimal_bv(self, eff_id):
+        return self.L.gsb_calculate_optimal_bv(self.d, eff_id)
+
+    def minimal_bv(self, eff_id):
+        return self.L.gsb_calculate_minimal_bv(self.d, eff_id)
+
+    def optimal_possible_haplotype(self, group, eff_id, na=b"-"):
+        buf = C.create_string_buffer(self.M + 1)
+        self.L.gsb_calculate_optimal_possible_haplotype(self.d, group, eff_id, C.c_char(na), buf)
+        self._check()
+        return buf.raw[:self.M]
+
+    def optimal_possible_bv(self, group, eff_id):
+        v = self.L.gsb_calculate_optimal_possible_bv(self.d, group, eff_id)
+        self._check()
+        return v
+
     def split_by_bv(self, group, eff_id, top_n, low_is_best=False):
         g = self.L.gsb_split_by_bv(self.d, group, eff_id, top_n, bool(low_is_best))
         self._check()

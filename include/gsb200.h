@@ -86,6 +86,8 @@ int  gsb200_store_gather_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d
 int  gsb200_store_scatter_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, const void* d_dense);
 /* gsc_change_allele_symbol (core.c:1029-1100) for one marker (marker == UINT32_MAX: all). */
 int  gsb200_store_change_symbol(gsb200_ctx* ctx, uint32_t marker, char from, char to);
+/* the whole dictionary: symbols[(m << planes) + code] and n_codes[m] (codes defined at marker m) */
+int  gsb200_store_dictionary(const gsb200_ctx* ctx, char* symbols, uint16_t* n_codes);
 /* dictionary of one marker: up to 2^planes symbols, returns how many are defined */
 int  gsb200_store_symbols(const gsb200_ctx* ctx, uint32_t marker, char* out, uint32_t cap);
 
@@ -205,6 +207,11 @@ int  gsb200_local_gebv_multi_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
 enum { GSB200_COUNTS_F64 = 0, GSB200_COUNTS_I32 = 1, GSB200_COUNTS_U8 = 2 };
 int  gsb200_allele_counts(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, char allele,
                           int out_kind, void* out);
+
+/* Which alleles a set of genotypes carries: present[(m << planes) + code] = 1 if some strand of some
+ * row has `code` at marker m.  The genotype scan of gsc_calculate_optimal_possible_haplotype /
+ * gsc_calculate_optimal_possible_bv (core.c:10171-10222, 10285-10346) as an OR-reduction. */
+int  gsb200_allele_presence(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint8_t* present);
 
 /* The ranking step of gsc_split_by_bv (core.c:9489-9508): positions (0..n-1) of the
  * `top_n` best values, best first; ties broken by lower position (the reference leaves

@@ -138,6 +138,12 @@ unsigned int gsb_get_group_bvs(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID 
 gsb_DecimalMatrix gsb_calculate_allele_counts(gsb_SimData* d, gsb_GroupNum group, char allele);
 gsb_DecimalMatrix gsb_calculate_local_bvs(gsb_SimData* d, gsb_GroupNum group, gsb_MarkerBlocks b, gsb_EffectID effID);
 gsb_MarkerBlocks gsb_create_evenlength_blocks_each_chr(const gsb_SimData* d, gsb_MapID mapid, unsigned int n);
+/* optimal haplotypes / breeding values (core.c:10112-10392); opt_haplotype needs n_markers + 1 chars */
+void gsb_calculate_optimal_haplotype(const gsb_SimData* d, gsb_EffectID effID, char symbol_na, char* opt_haplotype);
+double gsb_calculate_optimal_bv(const gsb_SimData* d, gsb_EffectID effID);
+double gsb_calculate_minimal_bv(const gsb_SimData* d, gsb_EffectID effID);
+void gsb_calculate_optimal_possible_haplotype(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID effID, char symbol_na, char* opt_haplotype);
+double gsb_calculate_optimal_possible_bv(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID effID);
 gsb_GroupNum gsb_split_by_bv(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID effID, unsigned int top_n, _Bool lowIsBest);
 void gsb_delete_dmatrix(gsb_DecimalMatrix* m);          /* core.c:4628-4641 */
 void gsb_delete_markerblocks(gsb_MarkerBlocks* b);      /* core.c:4757-4766 */

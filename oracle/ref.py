@@ -330,6 +330,28 @@ class RefSim:
         assert rows == n
         return out
 
+    def optimal_haplotype(self, eff_id, na=b"-"):
+        buf = C.create_string_buffer(self.n_markers + 1)
+        self.L.refb_optimal_haplotype(self.d, eff_id, C.c_char(na), buf)
+        return buf.raw[:self.n_markers]
+
+    def optimal_possible_haplotype(self, group, eff_id, na=b"-"):
+        buf = C.create_string_buffer(self.n_markers + 1)
+        self.L.refb_optimal_possible_haplotype(self.d, group, eff_id, C.c_char(na), buf)
+        return buf.raw[:self.n_markers]
+
+    def optimal_bv(self, eff_id):
+        self.L.refb_optimal_bv.restype = C.c_double
+        return self.L.refb_optimal_bv(self.d, eff_id)
+
+    def minimal_bv(self, eff_id):
+        self.L.refb_minimal_bv.restype = C.c_double
+        return self.L.refb_minimal_bv(self.d, eff_id)
+
+    def optimal_possible_bv(self, group, eff_id):
+        self.L.refb_optimal_possible_bv.restype = C.c_double
+        return self.L.refb_optimal_possible_bv(self.d, group, eff_id)
+
     def split_by_bv(self, group, eff_id, top_n, low_is_best=False):
         return self.L.refb_split_by_bv(self.d, group, eff_id, top_n, int(low_is_best))
 

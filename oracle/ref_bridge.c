@@ -175,6 +175,17 @@ EXPORT unsigned refb_make_all_unidirectional_crosses(void* d, unsigned group, un
     return gsc_make_all_unidirectional_crosses((gsc_SimData*) d, (gsc_GroupNum){.num = group},
                                                (gsc_MapID){.id = map_id}, make_opts(opt, np, fp)).num;
 }
+EXPORT void refb_optimal_haplotype(void* d, unsigned eff_id, char na, char* out) {
+    gsc_calculate_optimal_haplotype((gsc_SimData*) d, (gsc_EffectID){.id = eff_id}, na, out);
+}
+EXPORT void refb_optimal_possible_haplotype(void* d, unsigned group, unsigned eff_id, char na, char* out) {
+    gsc_calculate_optimal_possible_haplotype((gsc_SimData*) d, (gsc_GroupNum){.num = group}, (gsc_EffectID){.id = eff_id}, na, out);
+}
+EXPORT double refb_optimal_bv(void* d, unsigned eff_id) { return gsc_calculate_optimal_bv((gsc_SimData*) d, (gsc_EffectID){.id = eff_id}); }
+EXPORT double refb_minimal_bv(void* d, unsigned eff_id) { return gsc_calculate_minimal_bv((gsc_SimData*) d, (gsc_EffectID){.id = eff_id}); }
+EXPORT double refb_optimal_possible_bv(void* d, unsigned group, unsigned eff_id) {
+    return gsc_calculate_optimal_possible_bv((gsc_SimData*) d, (gsc_GroupNum){.num = group}, (gsc_EffectID){.id = eff_id});
+}
 EXPORT unsigned refb_make_crosses_from_file(void* d, const char* path, unsigned map1, unsigned map2,
                                             const unsigned opt[8], const char* np, const char* fp) {
     return gsc_make_crosses_from_file((gsc_SimData*) d, path, (gsc_MapID){.id = map1}, (gsc_MapID){.id = map2},

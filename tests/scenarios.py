@@ -38,6 +38,20 @@ def crossing_scheme(sim, founders, small=False):
     return groups
 
 
+def naming_scheme(sim, founders):
+    """Names: prefix + id counter per 1000-genotype buffer (core.c:552-591, 8168-8180), clones that
+    inherit their parent's name (core.c:9097-9108), unnamed offspring, ids switched off."""
+    m0 = sim.map_arg(0)
+    groups = []
+    groups.append(sim.make_random_crosses(founders, 7, 0, m0, family_size=3, name_offspring=True, name_prefix="F1_"))
+    groups.append(sim.make_clones(groups[0], inherit_names=True))
+    groups.append(sim.make_clones(founders, inherit_names=False, name_offspring=True, name_prefix="cl"))
+    groups.append(sim.self_n_times(1, groups[0], m0, allocate_ids=False, name_offspring=True, name_prefix="S"))
+    groups.append(sim.make_doubled_haploids(groups[3], m0))
+    groups.append(sim.make_random_crosses(groups[1], 1100, 0, m0, name_offspring=True, name_prefix="big"))
+    return groups
+
+
 def export_state(sim):
     x = sim.export_group(0)
     return dict(genotypes=x["genotypes"], ids=x["ids"], ped1=x["ped1"], ped2=x["ped2"], groups=x["groups"])

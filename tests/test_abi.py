@@ -60,3 +60,29 @@ def test_product_does_not_import_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
                 assert "gs_oracle" not in txt and "libgsoracle" not in txt, f
+
+
+def _compile_capi(out):
+    import subprocess
+    lib = os.path.join(ROOT, "genomicsimulation_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "test_capi.c"), "-L" + lib, "-lgsb200_gsc", "-lgsb200",
+                           "-Wl,-rpath," + lib, "-lm", "-o", out])
+
+
+def test_headers_are_plain_c_and_the_c_client_links(tmp_path):
+    """include/*.h compile as strict C11 and a pure-C client of the mirror API links against the two
+    shared objects (what r-wrappers.c would do)."""
+    import genomicsimulation_b200 as g
+    g.host()
+    _compile_capi(str(tmp_path / "test_capi"))
+
+
+@pytest.mark.gpu
+def test_c_client_runs_a_breeding_scheme(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "test_capi")
+    _compile_capi(exe)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "capi ok: 216 genotypes" in out.stdout

@@ -436,3 +436,54 @@ def test_config5_marker_count():
         bv_close(s.calculate_local_bvs(gs[2], b, e + 1), want, scale=np.abs(want).mean())
     np.testing.assert_array_equal(p.calculate_allele_counts(gp[0], "A"), s.calculate_allele_counts(gs[0], "A"))
     p.close(); s.close()
+
+
+def test_names_ids_and_pedigrees_match_the_oracle():
+    """Offspring names, ids and pedigrees as the reference hands them out (scenarios.naming_scheme)."""
+    ds = datasets.synthetic(9, 200, 2, 100.0, seed=61)
+    p = port.PortSim.from_dataset(ds)
+    port.seed(4)
+    port.record_start()
+    gp = scenarios.naming_scheme(p, 1)
+    tape = port.record_stop().draws_only()
+    s = engine_from(ds)
+    with port.Replay(tape) as rp:
+        gs = scenarios.naming_scheme(s, 1)
+    assert not rp.error and rp.consumed == len(tape) and gp == gs
+    assert p.group_names(0) == s.group_names(0)
+    scenarios.assert_same_state(scenarios.export_state(p), scenarios.export_state(s))
+    p.close(); s.close()
+
+
+def test_optimal_haplotypes_known_answers(helper):
+    """test-calculators.R:238-273: see.optimal.haplotype "TAA"/"AAA", see.optimal.GEBV 1.8/4.2,
+    see.minimal.GEBV -2.8/-0.696, see.optimal.possible.* on the whole group and on {G05, G06}."""
+    s = engine_from(datasets.from_jsonable(helper["dataset"]))
+    assert s.optimal_haplotype(1) == b"TAA" and s.optimal_haplotype(2) == b"AAA"
+    np.testing.assert_allclose([s.optimal_bv(1), s.minimal_bv(1), s.optimal_bv(2), s.minimal_bv(2)], [1.8, -2.8, 4.2, -0.696], atol=1e-12)
+    assert s.optimal_possible_haplotype(1, 1) == b"TAA"
+    np.testing.assert_allclose(s.optimal_possible_bv(1, 1), 1.8, atol=1e-12)
+    g2 = s.make_group_from([4, 5])
+    assert s.optimal_possible_haplotype(g2, 1) == b"TAT"
+    np.testing.assert_allclose(s.optimal_possible_bv(g2, 1), 1.4, atol=1e-12)
+    s.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not present")
+def test_optimal_possible_matches_the_reference(tmp_path):
+    """Allele-presence OR-reduction + effect-table walk against the reference's genotype scan, on a
+    4-allele dataset with unknowns (several bit-planes) and on subgroups that lack some alleles."""
+    ds = datasets.synthetic(14, 900, 3, 100.0, seed=70, spacing="random", alleles=(b"A", b"C", b"G", b"T"), missing_rate=0.05)
+    gf, mf, ef = datasets.write_files(ds, str(tmp_path))
+    r = ref.RefSim()
+    ref.set_print_mode(0)
+    g, m, e = r.load(gf, mf, ef)
+    s = engine_from(datasets.from_ref(r, g))
+    for members in ([0, 1], [2, 5, 7, 11], list(range(14))):
+        gr = r.make_group_from(members)
+        gs = s.make_group_from(members)
+        assert r.optimal_possible_haplotype(gr, e) == s.optimal_possible_haplotype(gs, 1)
+        np.testing.assert_allclose(s.optimal_possible_bv(gs, 1), r.optimal_possible_bv(gr, e), rtol=1e-12)
+    assert r.optimal_haplotype(e) == s.optimal_haplotype(1)
+    np.testing.assert_allclose([s.optimal_bv(1), s.minimal_bv(1)], [r.optimal_bv(e), r.minimal_bv(e)], rtol=1e-12)
+    r.close(); s.close()

@@ -210,3 +210,26 @@ def test_reference_known_answers_through_shim():
     b = r.blocks_evenlength(3)
     assert r.calculate_local_bvs(g, b, e)[0].tolist() == [0.9, 0, -0.1, -0.1, 0, 0]
     r.close()
+
+
+@needs_ref
+def test_port_names_match_reference():
+    """Offspring names (prefix + counter per 1000-genotype buffer, inherited clone names) in the
+    restatement against the unmodified reference."""
+    ds = datasets.synthetic(9, 200, 2, 100.0, seed=61)
+    d = tempfile.mkdtemp()
+    gf, mf, ef = datasets.write_files(ds, d)
+    r = ref.RefSim()
+    ref.set_print_mode(0)
+    g, m, e = r.load(gf, mf, ef)
+    ref.seed(4)
+    ref.record_start()
+    groups_r = scenarios.naming_scheme(r, g)
+    tape = ref.record_stop()
+    p = port.PortSim.from_dataset(datasets.from_ref(r, g))
+    with port.Replay(tape) as rp:
+        groups_p = scenarios.naming_scheme(p, 1)
+    assert not rp.error and rp.consumed == len(tape) and groups_r == groups_p
+    assert r.group_names(0) == p.group_names(0)
+    scenarios.assert_same_state(scenarios.export_state(r), scenarios.export_state(p))
+    r.close(); p.close()
