@@ -46,7 +46,7 @@ void DeviceMap::release() {
 }
 
 void DeviceEffects::release() {
-    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag, d_digit_umma, d_local };
+    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag, d_digit_tc5, d_local };
     for (void* p : ptrs) if (p) cudaFree(p);
     *this = DeviceEffects();
 }

@@ -25,24 +25,20 @@ using namespace gsb;
 namespace {
 
 // ------------------------------------------------------------------ GEBV, one plane
-// BV_i = base + sum_m delta_m * (bit0_im + bit1_im) is a {0,1}-matrix times a vector.  Walking it
+// BV_i = base + sum_m delta_m * (bit0_im + bit1_im) is a {0,1,2}-matrix times a vector.  Walking it
 // marker by marker on the CUDA cores costs ~5 instructions (two of them FP64) per marker and
 // individual — 4x more issue slots than the 1/4 byte per marker the HBM stream delivers.  So the
 // product is done EXACTLY in integers on the tensor cores instead: delta_m is turned (on the
 // host, once per effect set) into a 62-bit fixed-point number split into 8 balanced base-256
 // digits, the digits are the 8 columns of the B operand of mma.m16n8k32 (u8 x s8 -> s32), the
-// genotype bits of 16 individuals x 32 markers — expanded to 0/1 bytes with one shift and one
-// AND per register, by choosing the k <-> marker permutation so that a register's four bytes
-// are bits 8 apart — are the A operand, and the eight int32 digit sums per individual are
-// recombined in fp64 at the end.  Integer accumulation is exact and order-free, so marker
-// segments can be summed with integer atomics and the result is still deterministic.
+// allele counts of 16 individuals x 32 markers are the A operand, and the eight int32 digit
+// sums per individual are recombined in fp64 at the end.  Integer accumulation is exact and
+// order-free, so marker segments can be summed with integer atomics and the result is still
+// deterministic.
 constexpr int kGebvWarps = 4;                  // warps per block, 16 individuals each
+constexpr int kGebvMinBlocks = 7;              // per SM: 72 registers
 constexpr uint32_t kGebvMaxMarkers = 1u << 26;
-constexpr uint32_t kChunkWords = 16;           // 512 markers = 4 mma tiles of 128 = 64 bytes per strand row
-constexpr uint32_t kChunkTiles = kChunkWords / 4;
-constexpr uint32_t kRowStride = 20;            // words: 64 B + 16 B pad -> the 8 row reads of an LDS.128 hit 32 distinct banks
-constexpr uint32_t kBufWords = 32 * kRowStride;   // 16 individuals x 2 strands; small on purpose: what shared
-                                                  // memory does not take stays L1 for the B fragments
+constexpr uint32_t kChunkWords = 16;           // 512 markers = 16 mma = 64 bytes per strand row
 constexpr uint32_t kGebvMaxSegChunks = 64;     // 32768 markers * 128 * 128 < 2^31
 
 __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -57,85 +53,110 @@ __device__ __forceinline__ void cp_async16(uint32_t* smem_dst, const uint32_t* g
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-// One warp = 16 individuals x one segment of marker chunks.  The warp streams its 32 strand rows
-// through shared memory with 16-byte cp.async (64 contiguous bytes per row and chunk),
-// double-buffered; lanes then pick their mma A words
-// with conflict-free LDS.128.  An A byte is `strand_word & mask`: bit 8j+s of the word, left at
-// the weight 2^s its position gives it; the weight is divided out of the digits on the host
-// (ensure_effect_tables).
-// bfrag[(w * 32 + lane)] = the two B registers of `lane` for marker word w.
-__global__ void __launch_bounds__(kGebvWarps * 32) gebv_digits_kernel(
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// One block = 4 warps x 16 individuals x one segment of marker chunks.
+//   * lane (g, c) loads words 4c..4c+3 of a 16-word chunk of the two strands of individuals g and
+//     g + 8 straight into registers (LDG.128; the four lanes of a row cover 64 contiguous bytes),
+//     one chunk ahead, two chunks per loop trip so that no register is ever copied;
+//   * the two strands are ADDED before the tensor core sees them, so an A row is an individual,
+//     not a strand, and one mma covers 16 individuals: with x = w0 ^ w1 (one copy) and
+//     a = w0 & w1 (two copies), ye = (x & 0x55..) | ((a << 1) & 0xAA..) holds the allele count of
+//     every even-numbered marker of the word as a 2-bit field, yo = ((x >> 1) & 0x55..) | (a & 0xAA..)
+//     that of every odd-numbered one: 6 logic ops per word pair, then ONE op per A register,
+//     `ye & (0x03030303 << 2p)`: byte j = count(marker 8j + 2p) at weight 4^p.  The weight is
+//     divided out of the digits on the host (ensure_effect_tables);
+//   * every lane uses the same masks, so they are immediates; mma (i, p) of a chunk contracts
+//     k = 4c + j with marker bit 8j + 2p of word 4c + i and k = 16 + 4c + j with bit 8j + 2p + 1;
+//   * the B fragments of a chunk (4 KB) are shared by the block's warps through shared memory
+//     (cp.async, double-buffered, one barrier per chunk): read through L1 they missed often
+//     enough to stall the mma on its operand.
+// bfrag[(chunk * 8 + i * 2 + p / 2) * 32 + lane] (uint4) = the B registers of `lane` for mma
+// (i, p) and (i, p + 1), p even.
+// What bounds it: the logic ops (alu pipe, one per 2 cycles and scheduler) and IMMA.16832 (~10
+// cycles) do not overlap on sm_100a — their pipe-active percentages add up to ~95 %
+// (profiles/r1_pipe_overlap.txt).
+__global__ void __launch_bounds__(kGebvWarps * 32, kGebvMinBlocks) gebv_counts_kernel(
         const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
-        const uint32_t* __restrict__ rows, uint32_t n, const uint2* __restrict__ bfrag,
-        uint32_t n_segments, uint32_t seg_chunks, unsigned long long* __restrict__ digit_sums) {
-    __shared__ __align__(16) uint32_t s_buf[kGebvWarps][2][kBufWords];
+        const uint32_t* __restrict__ rows, uint32_t n, const uint4* __restrict__ bfrag,
+        uint32_t group_blocks, uint32_t n_segments, uint32_t seg_chunks, unsigned long long* __restrict__ digit_sums) {
+    __shared__ __align__(16) uint4 s_b[2][256];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t warp_global = blockIdx.x * kGebvWarps + warp;
     const uint32_t n_groups = (n + 15) / 16;
-    if (warp_global >= n_groups * n_segments) return;
-    const uint32_t group = warp_global % n_groups, seg = warp_global / n_groups;   // neighbours share B
+    // neighbouring blocks read the same rows (all their segments), last rows of the list first: what a
+    // preceding kernel wrote last is still in L2
+    const uint32_t seg = blockIdx.x % n_segments, group = (group_blocks - 1 - blockIdx.x / n_segments) * kGebvWarps + warp;
     const uint32_t g = lane >> 2, c = lane & 3;
     const uint32_t ch_lo = seg * seg_chunks, ch_hi = min(ch_lo + seg_chunks, plane_words / kChunkWords);
-    if (ch_lo >= ch_hi) return;
+    if (ch_lo >= ch_hi) return;                              // whole block
 
-    // staging role: copy `it` moves 16 bytes of strand row r = it*8 + lane/4 (individual r & 15, strand r >> 4)
-    const uint32_t my_row = rows[min(group * 16 + (lane & 15), n - 1)];
-    uint32_t stage_row[4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) stage_row[it] = __shfl_sync(0xffffffffu, my_row, (it * 8 + (lane >> 2)) & 15);
-    const uint32_t* stage_base = store + (lane & 3) * 4;
-    auto stage = [&](uint32_t ch, uint32_t* buf) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const uint32_t r = it * 8 + (lane >> 2);
-            cp_async16(buf + r * kRowStride + (lane & 3) * 4,
-                       stage_base + (uint64_t) stage_row[it] * row_words + (r >> 4) * plane_words + ch * kChunkWords);
-        }
+    auto stage_b = [&](uint32_t ch) {
+        for (uint32_t i = threadIdx.x; i < 256; i += kGebvWarps * 32)
+            cp_async16(reinterpret_cast<uint32_t*>(&s_b[(ch - ch_lo) & 1][i]), reinterpret_cast<const uint32_t*>(bfrag + (size_t) ch * 256 + i));
         cp_async_commit();
     };
+    stage_b(ch_lo);
 
-    int acc0[4] = { 0, 0, 0, 0 }, acc1[4] = { 0, 0, 0, 0 };
-    // A rows are STRANDS: row g = strand 0 of an individual, row g + 8 = its strand 1, so a register
-    // is one LOP3: byte j = bit 8j + s of the strand's word, left at weight 2^s (s = c for a0/a1,
-    // c + 4 for a2/a3).  One mma covers 8 individuals; the warp issues two per marker word
-    // (individuals g and g + 8 of its 16) on the same B registers.  The expansion runs on the ALU
-    // pipe (one LOP3 per 2 cycles per scheduler), which is what bounds this kernel.
-    const uint32_t k_lo = 0x01010101u << c, k_hi = k_lo << 4;
-    auto word = [&](uint32_t a_s0, uint32_t a_s1, uint32_t b_s0, uint32_t b_s1, const uint2& f) {
-        mma_u8s8(acc0, a_s0 & k_lo, a_s1 & k_lo, a_s0 & k_hi, a_s1 & k_hi, f.x, f.y);
-        mma_u8s8(acc1, b_s0 & k_lo, b_s1 & k_lo, b_s0 & k_hi, b_s1 & k_hi, f.x, f.y);
+    // a warp past the last group walks the last group's rows (it must keep the barriers) and adds nothing
+    const uint32_t ia = min(group, n_groups - 1) * 16 + g, ib = ia + 8;
+    const uint4* pa0 = reinterpret_cast<const uint4*>(store + (uint64_t) rows[min(ia, n - 1)] * row_words) + c;
+    const uint4* pb0 = reinterpret_cast<const uint4*>(store + (uint64_t) rows[min(ib, n - 1)] * row_words) + c;
+    const uint32_t strand1 = plane_words / 4;          // uint4 units
+
+    int acc0[4] = { 0, 0, 0, 0 }, acc1[4] = { 0, 0, 0, 0 };      // two chains, for mma latency
+    struct Rows { uint4 a0, a1, b0, b1; };
+    auto load = [&](uint32_t ch, Rows& r) {
+        const uint32_t o = min(ch, ch_hi - 1) * 4;
+        r.a0 = ldg_stream(pa0 + o); r.a1 = ldg_stream(pa0 + strand1 + o);
+        r.b0 = ldg_stream(pb0 + o); r.b1 = ldg_stream(pb0 + strand1 + o);
     };
-    stage(ch_lo, s_buf[warp][0]);
-    for (uint32_t ch = ch_lo; ch < ch_hi; ++ch) {
-        const uint32_t* buf = s_buf[warp][(ch - ch_lo) & 1];
-        if (ch + 1 < ch_hi) { stage(ch + 1, s_buf[warp][(ch - ch_lo + 1) & 1]); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncwarp();
-        const uint2* f = bfrag + (size_t) ch * (kChunkWords * 32) + lane;
-#pragma unroll 2
-        for (uint32_t t = 0; t < kChunkTiles; ++t) {
-            const uint4 xa0 = *reinterpret_cast<const uint4*>(buf + g * kRowStride + t * 4);
-            const uint4 xb0 = *reinterpret_cast<const uint4*>(buf + (g + 8) * kRowStride + t * 4);
-            const uint4 xa1 = *reinterpret_cast<const uint4*>(buf + (16 + g) * kRowStride + t * 4);
-            const uint4 xb1 = *reinterpret_cast<const uint4*>(buf + (24 + g) * kRowStride + t * 4);
-            const uint2 f0 = __ldg(f + (t * 4 + 0) * 32), f1 = __ldg(f + (t * 4 + 1) * 32);
-            const uint2 f2 = __ldg(f + (t * 4 + 2) * 32), f3 = __ldg(f + (t * 4 + 3) * 32);
-            word(xa0.x, xa1.x, xb0.x, xb1.x, f0);
-            word(xa0.y, xa1.y, xb0.y, xb1.y, f1);
-            word(xa0.z, xa1.z, xb0.z, xb1.z, f2);
-            word(xa0.w, xa1.w, xb0.w, xb1.w, f3);
+    auto word = [&](uint32_t a_s0, uint32_t a_s1, uint32_t b_s0, uint32_t b_s1, const uint4* fw) {
+        const uint32_t xa = a_s0 ^ a_s1, ca = a_s0 & a_s1, xb = b_s0 ^ b_s1, cb = b_s0 & b_s1;
+        const uint32_t ae = (xa & 0x55555555u) | ((ca << 1) & 0xaaaaaaaau), ao = ((xa >> 1) & 0x55555555u) | (ca & 0xaaaaaaaau);
+        const uint32_t be = (xb & 0x55555555u) | ((cb << 1) & 0xaaaaaaaau), bo = ((xb >> 1) & 0x55555555u) | (cb & 0xaaaaaaaau);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t m0 = 0x03030303u << (4 * q), m1 = 0x0c0c0c0cu << (4 * q);
+            const uint4 fr = fw[q * 32];
+            mma_u8s8(acc0, ae & m0, be & m0, ao & m0, bo & m0, fr.x, fr.y);
+            mma_u8s8(acc1, ae & m1, be & m1, ao & m1, bo & m1, fr.z, fr.w);
         }
-        __syncwarp();      // everyone is done with `buf` before the next iteration overwrites it
+    };
+    // B of chunk `ch` has landed and everyone is done with the other buffer: refill that one, use this one
+    auto chunk = [&](uint32_t ch, const Rows& r) {
+        cp_async_wait<0>();
+        __syncthreads();
+        if (ch + 1 < ch_hi) stage_b(ch + 1);
+        const uint4* f = s_b[(ch - ch_lo) & 1] + lane;
+        word(r.a0.x, r.a1.x, r.b0.x, r.b1.x, f);
+        word(r.a0.y, r.a1.y, r.b0.y, r.b1.y, f + 2 * 32);
+        word(r.a0.z, r.a1.z, r.b0.z, r.b1.z, f + 4 * 32);
+        word(r.a0.w, r.a1.w, r.b0.w, r.b1.w, f + 6 * 32);
+    };
+    Rows x, y;
+    load(ch_lo, x);
+    for (uint32_t ch = ch_lo; ch < ch_hi; ch += 2) {             // two chunks per trip: no register shuffling
+        load(ch + 1, y);
+        chunk(ch, x);
+        if (ch + 1 < ch_hi) {                                    // block-uniform
+            load(ch + 2, x);
+            chunk(ch + 1, y);
+        }
     }
-    // acc0: individual ia (rows g, g+8 = its two strands), digits 2c, 2c+1;  acc1: individual ib
-    const uint32_t ia = group * 16 + g, ib = ia + 8;
+    if (group >= n_groups) return;
+    // rows g / g + 8 of the accumulator = individuals ia / ib; this lane: digits 2c, 2c + 1
     if (ia < n) {
-        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c], (unsigned long long) (long long) (acc0[0] + acc0[2]));
-        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[1] + acc0[3]));
+        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c], (unsigned long long) (long long) (acc0[0] + acc1[0]));
+        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[1] + acc1[1]));
     }
     if (ib < n) {
-        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c], (unsigned long long) (long long) (acc1[0] + acc1[2]));
-        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c + 1], (unsigned long long) (long long) (acc1[1] + acc1[3]));
+        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c], (unsigned long long) (long long) (acc0[2] + acc1[2]));
+        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[3] + acc1[3]));
     }
 }
 
@@ -430,32 +451,32 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
         }
         GSB_TRY(to_device_vec(delta, &e.d_delta));
         e.base_all = base;
-        // 62-bit fixed point, 8 balanced base-256 digits, in mma B-fragment order: lane = 4*digit + c
-        // holds, for marker word w, register `half` (0/1) whose byte j is the digit of marker
-        // 32*w + 8*j + c + 4*half — the k <-> marker permutation the kernel's A expansion uses.
+        // 62-bit fixed point, 8 balanced base-256 digits, in the mma B-fragment order of
+        // gebv_counts_kernel: lane = 4 * digit + c holds, for mma (i, p) of a chunk, register `half`
+        // whose byte j is the digit of marker bit 8j + 2p + half of word 4c + i.
         double maxabs = 0.0;
         for (uint32_t m = 0; m < M; ++m) maxabs = std::max(maxabs, std::fabs(delta[m]));
         int exp2 = 0;
         if (maxabs > 0.0 && std::isfinite(maxabs)) exp2 = 61 - std::ilogb(maxabs);
-        // the kernel leaves the strand bit of marker (8j + sft) of a word at weight 2^sft, so the
-        // digits are those of round(delta * 2^(exp2 - sft)): 55..62 significant bits
+        // the kernel leaves the count of marker bit (8j + sft) of a word at weight 2^(sft & 6), so
+        // the digits are those of round(delta * 2^(exp2 - (sft & 6))): 55..62 significant bits
         e.digit_scale = std::ldexp(1.0, -exp2);
         const uint32_t words = ctx->plane_words;
         std::vector<uint32_t> frag((size_t) words * 64, 0u);
         for (uint32_t m = 0; m < M; ++m) {
-            const uint32_t w = m >> 5, bit = m & 31, j = bit >> 3, sft = bit & 7, cc = sft & 3, half = sft >> 2;
-            long long q = std::isfinite(delta[m]) ? std::llrint(std::ldexp(delta[m], exp2 - (int) sft)) : 0;
+            const uint32_t w = m >> 5, bit = m & 31, j = bit >> 3, sft = bit & 7, p = sft >> 1, half = sft & 1;
+            const uint32_t chunk = w / kChunkWords, wi = w % kChunkWords, cc = wi >> 2, i = wi & 3;
+            long long q = std::isfinite(delta[m]) ? std::llrint(std::ldexp(delta[m], exp2 - (int) (sft & 6))) : 0;
             for (uint32_t dg = 0; dg < 8; ++dg) {
                 const long long d8 = ((q + 128) & 255) - 128;
                 q = (q - d8) >> 8;
                 const uint32_t lane = 4 * dg + cc;
-                frag[((size_t) w * 32 + lane) * 2 + half] |= ((uint32_t) (uint8_t) (int8_t) d8) << (8 * j);
+                frag[((((size_t) chunk * 8 + i * 2 + (p >> 1)) * 32 + lane) * 2 + (p & 1)) * 2 + half] |= ((uint32_t) (uint8_t) (int8_t) d8) << (8 * j);
             }
         }
         GSB_TRY(to_device_vec(frag, &e.d_digit_frag));
-        std::vector<uint32_t> ufrag;
-        build_umma_fragments(delta, M, words, exp2, ufrag);
-        GSB_TRY(to_device_vec(ufrag, &e.d_digit_umma));
+        build_tc5_fragments(delta, M, words, exp2, frag);
+        GSB_TRY(to_device_vec(frag, &e.d_digit_tc5));
     }
     e.built_for_dict_version = ctx->dict_version;
     e.built_for_planes = planes;
@@ -474,26 +495,24 @@ int gebv_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t ef
         GSB_TRY(ctx->s_eval[2].ensure((size_t) n * 8 * sizeof(long long)));
         unsigned long long* d_digits = (unsigned long long*) ctx->s_eval[2].ptr;
         GSB_CUDA_TRY(cudaMemsetAsync(d_digits, 0, (size_t) n * 8 * sizeof(long long), ctx->stream));
-        static const bool use_umma = [] { const char* v = getenv("GSB200_GEBV_PATH"); return v && strcmp(v, "umma") == 0; }();
-        if (use_umma) {
-            GSB_TRY(gebv_umma_launch(ctx, n, d_rows, e->d_digit_umma, d_digits));
-            gebv_finish_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const long long*) d_digits, n, e->digit_scale,
-                                                                        e->base_all - centre_sum, d_out);
+        // the tcgen05 experiment (gebv_tc5.cu): same digits, same answer, slower
+        static const bool use_tc5 = [] { const char* v = getenv("GSB200_GEBV_PATH"); return v && strcmp(v, "tc5") == 0; }();
+        if (use_tc5) {
+            GSB_TRY(gebv_tc5_launch(ctx, n, d_rows, e->d_digit_tc5, d_digits));
+        } else {
+            const uint32_t chunks = ctx->plane_words / kChunkWords, n_groups = (n + 15) / 16;
+            const uint32_t group_blocks = (n_groups + kGebvWarps - 1) / kGebvWarps;
+            // enough marker segments to fill the machine a few times over
+            uint32_t n_segments = (uint32_t) std::min<uint64_t>(chunks, ((uint64_t) ctx->sm_count * 64 + group_blocks - 1) / group_blocks);
+            n_segments = std::max<uint32_t>(n_segments, (chunks + kGebvMaxSegChunks - 1) / kGebvMaxSegChunks);
+            const uint32_t seg_chunks = (chunks + n_segments - 1) / n_segments;
+            n_segments = (chunks + seg_chunks - 1) / seg_chunks;
+            GSB_REQUIRE((uint64_t) group_blocks * n_segments < (1ull << 31), GSB200_ERR_ARG, "%s: too many individuals x markers for one launch", what);
+            gebv_counts_kernel<<<group_blocks * n_segments, kGebvWarps * 32, 0, ctx->stream>>>(
+                ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, (const uint4*) e->d_digit_frag, group_blocks, n_segments, seg_chunks, d_digits);
             ++ctx->launches;
             GSB_CUDA_TRY(cudaGetLastError());
-            return GSB200_OK;
         }
-        const uint32_t chunks = ctx->plane_words / kChunkWords, n_groups = (n + 15) / 16;
-        // enough marker segments to fill the machine a few times over
-        uint32_t n_segments = (uint32_t) std::min<uint64_t>(chunks, ((uint64_t) ctx->sm_count * 64 * 4 + n_groups - 1) / n_groups);
-        n_segments = std::max<uint32_t>(n_segments, (chunks + kGebvMaxSegChunks - 1) / kGebvMaxSegChunks);
-        const uint32_t seg_chunks = (chunks + n_segments - 1) / n_segments;
-        n_segments = (chunks + seg_chunks - 1) / seg_chunks;
-        const uint64_t warps = (uint64_t) n_groups * n_segments;
-        gebv_digits_kernel<<<(unsigned) ((warps + kGebvWarps - 1) / kGebvWarps), kGebvWarps * 32, 0, ctx->stream>>>(
-            ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, (const uint2*) e->d_digit_frag, n_segments, seg_chunks, d_digits);
-        ++ctx->launches;
-        GSB_CUDA_TRY(cudaGetLastError());
         gebv_finish_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const long long*) d_digits, n, e->digit_scale,
                                                                     e->base_all - centre_sum, d_out);
     } else {

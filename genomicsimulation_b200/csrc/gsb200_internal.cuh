@@ -106,7 +106,7 @@ struct DeviceEffects {
     double* d_delta = nullptr;        // planes == 1: value_all[m][1] - value_all[m][0]
     double  base_all = 0.0;           // planes == 1: sum_m 2 * value_all[m][0]
     uint32_t* d_digit_frag = nullptr; // planes == 1: fixed-point digits of delta as mma B fragments
-    uint32_t* d_digit_umma = nullptr; // ... in the shared-memory layout of the tcgen05 path
+    uint32_t* d_digit_tc5 = nullptr;  // ... in the shared-memory layout of gebv_tc5_kernel
     double  digit_scale = 1.0;        // value of one fixed-point unit
     std::vector<double> h_value_first; // host copy of d_value_first (source of the local-GEBV digit fragments)
     uint64_t  local_key = 0;           // block definition d_local was built for
@@ -165,9 +165,9 @@ namespace gsb {
 int sync_dictionary(gsb200_ctx* ctx);                       // store.cu
 int ensure_symbol(gsb200_ctx* ctx, uint32_t marker, uint8_t symbol, uint32_t* code);   // store.cu
 int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff);    // evaluate.cu
-void build_umma_fragments(const std::vector<double>& delta, uint32_t n_markers, uint32_t plane_words, int exp2,
-                          std::vector<uint32_t>& frag);     // gebv_umma.cu
-int gebv_umma_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, const uint32_t* d_frag, unsigned long long* d_digits);
+void build_tc5_fragments(const std::vector<double>& delta, uint32_t n_markers, uint32_t plane_words, int exp2,
+                         std::vector<uint32_t>& frag);     // gebv_tc5.cu
+int gebv_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, const uint32_t* d_frag, unsigned long long* d_digits);
 int upload_u32(gsb200_ctx* ctx, Scratch& s, const uint32_t* host, size_t n, uint32_t** out);
 int check_rows(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const char* what);
 }  // namespace gsb

@@ -395,17 +395,17 @@ def test_scheme_replay_matches_the_unmodified_reference(shape, tmp_path):
 
 
 def test_gebv_tcgen05_path():
-    """The experimental tcgen05/TMEM GEBV kernel (GSB200_GEBV_PATH=umma, csrc/gebv_umma.cu) gives the
+    """The experimental tcgen05/TMEM GEBV kernel (GSB200_GEBV_PATH=tc5, csrc/gebv_tc5.cu) gives the
     same GEBVs as the oracle; the path is chosen once per process, hence the subprocess."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, GSB200_GEBV_PATH="umma")
-    out = subprocess.run([sys.executable, os.path.join(root, "profiles", "scripts", "umma_check.py")], cwd=root, env=env,
+    env = dict(os.environ, GSB200_GEBV_PATH="tc5")
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "gebv_path_check.py")], cwd=root, env=env,
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("n=")]
-    assert len(lines) == 2 and all("path=umma" in l and l.rstrip().endswith("OK") for l in lines), out.stdout
+    assert len(lines) == 2 and all("path=tc5" in l and l.rstrip().endswith("OK") for l in lines), out.stdout
 
 
 def test_config5_marker_count():
