@@ -318,7 +318,7 @@ def engine_arm(a):
             "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src, "ms_per_launch": cross_ms,
             "algorithmic_bytes_per_launch": alg_cross}
     roof["frac"] = roof["achieved"] / peak
-    roof_g = {"bound": "hbm", "kernel": "gebv_digits_kernel (+ memset + gebv_finish_kernel)", "achieved": alg_gebv / (gebv_ms * 1e-3) / 1e9, "peak": peak,
+    roof_g = {"bound": "hbm", "kernel": "gebv_counts_kernel (+ memset + gebv_finish_kernel)", "achieved": alg_gebv / (gebv_ms * 1e-3) / 1e9, "peak": peak,
               "unit": "GB/s", "traffic": None, "ms_per_launch": gebv_ms, "algorithmic_bytes_per_launch": alg_gebv}
     roof_g["frac"] = roof_g["achieved"] / peak
     # per-launch DRAM traffic from the committed ncu capture, when there is one
@@ -326,7 +326,7 @@ def engine_arm(a):
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f)
         roof["traffic"] = tr.get("splice_flat_kernel")
-        roof_g["traffic"] = tr.get("gebv_digits_kernel")
+        roof_g["traffic"] = tr.get("gebv_counts_kernel")
     except Exception:
         pass
 

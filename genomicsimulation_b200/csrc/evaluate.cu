@@ -35,11 +35,8 @@ namespace {
 // sums per individual are recombined in fp64 at the end.  Integer accumulation is exact and
 // order-free, so marker segments can be summed with integer atomics and the result is still
 // deterministic.
-constexpr int kGebvWarps = 4;                  // warps per block, 16 individuals each
-constexpr int kGebvMinBlocks = 7;              // per SM: 72 registers
 constexpr uint32_t kGebvMaxMarkers = 1u << 26;
 constexpr uint32_t kChunkWords = 16;           // 512 markers = 16 mma = 64 bytes per strand row
-constexpr uint32_t kGebvMaxSegChunks = 64;     // 32768 markers * 128 * 128 < 2^31
 
 __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -55,66 +52,82 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 
-// One block = 4 warps x 16 individuals x one segment of marker chunks.
+// Persistent blocks, three per SM.  A block keeps the B fragments of ONE marker segment (<= 16
+// chunks = 64 KB) in shared memory, loaded once, and its 8 warps pull groups of 16 individuals from
+// the segment's counter: no per-chunk staging, no barrier after the first, no tail.
 //   * lane (g, c) loads words 4c..4c+3 of a 16-word chunk of the two strands of individuals g and
 //     g + 8 straight into registers (LDG.128; the four lanes of a row cover 64 contiguous bytes),
-//     one chunk ahead, two chunks per loop trip so that no register is ever copied;
+//     one chunk ahead — across group boundaries too — two chunks per loop trip so that no
+//     register is ever copied;
 //   * the two strands are ADDED before the tensor core sees them, so an A row is an individual,
-//     not a strand, and one mma covers 16 individuals: with x = w0 ^ w1 (one copy) and
-//     a = w0 & w1 (two copies), ye = (x & 0x55..) | ((a << 1) & 0xAA..) holds the allele count of
-//     every even-numbered marker of the word as a 2-bit field, yo = ((x >> 1) & 0x55..) | (a & 0xAA..)
-//     that of every odd-numbered one: 6 logic ops per word pair, then ONE op per A register,
+//     not a strand, and one mma covers 16 individuals: with x = w0 ^ w1 and a = w0 & w1,
+//     ye = (x & 0x55..) | ((a << 1) & 0xAA..) holds the allele count of every even-numbered marker
+//     of the word as a 2-bit field, yo = ((x >> 1) & 0x55..) | (a & 0xAA..) that of every
+//     odd-numbered one: 6 logic ops per word pair, then ONE op per A register,
 //     `ye & (0x03030303 << 2p)`: byte j = count(marker 8j + 2p) at weight 4^p.  The weight is
 //     divided out of the digits on the host (ensure_effect_tables);
 //   * every lane uses the same masks, so they are immediates; mma (i, p) of a chunk contracts
-//     k = 4c + j with marker bit 8j + 2p of word 4c + i and k = 16 + 4c + j with bit 8j + 2p + 1;
-//   * the B fragments of a chunk (4 KB) are shared by the block's warps through shared memory
-//     (cp.async, double-buffered, one barrier per chunk): read through L1 they missed often
-//     enough to stall the mma on its operand.
+//     k = 4c + j with marker bit 8j + 2p of word 4c + i and k = 16 + 4c + j with bit 8j + 2p + 1.
 // bfrag[(chunk * 8 + i * 2 + p / 2) * 32 + lane] (uint4) = the B registers of `lane` for mma
 // (i, p) and (i, p + 1), p even.
 // What bounds it: the logic ops (alu pipe, one per 2 cycles and scheduler) and IMMA.16832 (~10
-// cycles) do not overlap on sm_100a — their pipe-active percentages add up to ~95 %
-// (profiles/r1_pipe_overlap.txt).
-__global__ void __launch_bounds__(kGebvWarps * 32, kGebvMinBlocks) gebv_counts_kernel(
+// cycles) do not overlap on sm_100a — their pipe-active percentages add up to ~95 %; without
+// the row loads the kernel still takes 0.22 ms per 100 k x 50 k.
+constexpr int kGebvWarps = 8;
+constexpr int kGebvBlocksPerSm = 3;
+constexpr uint32_t kGebvSegChunks = 16;        // B of a segment: 64 KB of shared memory; 8192 markers * 128 * 128 < 2^31
+__global__ void __launch_bounds__(kGebvWarps * 32, kGebvBlocksPerSm) gebv_counts_kernel(
         const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
         const uint32_t* __restrict__ rows, uint32_t n, const uint4* __restrict__ bfrag,
-        uint32_t group_blocks, uint32_t n_segments, uint32_t seg_chunks, unsigned long long* __restrict__ digit_sums) {
-    __shared__ __align__(16) uint4 s_b[2][256];
+        uint32_t n_groups, uint32_t n_segments, uint32_t seg_chunks, unsigned long long* __restrict__ digit_sums,
+        unsigned int* __restrict__ next_group /* [n_segments], zeroed */) {
+    extern __shared__ __align__(16) uint4 s_seg[];          // seg_chunks (rounded up to even) x 256
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t n_groups = (n + 15) / 16;
-    // neighbouring blocks read the same rows (all their segments), last rows of the list first: what a
-    // preceding kernel wrote last is still in L2
-    const uint32_t seg = blockIdx.x % n_segments, group = (group_blocks - 1 - blockIdx.x / n_segments) * kGebvWarps + warp;
+    const uint32_t seg = blockIdx.x % n_segments;
     const uint32_t g = lane >> 2, c = lane & 3;
     const uint32_t ch_lo = seg * seg_chunks, ch_hi = min(ch_lo + seg_chunks, plane_words / kChunkWords);
     if (ch_lo >= ch_hi) return;                              // whole block
+    const uint32_t segc = ch_hi - ch_lo, segc2 = (segc + 1) & ~1u;      // an odd segment gets a chunk of zero digits
+    for (uint32_t i = threadIdx.x; i < segc2 * 256; i += kGebvWarps * 32) {
+        if (i < segc * 256) cp_async16(reinterpret_cast<uint32_t*>(&s_seg[i]), reinterpret_cast<const uint32_t*>(bfrag + (size_t) ch_lo * 256 + i));
+        else s_seg[i] = make_uint4(0, 0, 0, 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
 
-    auto stage_b = [&](uint32_t ch) {
-        for (uint32_t i = threadIdx.x; i < 256; i += kGebvWarps * 32)
-            cp_async16(reinterpret_cast<uint32_t*>(&s_b[(ch - ch_lo) & 1][i]), reinterpret_cast<const uint32_t*>(bfrag + (size_t) ch * 256 + i));
-        cp_async_commit();
+    // groups are handed out last-first: what a preceding kernel wrote last is still in L2
+    auto take = [&]() {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(&next_group[seg], 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        return k < n_groups ? n_groups - 1 - k : 0xffffffffu;
     };
-    stage_b(ch_lo);
-
-    // a warp past the last group walks the last group's rows (it must keep the barriers) and adds nothing
-    const uint32_t ia = min(group, n_groups - 1) * 16 + g, ib = ia + 8;
-    const uint4* pa0 = reinterpret_cast<const uint4*>(store + (uint64_t) rows[min(ia, n - 1)] * row_words) + c;
-    const uint4* pb0 = reinterpret_cast<const uint4*>(store + (uint64_t) rows[min(ib, n - 1)] * row_words) + c;
     const uint32_t strand1 = plane_words / 4;          // uint4 units
-
-    int acc0[4] = { 0, 0, 0, 0 }, acc1[4] = { 0, 0, 0, 0 };      // two chains, for mma latency
-    struct Rows { uint4 a0, a1, b0, b1; };
-    auto load = [&](uint32_t ch, Rows& r) {
-        const uint32_t o = min(ch, ch_hi - 1) * 4;
-        r.a0 = ldg_stream(pa0 + o); r.a1 = ldg_stream(pa0 + strand1 + o);
-        r.b0 = ldg_stream(pb0 + o); r.b1 = ldg_stream(pb0 + strand1 + o);
+    struct Ptrs { const uint4* a; const uint4* b; };
+    auto ptrs = [&](uint32_t group) {
+        const uint32_t gr = min(group, n_groups - 1);
+        Ptrs p;
+        p.a = reinterpret_cast<const uint4*>(store + (uint64_t) rows[min(gr * 16 + g, n - 1)] * row_words) + ch_lo * 4 + c;
+        p.b = reinterpret_cast<const uint4*>(store + (uint64_t) rows[min(gr * 16 + g + 8, n - 1)] * row_words) + ch_lo * 4 + c;
+        return p;
     };
+    uint32_t cur = take();
+    if (cur == 0xffffffffu) return;
+    uint32_t nxt = take();
+    Ptrs lp = ptrs(cur), np = ptrs(nxt);
+    struct Rows { uint4 a0, a1, b0, b1; };
+    auto load = [&](const Ptrs& p, uint32_t ch, Rows& r) {
+        const uint32_t o = min(ch, segc - 1) * 4;
+        r.a0 = ldg_stream(p.a + o); r.a1 = ldg_stream(p.a + strand1 + o);
+        r.b0 = ldg_stream(p.b + o); r.b1 = ldg_stream(p.b + strand1 + o);
+    };
+    int acc0[4] = { 0, 0, 0, 0 }, acc1[4] = { 0, 0, 0, 0 };
     auto word = [&](uint32_t a_s0, uint32_t a_s1, uint32_t b_s0, uint32_t b_s1, const uint4* fw) {
         const uint32_t xa = a_s0 ^ a_s1, ca = a_s0 & a_s1, xb = b_s0 ^ b_s1, cb = b_s0 & b_s1;
         const uint32_t ae = (xa & 0x55555555u) | ((ca << 1) & 0xaaaaaaaau), ao = ((xa >> 1) & 0x55555555u) | (ca & 0xaaaaaaaau);
@@ -127,36 +140,40 @@ __global__ void __launch_bounds__(kGebvWarps * 32, kGebvMinBlocks) gebv_counts_k
             mma_u8s8(acc1, ae & m1, be & m1, ao & m1, bo & m1, fr.z, fr.w);
         }
     };
-    // B of chunk `ch` has landed and everyone is done with the other buffer: refill that one, use this one
-    auto chunk = [&](uint32_t ch, const Rows& r) {
-        cp_async_wait<0>();
-        __syncthreads();
-        if (ch + 1 < ch_hi) stage_b(ch + 1);
-        const uint4* f = s_b[(ch - ch_lo) & 1] + lane;
+    auto use = [&](uint32_t ch, const Rows& r) {
+        const uint4* f = s_seg + ch * 256 + lane;
         word(r.a0.x, r.a1.x, r.b0.x, r.b1.x, f);
         word(r.a0.y, r.a1.y, r.b0.y, r.b1.y, f + 2 * 32);
         word(r.a0.z, r.a1.z, r.b0.z, r.b1.z, f + 4 * 32);
         word(r.a0.w, r.a1.w, r.b0.w, r.b1.w, f + 6 * 32);
     };
     Rows x, y;
-    load(ch_lo, x);
-    for (uint32_t ch = ch_lo; ch < ch_hi; ch += 2) {             // two chunks per trip: no register shuffling
-        load(ch + 1, y);
-        chunk(ch, x);
-        if (ch + 1 < ch_hi) {                                    // block-uniform
-            load(ch + 2, x);
-            chunk(ch + 1, y);
+    load(lp, 0, x);
+    for (;;) {
+        for (uint32_t ch = 0; ch < segc2; ch += 2) {             // two chunks per trip: no register shuffling
+            load(lp, ch + 1, y);
+            use(ch, x);
+            if (ch + 2 < segc2) load(lp, ch + 2, x);
+            else if (nxt != 0xffffffffu) load(np, 0, x);         // the next group's first chunk
+            use(ch + 1, y);
         }
-    }
-    if (group >= n_groups) return;
-    // rows g / g + 8 of the accumulator = individuals ia / ib; this lane: digits 2c, 2c + 1
-    if (ia < n) {
-        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c], (unsigned long long) (long long) (acc0[0] + acc1[0]));
-        atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[1] + acc1[1]));
-    }
-    if (ib < n) {
-        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c], (unsigned long long) (long long) (acc0[2] + acc1[2]));
-        atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[3] + acc1[3]));
+        // rows g / g + 8 of the accumulators = individuals ia / ib of `cur`; this lane: digits 2c, 2c + 1
+        const uint32_t ia = cur * 16 + g, ib = ia + 8;
+        if (ia < n) {
+            atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c], (unsigned long long) (long long) (acc0[0] + acc1[0]));
+            atomicAdd(&digit_sums[(size_t) ia * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[1] + acc1[1]));
+        }
+        if (ib < n) {
+            atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c], (unsigned long long) (long long) (acc0[2] + acc1[2]));
+            atomicAdd(&digit_sums[(size_t) ib * 8 + 2 * c + 1], (unsigned long long) (long long) (acc0[3] + acc1[3]));
+        }
+        if (nxt == 0xffffffffu) break;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc0[k] = acc1[k] = 0;
+        cur = nxt;
+        lp = np;
+        nxt = take();
+        np = ptrs(nxt);
     }
 }
 
@@ -492,24 +509,25 @@ int gebv_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t ef
     GSB_TRY(get_effects(ctx, eff_index, &e, what));
     const double centre_sum = e->has_centre ? e->centre_sum : 0.0;
     if (ctx->planes == 1 && ctx->n_markers <= kGebvMaxMarkers) {
-        GSB_TRY(ctx->s_eval[2].ensure((size_t) n * 8 * sizeof(long long)));
+        const size_t counters = (size_t) (ctx->plane_words / kChunkWords + 1) * sizeof(unsigned int);
+        GSB_TRY(ctx->s_eval[2].ensure((size_t) n * 8 * sizeof(long long) + counters));
         unsigned long long* d_digits = (unsigned long long*) ctx->s_eval[2].ptr;
-        GSB_CUDA_TRY(cudaMemsetAsync(d_digits, 0, (size_t) n * 8 * sizeof(long long), ctx->stream));
+        GSB_CUDA_TRY(cudaMemsetAsync(d_digits, 0, (size_t) n * 8 * sizeof(long long) + counters, ctx->stream));
         // the tcgen05 experiment (gebv_tc5.cu): same digits, same answer, slower
         static const bool use_tc5 = [] { const char* v = getenv("GSB200_GEBV_PATH"); return v && strcmp(v, "tc5") == 0; }();
         if (use_tc5) {
             GSB_TRY(gebv_tc5_launch(ctx, n, d_rows, e->d_digit_tc5, d_digits));
         } else {
             const uint32_t chunks = ctx->plane_words / kChunkWords, n_groups = (n + 15) / 16;
-            const uint32_t group_blocks = (n_groups + kGebvWarps - 1) / kGebvWarps;
-            // enough marker segments to fill the machine a few times over
-            uint32_t n_segments = (uint32_t) std::min<uint64_t>(chunks, ((uint64_t) ctx->sm_count * 64 + group_blocks - 1) / group_blocks);
-            n_segments = std::max<uint32_t>(n_segments, (chunks + kGebvMaxSegChunks - 1) / kGebvMaxSegChunks);
-            const uint32_t seg_chunks = (chunks + n_segments - 1) / n_segments;
-            n_segments = (chunks + seg_chunks - 1) / seg_chunks;
-            GSB_REQUIRE((uint64_t) group_blocks * n_segments < (1ull << 31), GSB200_ERR_ARG, "%s: too many individuals x markers for one launch", what);
-            gebv_counts_kernel<<<group_blocks * n_segments, kGebvWarps * 32, 0, ctx->stream>>>(
-                ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, (const uint4*) e->d_digit_frag, group_blocks, n_segments, seg_chunks, d_digits);
+            const uint32_t want = (chunks + kGebvSegChunks - 1) / kGebvSegChunks, seg_chunks = (chunks + want - 1) / want;
+            const uint32_t n_segments = (chunks + seg_chunks - 1) / seg_chunks;
+            const uint64_t useful = (uint64_t) ((n_groups + kGebvWarps - 1) / kGebvWarps) * n_segments;
+            const uint32_t grid = (uint32_t) std::min<uint64_t>(std::max<uint64_t>((uint64_t) ctx->sm_count * kGebvBlocksPerSm, n_segments), useful);
+            GSB_CUDA_TRY(cudaFuncSetAttribute(gebv_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kGebvSegChunks * 4096));   // per device
+            unsigned int* d_next = reinterpret_cast<unsigned int*>(d_digits + (size_t) n * 8);     // one counter per segment, zeroed above
+            gebv_counts_kernel<<<grid, kGebvWarps * 32, ((seg_chunks + 1) & ~1u) * 4096, ctx->stream>>>(
+                ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, (const uint4*) e->d_digit_frag, n_groups, n_segments, seg_chunks,
+                d_digits, d_next);
             ++ctx->launches;
             GSB_CUDA_TRY(cudaGetLastError());
         }
