@@ -215,7 +215,7 @@ def engine_arm(a):
             raise RuntimeError(E.gsb200_last_error().decode())
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    kernel_ms = {"cross": [], "gebv": []}
+    kernel_ms = {"cross": [], "gebv": [], "broadcast": [], "allgather": []}
 
     torch.cuda.synchronize()
 
@@ -223,13 +223,14 @@ def engine_arm(a):
         # everything is enqueued on the engine's stream (torch's current stream inside this call):
         # NCCL orders itself against it with events, so the step has no host synchronisation
         with torch.cuda.stream(ext):
+            eb, e0, e1, e2, eg = ev(), ev(), ev(), ev(), ev()
+            eb.record(ext)
             if world > 1:
                 # generation boundary: rank 0's parent pool to everyone over NVLink, straight from
                 # and into the packed stores (scattered pools go through gsb200_store_gather/scatter_rows_dev,
                 # genomicsimulation_b200/sharding.py)
                 dist.broadcast(pool, 0)
             dr = Draws(mode=0, seed=20261019, stream=i, first_unit=rank * n)
-            e0, e1, e2 = ev(), ev(), ev()
             e0.record(ext)
             check(E.gsb200_cross_dev(ctx, n, d_p1.data_ptr(), d_p2.data_ptr(), 0, 0, d_out.data_ptr(), C.byref(dr)))
             e1.record(ext)
@@ -237,8 +238,9 @@ def engine_arm(a):
             e2.record(ext)
             if world > 1:
                 dist.all_gather_into_tensor(all_bv, d_bv)      # GEBVs for replicated selection
+            eg.record(ext)
         if timed:
-            kernel_ms["_ev"].append((e0, e1, e2))
+            kernel_ms["_ev"].append((eb, e0, e1, e2, eg))
 
     for i in range(a.warmup):
         step(i, False)
@@ -263,9 +265,11 @@ def engine_arm(a):
     check(E.gsb200_cross_dev_status(ctx))
     launches = E.gsb200_kernel_launches(ctx) - launches0
     ms_total = t0.elapsed_time(t1)
-    for e0, e1, e2 in kernel_ms["_ev"]:
+    for eb, e0, e1, e2, eg in kernel_ms["_ev"]:
+        kernel_ms["broadcast"].append(eb.elapsed_time(e0))
         kernel_ms["cross"].append(e0.elapsed_time(e1))
         kernel_ms["gebv"].append(e1.elapsed_time(e2))
+        kernel_ms["allgather"].append(e2.elapsed_time(eg))
     tt = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -339,6 +343,9 @@ def engine_arm(a):
            "gebv_marker_ind_per_s": n * M / (gebv_ms * 1e-3),
            "roofline": roof, "roofline_gebv": roof_g, "e2e": e2e, "gpu_launches": int(launches),
            "clocks": clocks.summary()}
+    if world > 1:
+        out["collectives"] = {"pool_broadcast_ms": float(np.mean(kernel_ms["broadcast"])), "gebv_allgather_ms": float(np.mean(kernel_ms["allgather"])),
+                              "note": "rank 0, CUDA events on the engine's stream; includes waiting for the slowest rank"}
     if world == 1 and not a.no_cpu_baseline:
         shape = (M, a.chr, 50)
         kind, n_done, sec = cpu_run(shape, a.cpu_sample, 1, 0, 1)
