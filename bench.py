@@ -277,6 +277,47 @@ def engine_arm(a):
     ms_step = ms_total / a.steps
     value = world * n / (ms_step * 1e-3)
 
+    # ---- the same step through the fused entry point: GEBVs assembled from the crossover plan and the
+    #      parents' prefix tables while the offspring are spliced, instead of reading them back
+    d_pool = torch.arange(0, F, dtype=torch.int32, device="cuda")
+    d_bv2 = torch.empty(n, dtype=torch.float64, device="cuda")
+
+    def fused_step(i):
+        with torch.cuda.stream(ext):
+            if world > 1:
+                dist.broadcast(pool, 0)
+            dr = Draws(mode=0, seed=20261019, stream=i, first_unit=rank * n)
+            check(E.gsb200_cross_gebv_dev(ctx, n, d_p1.data_ptr(), d_p2.data_ptr(), 0, 0, d_out.data_ptr(), C.byref(dr),
+                                          F, d_pool.data_ptr(), 0, d_bv2.data_ptr()))
+            if world > 1:
+                dist.all_gather_into_tensor(all_bv, d_bv2)
+
+    last = a.warmup + a.steps - 1
+    fused_step(last)                                     # same draws as the last timed step: same offspring, same GEBVs
+    torch.cuda.synchronize()
+    check(E.gsb200_cross_dev_status(ctx))
+    fused_err = float((d_bv2 - d_bv).abs().max().item() / (d_bv.abs().mean().item() + 1e-300))
+    for i in range(a.warmup):
+        fused_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    f0, f1 = ev(), ev()
+    f0.record(ext)
+    for i in range(a.steps):
+        fused_step(a.warmup + i)
+    f1.record(ext)
+    ext.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    check(E.gsb200_cross_dev_status(ctx))
+    tf = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+    fused_ms = float(tf.item()) / a.steps
+
     # ---- end to end through the reference-facing API (host buffers, copies inside the timed region)
     g_f = sim.founders
     e2e_t = []
@@ -343,6 +384,10 @@ def engine_arm(a):
            "gebv_marker_ind_per_s": n * M / (gebv_ms * 1e-3),
            "roofline": roof, "roofline_gebv": roof_g, "e2e": e2e, "gpu_launches": int(launches),
            "clocks": clocks.summary()}
+    out["fused_cross_gebv"] = {"ms_per_step": fused_ms, "value": world * n / (fused_ms * 1e-3), "unit": UNIT,
+                               "max_rel_diff_vs_two_pass": fused_err,
+                               "api": "gsb200_cross_gebv_dev: same offspring, GEBVs from the crossover plan + per-parent prefix "
+                                      "tables (1000-row pool rebuilt every step); NOT the headline value, which keeps the two kernels"}
     if world > 1:
         out["collectives"] = {"pool_broadcast_ms": float(np.mean(kernel_ms["broadcast"])), "gebv_allgather_ms": float(np.mean(kernel_ms["allgather"])),
                               "note": "rank 0, CUDA events on the engine's stream; includes waiting for the slowest rank"}

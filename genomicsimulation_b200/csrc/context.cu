@@ -46,7 +46,7 @@ void DeviceMap::release() {
 }
 
 void DeviceEffects::release() {
-    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag, d_digit_tc5, d_local };
+    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag, d_digit_tc5, d_local, d_bvq };
     for (void* p : ptrs) if (p) cudaFree(p);
     *this = DeviceEffects();
 }
@@ -138,6 +138,7 @@ void gsb200_destroy(gsb200_ctx* ctx) {
     for (auto& s : ctx->s_plan) s.release();
     for (auto& s : ctx->s_eval) s.release();
     for (auto& s : ctx->s_chain) s.release();
+    for (auto& s : ctx->s_bv) s.release();
     ctx->s_null.release();
     ctx->local_sched.d_steps.release();
     if (ctx->d_flag) cudaFree(ctx->d_flag);

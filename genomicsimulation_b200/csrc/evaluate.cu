@@ -494,6 +494,18 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
         GSB_TRY(to_device_vec(frag, &e.d_digit_frag));
         build_tc5_fragments(delta, M, words, exp2, frag);
         GSB_TRY(to_device_vec(frag, &e.d_digit_tc5));
+        // one int64 per marker for the fused cross + GEBV (meiosis.cu): sums over both strands of
+        // every marker stay below 2^62
+        int eq = 0;
+        if (maxabs > 0.0 && std::isfinite(maxabs)) {
+            int bits = 1;
+            while ((1ull << bits) < 2ull * M) ++bits;
+            eq = 60 - std::ilogb(maxabs) - bits;
+        }
+        e.bvq_scale = std::ldexp(1.0, -eq);
+        std::vector<long long> bvq((size_t) words * 32, 0);
+        for (uint32_t m = 0; m < M; ++m) bvq[m] = std::isfinite(delta[m]) ? std::llrint(std::ldexp(delta[m], eq)) : 0;
+        GSB_TRY(to_device_vec(bvq, &e.d_bvq));
     }
     e.built_for_dict_version = ctx->dict_version;
     e.built_for_planes = planes;

@@ -108,6 +108,8 @@ struct DeviceEffects {
     uint32_t* d_digit_frag = nullptr; // planes == 1: fixed-point digits of delta as mma B fragments
     uint32_t* d_digit_tc5 = nullptr;  // ... in the shared-memory layout of gebv_tc5_kernel
     double  digit_scale = 1.0;        // value of one fixed-point unit
+    long long* d_bvq = nullptr;       // planes == 1: delta as one int64 per marker (fused cross + GEBV), padded to whole words
+    double  bvq_scale = 1.0;          // value of one unit of d_bvq
     std::vector<double> h_value_first; // host copy of d_value_first (source of the local-GEBV digit fragments)
     uint64_t  local_key = 0;           // block definition d_local was built for
     uint32_t* d_local = nullptr;       // local GEBV: per-step digit fragments, then the per-block bases (fp64)
@@ -154,6 +156,7 @@ struct gsb200_ctx {
     gsb::Scratch s_plan[8];         // meiosis draw buffers
     gsb::Scratch s_eval[4];
     gsb::Scratch s_chain[2];        // ping-pong rows of chained selfing
+    gsb::Scratch s_bv[3];           // fused cross + GEBV: parent prefix tables, row -> table slot, per-offspring sums
     gsb::LocalSchedule local_sched;
     gsb::Scratch s_null;            // per marker: the code that decodes to '\0' (uncovered markers)
     uint64_t null_built_for = ~0ull;

@@ -85,6 +85,11 @@ struct MeiosisArgs {
     uint32_t xcap, tcap;       // crossovers / toggles one gamete's plan can hold
     uint32_t warp_smem_words;
     int* flag;
+    // fused GEBV (splice_flat_kernel<true>): see parent_tables_kernel
+    const long long* bv_tab;   // [slot][plane_words + 2]
+    const uint32_t* bv_slot;   // row -> slot
+    const long long* bv_q;     // [plane_words * 32]: fixed-point delta per marker
+    unsigned long long* bv_acc;// per unit: sum over its gametes, two's complement
 };
 
 // ------------------------------------------------------------------ native draw stream
@@ -216,6 +221,17 @@ __device__ __forceinline__ void emit_toggles(uint32_t t, uint32_t lane, const Me
 //   chr_start[n_chr/32 + 1]   bit c: start strand of chromosome c
 //   list[tcap]                the toggles (marker positions), unordered
 //   xinfo[xcap]               crossover -> (chromosome, index within chromosome)
+//
+// kBv: also the gamete's contribution to its offspring's GEBV, WITHOUT reading the gamete back.
+// With Q_m the fixed-point effect difference of marker m and F_s(x) = sum_{m < x} Q_m * h_s(m) for
+// the parent's strand s, a gamete that runs on strand s_k between toggles t_k and t_{k+1} is worth
+//   sum_k F_{s_k}(t_{k+1}) - F_{s_k}(t_k)  =  F_{s_last}(M) + sum_toggles +-(F_0 - F_1)(t),
+// + when the toggle leaves strand 0, - when it leaves strand 1.  (F_0 - F_1) at every word boundary
+// and F_0(M) come from the parent's prefix table (parent_tables_kernel); the < 32 markers between
+// the word boundary and the toggle are summed here from the parent's words.  The strand a toggle
+// leaves = the strand its 128-marker piece starts on, flipped once per earlier toggle in the
+// same piece (rare: found with two bitsets, ranked by scanning the list only then).
+template <bool kBv>
 __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -224,6 +240,8 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
     uint32_t* piece_parity = list + a.tcap;
     uint32_t* chr_flip = piece_parity + a.parity_words;
     uint32_t* chr_start = chr_flip + a.chr_words;
+    uint32_t* piece_seen = chr_start + a.chr_words;          // kBv only: pieces holding >= 1 / >= 2 toggles
+    uint32_t* piece_multi = piece_seen + a.parity_words;
 
     const uint32_t n_gametes = a.n_units * a.gametes_per_unit;      // host keeps this below 2^32
     for (uint32_t g = blockIdx.x * warps + warp; g < n_gametes; g += gridDim.x * warps) {
@@ -284,19 +302,34 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
             emit_toggles(t, lane, a, piece_parity, list, n_list);
         }
         __syncwarp();
-        // chromosome boundaries: enter on the start strand, leave back on strand 0
-        for (uint32_t c0 = 0; c0 < mv.n_chr; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            uint32_t t_in = kNoToggle, t_out = kNoToggle;
-            if (c < mv.n_chr) {
-                const uint32_t s_c = (chr_start[c0 >> 5] >> lane) & 1u;
-                const uint32_t e_c = s_c ^ ((chr_flip[c0 >> 5] >> lane) & 1u);
-                const ChrInfo ci = mv.chr[c];
-                if (s_c) t_in = ci.first;
-                if (e_c) t_out = ci.first + ci.len;
+        // chromosome boundaries: enter on the start strand, leave back on strand 0.  Where one chromosome
+        // ends on strand 1 exactly where the next starts on strand 1 the two toggles cancel and are not made.
+        {
+            uint32_t carry_e = 0, carry_pos = 0;              // the previous group's last chromosome
+            for (uint32_t c0 = 0; c0 < mv.n_chr; c0 += 32) {
+                const uint32_t c = c0 + lane;
+                uint32_t s_c = 0, e_c = 0, first = 0, end = 0;
+                if (c < mv.n_chr) {
+                    s_c = (chr_start[c0 >> 5] >> lane) & 1u;
+                    e_c = s_c ^ ((chr_flip[c0 >> 5] >> lane) & 1u);
+                    const ChrInfo ci = mv.chr[c];
+                    first = ci.first;
+                    end = ci.first + ci.len;
+                }
+                uint32_t e_prev = __shfl_up_sync(0xffffffffu, e_c, 1), end_prev = __shfl_up_sync(0xffffffffu, end, 1);
+                if (lane == 0) { e_prev = carry_e; end_prev = carry_pos; }
+                uint32_t t_in = kNoToggle, t_out = kNoToggle;    // t_out: the PREVIOUS chromosome's way out
+                if (c < mv.n_chr) {
+                    if (end_prev == first) { if (s_c ^ e_prev) t_in = first; }
+                    else { if (s_c) t_in = first; if (e_prev) t_out = end_prev; }
+                }
+                emit_toggles(t_in, lane, a, piece_parity, list, n_list);
+                emit_toggles(t_out, lane, a, piece_parity, list, n_list);
+                const uint32_t last = min(31u, mv.n_chr - 1 - c0);
+                carry_e = __shfl_sync(0xffffffffu, e_c, last);
+                carry_pos = __shfl_sync(0xffffffffu, end, last);
             }
-            emit_toggles(t_in, lane, a, piece_parity, list, n_list);
-            emit_toggles(t_out, lane, a, piece_parity, list, n_list);
+            emit_toggles(lane == 0 && carry_e ? carry_pos : kNoToggle, lane, a, piece_parity, list, n_list);
         }
         __syncwarp();
         if (n_list > a.tcap) {
@@ -365,6 +398,42 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
         // E2. lane per toggle: flipping the strand from bit o of its piece on means XOR-ing
         //     (strand0 ^ strand1) & (ones from bit o) into what E1 wrote; XOR fix-ups of several
         //     toggles in one piece commute, so they are applied with 64-bit atomic XORs.
+        long long bv = 0;
+        const long long* bv_tab = nullptr;
+        uint32_t* multi_keys = reinterpret_cast<uint32_t*>(xinfo);       // the crossover list is dead by now
+        uint32_t n_multi = 0;
+        if (kBv) {
+            uint32_t slot = a.bv_slot[src_row];
+            if (slot == 0xffffffffu) {                       // parent outside the pool: the GEBV is void
+                if (lane == 0) atomicExch(a.flag, 4);
+                slot = 0;
+            }
+            bv_tab = a.bv_tab + (size_t) slot * (a.plane_words + 2);
+            // pieces holding two or more toggles, and the (few) toggles inside them as keys (position, index)
+            for (uint32_t i = lane; i < 2 * a.parity_words; i += 32) piece_seen[i] = 0;
+            __syncwarp();
+            for (uint32_t i = lane; i < n_list; i += 32) {
+                const uint32_t u = list[i] >> 7, bit = 1u << (u & 31);
+                if (atomicOr(&piece_seen[u >> 5], bit) & bit) atomicOr(&piece_multi[u >> 5], bit);
+            }
+            __syncwarp();
+            for (uint32_t i0 = 0; i0 < n_list; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const uint32_t t = i < n_list ? list[i] : 0u;
+                const bool in_multi = i < n_list && ((piece_multi[t >> 12] >> ((t >> 7) & 31)) & 1u);
+                const uint32_t ballot = __ballot_sync(0xffffffffu, in_multi);
+                if (in_multi) {
+                    const uint32_t k = n_multi + __popc(ballot & ((1u << lane) - 1u));
+                    if (k < 2 * a.xcap) multi_keys[k] = (t << 7) | (i & 127u);
+                }
+                n_multi += __popc(ballot);
+            }
+            __syncwarp();
+            if (n_multi > 2 * a.xcap || n_list > 128) {      // cannot rank them here: the batch is redone
+                if (lane == 0) atomicExch(a.flag, 1);
+                n_multi = 0;
+            }
+        }
         for (uint32_t i0 = 0; i0 < n_list; i0 += 32) {
             const uint32_t i = i0 + lane;
             if (i >= n_list) continue;
@@ -375,6 +444,38 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
             for (uint32_t p = 0; p < a.planes; ++p) {
                 const uint32_t* s0 = src + p * a.plane_words + 4 * u;
                 const uint4 h0 = ldg128(s0), h1 = ldg128(s0 + hap_stride);
+                if (kBv) {
+                    // strand this toggle leaves: the one its piece starts on, flipped per earlier toggle in the piece
+                    uint32_t leaves = (piece_parity[u >> 5] >> (u & 31)) & 1u;
+                    if ((piece_multi[u >> 5] >> (u & 31)) & 1u) {
+                        const uint32_t key = (t << 7) | (i & 127u);
+                        for (uint32_t k = 0; k < n_multi; ++k) {
+                            const uint32_t kj = multi_keys[k];
+                            leaves ^= (uint32_t) ((kj >> 14) == u && kj < key);
+                        }
+                    }
+                    const uint32_t wq = (uint32_t) o >> 5, low = (1u << (o & 31)) - 1u;
+                    const uint32_t x0 = wq == 0 ? h0.x : wq == 1 ? h0.y : wq == 2 ? h0.z : h0.w;
+                    const uint32_t x1 = wq == 0 ? h1.x : wq == 1 ? h1.y : wq == 2 ? h1.z : h1.w;
+                    long long gd = bv_tab[t >> 5];
+                    // markers below the toggle in its word where the strands differ: four table reads in
+                    // flight at a time (one read per trip would cost a full cache latency per marker)
+                    const long long* qw = a.bv_q + ((size_t) (t >> 5) << 5);
+                    for (uint32_t m = (x0 ^ x1) & low; m;) {
+                        uint32_t b[4];
+                        long long v[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            b[k] = m ? (uint32_t) __ffs((int) m) - 1u : 32u;
+                            m &= m - 1;                      // 0 stays 0
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[k] = b[k] < 32u ? qw[b[k]] : 0ll;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) gd += ((x0 >> (b[k] & 31u)) & 1u) ? v[k] : -v[k];
+                    }
+                    bv += leaves ? -gd : gd;
+                }
                 const unsigned long long lo = ((unsigned long long) ((h0.y ^ h1.y) & m1) << 32) | ((h0.x ^ h1.x) & m0);
                 const unsigned long long hi = ((unsigned long long) ((h0.w ^ h1.w) & m3) << 32) | ((h0.z ^ h1.z) & m2);
                 unsigned long long* out = reinterpret_cast<unsigned long long*>(dst + (gam * a.planes + p) * a.plane_words + 4 * u);
@@ -387,8 +488,81 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
                 }
             }
         }
+        if (kBv) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bv += __shfl_xor_sync(0xffffffffu, bv, o);
+            if (lane == 0) {
+                // the walk starts on strand 0; an odd number of toggles leaves it on strand 1 at the end
+                bv += bv_tab[a.plane_words + 1] - ((n_list & 1u) ? bv_tab[a.plane_words] : 0ll);
+                atomicAdd(a.bv_acc + unit_local, (unsigned long long) bv);
+            }
+        }
         __syncwarp();
     }
+}
+
+// Prefix tables of the pool rows, for splice_flat_kernel<true>:
+//   tab[slot][w]                = sum_{m < 32 w} Q_m * (h0(m) - h1(m)),   w = 0 .. plane_words
+//   tab[slot][plane_words + 1]  = sum_m Q_m * h0(m)
+// and slot_of_row[row] = slot.  First every word's own sum (a thread per word), then a scan per row.
+__global__ void parent_words_kernel(const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
+                                    const uint32_t* __restrict__ pool_rows, uint32_t n_pool, const long long* __restrict__ q,
+                                    long long* __restrict__ tab, uint32_t* __restrict__ slot_of_row) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x, slot = blockIdx.y;
+    const uint32_t row = pool_rows[slot];
+    long long* out = tab + (size_t) slot * (plane_words + 2);
+    if (w == 0) slot_of_row[row] = slot;
+    long long d = 0, t0 = 0;
+    if (w < plane_words) {
+        const uint32_t* h0 = store + (uint64_t) row * row_words;
+        const uint32_t x0 = h0[w], x1 = h0[plane_words + w];
+        const long long* qw = q + ((size_t) w << 5);
+        for (uint32_t m = x0 | x1; m;) {
+            uint32_t b[4];
+            long long v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { b[k] = m ? (uint32_t) __ffs((int) m) - 1u : 32u; m &= m - 1; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = b[k] < 32u ? qw[b[k]] : 0ll;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t in0 = (x0 >> (b[k] & 31u)) & 1u, in1 = (x1 >> (b[k] & 31u)) & 1u;
+                if (in0) t0 += v[k];
+                d += (long long) ((int) in0 - (int) in1) * v[k];
+            }
+        }
+        out[w] = d;
+    }
+    // strand 0's total: warp sums, one atomic per warp (the table was cleared before the launch)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+    if ((threadIdx.x & 31) == 0 && t0) atomicAdd(reinterpret_cast<unsigned long long*>(out + plane_words + 1), (unsigned long long) t0);
+}
+
+__global__ void parent_scan_kernel(uint32_t plane_words, uint32_t n_pool, long long* __restrict__ tab) {
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (slot >= n_pool) return;
+    long long* out = tab + (size_t) slot * (plane_words + 2);
+    long long carry = 0;
+    for (uint32_t w0 = 0; w0 < plane_words; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        const long long d = w < plane_words ? out[w] : 0ll;
+        long long incl = d;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int) lane >= o) incl += v;
+        }
+        if (w < plane_words) out[w] = carry + incl - d;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) out[plane_words] = carry;
+}
+
+// bv[i] = offset + scale * (sum of the unit's gamete values)
+__global__ void bv_finish_kernel(const long long* __restrict__ acc, uint32_t n, double scale, double offset, double* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = offset + (double) acc[i] * scale;
 }
 
 // ------------------------------------------------------------------ general kernel
@@ -610,6 +784,9 @@ struct Batch {
     uint32_t gametes_per_unit, doubled;
     DrawView draws;
     uint32_t tape_xcap;        // TAPE: most crossovers in one gamete
+    // fused GEBV (null: none); only taken on the fast kernel
+    const long long* bv_tab = nullptr; const uint32_t* bv_slot = nullptr; const long long* bv_q = nullptr;
+    unsigned long long* bv_acc = nullptr;
 };
 
 // Philox draws materialised in tape layout on the device (s_plan[4..7]).
@@ -690,6 +867,7 @@ int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
     a.map[1] = view_of(b.gametes_per_unit > 1 ? *b.map1 : *b.map0);
     a.draws = b.draws;
     a.flag = ctx->d_flag;
+    a.bv_tab = b.bv_tab; a.bv_slot = b.bv_slot; a.bv_q = b.bv_q; a.bv_acc = b.bv_acc;
 
     const DeviceMap* maps[2] = { b.map0, b.gametes_per_unit > 1 ? b.map1 : b.map0 };
     if (b.draws.mode == GSB200_DRAWS_PHILOX) {
@@ -717,21 +895,23 @@ int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
     xcap = std::max<uint32_t>((xcap + 31) / 32 * 32, 32);
     a.xcap = xcap;
     a.tcap = (xcap + 2 * n_chr_max + 1) / 2 * 2;
-    a.warp_smem_words = (a.parity_words + 2 * a.chr_words + a.tcap + 2 * a.xcap + 3) / 4 * 4;
+    a.warp_smem_words = (a.parity_words * (b.bv_acc ? 3 : 1) + 2 * a.chr_words + a.tcap + 2 * a.xcap + 3) / 4 * 4;
     if ((uint64_t) b.n_units * b.gametes_per_unit >= (1ull << 32)) fast = false;
     uint32_t warps = 8;
     const size_t smem_limit = 200 * 1024;
     while (warps > 1 && (size_t) warps * a.warp_smem_words * 4 > smem_limit / 2) warps >>= 1;
     if ((size_t) warps * a.warp_smem_words * 4 > smem_limit) fast = false;
 
+    GSB_REQUIRE(fast || !b.bv_acc, GSB200_ERR_UNSUPPORTED, "%s: internal: fused GEBV needs the flat splice kernel", b.what);
     if (fast) {
         const size_t smem = (size_t) warps * a.warp_smem_words * 4;
+        auto* kernel = b.bv_acc ? splice_flat_kernel<true> : splice_flat_kernel<false>;
         if (smem > 48 * 1024)
-            GSB_CUDA_TRY(cudaFuncSetAttribute(splice_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_limit));
+            GSB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_limit));
         const uint64_t n_gametes = (uint64_t) a.n_units * a.gametes_per_unit;
         const uint64_t blocks = (n_gametes + warps - 1) / warps;
         const unsigned grid = (unsigned) std::min<uint64_t>(blocks, (uint64_t) ctx->sm_count * 64);
-        splice_flat_kernel<<<grid, warps * 32, smem, ctx->stream>>>(a);
+        kernel<<<grid, warps * 32, smem, ctx->stream>>>(a);
         ++ctx->launches;
         GSB_CUDA_TRY(cudaGetLastError());
         if (!may_sync) return GSB200_OK;
@@ -810,8 +990,10 @@ int make_draw_view(const gsb200_draws* d, DrawView* v, const char* what) {
     return GSB200_OK;
 }
 
+struct FusedBv { const long long* tab; const uint32_t* slot; const long long* q; unsigned long long* acc; };
+
 int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t* d_p2, uint32_t map1, uint32_t map2,
-               const uint32_t* d_out, const gsb200_draws* draws, bool may_sync, const char* what) {
+               const uint32_t* d_out, const gsb200_draws* draws, bool may_sync, const char* what, const FusedBv* bv = nullptr) {
     const DeviceMap *m1, *m2;
     GSB_TRY(get_map(ctx, map1, &m1, what));
     GSB_TRY(get_map(ctx, map2, &m2, what));
@@ -821,6 +1003,7 @@ int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t
     b.what = what; b.n_units = n;
     b.src_base = ctx->d_store; b.d_src0 = d_p1; b.d_src1 = d_p2; b.dst_base = ctx->d_store; b.d_dst = d_out;
     b.map0 = m1; b.map1 = m2; b.gametes_per_unit = 2; b.doubled = 0; b.tape_xcap = 0;
+    if (bv) { b.bv_tab = bv->tab; b.bv_slot = bv->slot; b.bv_q = bv->q; b.bv_acc = bv->acc; }
     GSB_TRY(make_draw_view(draws, &b.draws, what));
     if (draws->mode == GSB200_DRAWS_TAPE) {
         GSB_REQUIRE(may_sync, GSB200_ERR_ARG, "%s: device-pointer entry points take PHILOX draws only", what);
@@ -864,6 +1047,57 @@ int gsb200_cross_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1_rows
     GSB_REQUIRE(d_parent1_rows && d_parent2_rows && d_out_rows, GSB200_ERR_ARG, "gsb200_cross_dev: null row array");
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
     return cross_impl(ctx, n, d_parent1_rows, d_parent2_rows, map1, map2, d_out_rows, draws, false, "gsb200_cross_dev");
+}
+
+int gsb200_cross_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1_rows, const uint32_t* d_parent2_rows,
+                          uint32_t map1, uint32_t map2, const uint32_t* d_out_rows, const gsb200_draws* draws,
+                          uint32_t n_pool, const uint32_t* d_pool_rows, uint32_t eff_index, double* d_bv) {
+    const char* what = "gsb200_cross_gebv_dev";
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    if (n == 0) return GSB200_OK;
+    GSB_REQUIRE(d_parent1_rows && d_parent2_rows && d_out_rows && d_bv, GSB200_ERR_ARG, "%s: null array", what);
+    GSB_REQUIRE(draws != nullptr, GSB200_ERR_ARG, "%s: null draws", what);
+    GSB_REQUIRE(eff_index < ctx->effects.size() && ctx->effects[eff_index].present, GSB200_ERR_ARG,
+                "%s: no effect set at index %u", what, eff_index);
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    const DeviceMap *m1, *m2;
+    GSB_TRY(get_map(ctx, map1, &m1, what));
+    GSB_TRY(get_map(ctx, map2, &m2, what));
+    // The plan-based GEBV needs the flat splice kernel, a one-plane store, the parents' pool and
+    // tables that fit; anything else is the two separate passes.
+    const size_t tab_bytes = (size_t) n_pool * (ctx->plane_words + 2) * sizeof(long long);
+    const bool fused = ctx->planes == 1 && m1->flat && m2->flat && d_pool_rows && n_pool > 0 && n_pool <= 65535 && tab_bytes <= ((size_t) 2 << 30)
+                       && ctx->n_markers < (1u << 25) && draws->mode == GSB200_DRAWS_PHILOX;
+    if (!fused) {
+        GSB_TRY(cross_impl(ctx, n, d_parent1_rows, d_parent2_rows, map1, map2, d_out_rows, draws, false, what));
+        return gsb200_gebv_dev(ctx, n, d_out_rows, eff_index, d_bv);
+    }
+    GSB_TRY(ensure_effect_tables(ctx, eff_index));
+    const DeviceEffects& e = ctx->effects[eff_index];
+    GSB_TRY(ctx->s_bv[0].ensure(tab_bytes));
+    GSB_TRY(ctx->s_bv[1].ensure((size_t) ctx->capacity * sizeof(uint32_t)));
+    GSB_TRY(ctx->s_bv[2].ensure((size_t) n * sizeof(long long)));
+    long long* d_tab = (long long*) ctx->s_bv[0].ptr;
+    uint32_t* d_slot = (uint32_t*) ctx->s_bv[1].ptr;
+    unsigned long long* d_acc = (unsigned long long*) ctx->s_bv[2].ptr;
+    // rows outside the pool keep slot 0xffffffff and raise the flag (gsb200_cross_dev_status); a stale slot
+    // of an earlier call would silently give a wrong GEBV, so the map is reset every time (4 bytes per row)
+    GSB_CUDA_TRY(cudaMemsetAsync(d_slot, 0xff, (size_t) ctx->capacity * sizeof(uint32_t), ctx->stream));
+    GSB_CUDA_TRY(cudaMemsetAsync(d_acc, 0, (size_t) n * sizeof(long long), ctx->stream));
+    // the per-row totals are accumulated with atomics: clear them first (the slot map reset covers the rest)
+    GSB_CUDA_TRY(cudaMemsetAsync(d_tab, 0, tab_bytes, ctx->stream));
+    parent_words_kernel<<<dim3((ctx->plane_words + 127) / 128, n_pool), 128, 0, ctx->stream>>>(
+        ctx->d_store, ctx->row_words(), ctx->plane_words, d_pool_rows, n_pool, e.d_bvq, d_tab, d_slot);
+    parent_scan_kernel<<<(n_pool * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->plane_words, n_pool, d_tab);
+    ctx->launches += 2;
+    GSB_CUDA_TRY(cudaGetLastError());
+    const FusedBv bv = { d_tab, d_slot, e.d_bvq, d_acc };
+    GSB_TRY(cross_impl(ctx, n, d_parent1_rows, d_parent2_rows, map1, map2, d_out_rows, draws, false, what, &bv));
+    const double centre_sum = e.has_centre ? e.centre_sum : 0.0;
+    bv_finish_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const long long*) d_acc, n, e.bvq_scale, e.base_all - centre_sum, d_bv);
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    return GSB200_OK;
 }
 
 int gsb200_cross_random_pairs(gsb200_ctx* ctx, uint32_t n_crosses, uint32_t family_size,
@@ -913,6 +1147,7 @@ int gsb200_cross_dev_status(gsb200_ctx* ctx) {
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
     int flag = 0;
     GSB_TRY(check_flag(ctx, &flag));
+    GSB_REQUIRE(flag != 4, GSB200_ERR_ARG, "gsb200_cross_gebv_dev: a parent row was not in the pool; the GEBVs of that batch are void");
     GSB_REQUIRE(flag == 0, GSB200_ERR_UNSUPPORTED,
                 "a gsb200_cross_dev batch exceeded the splice plan's capacity; redo it with gsb200_cross");
     return GSB200_OK;

@@ -164,6 +164,20 @@ int  gsb200_cross_random_pairs(gsb200_ctx* ctx, uint32_t n_crosses, uint32_t fam
  * multi-GPU generation loops).  PHILOX draws only.  Asynchronous on the context stream. */
 int  gsb200_cross_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1_rows, const uint32_t* d_parent2_rows,
                       uint32_t map1, uint32_t map2, const uint32_t* d_out_rows, const gsb200_draws* draws);
+/* gsb200_cross_dev plus the GEBVs of the offspring for effect set `eff_index` (d_bv[n], device), i.e.
+ * make.random.crosses followed by see.GEBVs (wrap.c:1914 + 795-813) in one pass.  The GEBVs are NOT
+ * computed by reading the offspring back: d_pool_rows[n_pool] (device) lists the distinct rows the
+ * parents come from (the crossed group), a prefix table of effect sums is built per pool row, and
+ * each gamete's value is assembled from the table at its crossover points while it is spliced.
+ * Same value as gsb200_gebv_dev on the offspring up to fp64 rounding (both are exact fixed-point
+ * sums converted once).  Falls back to the two separate passes when the store has several planes,
+ * a map is not in marker order, or the tables would not fit.  A parent row outside the pool is
+ * reported by gsb200_cross_dev_status. */
+int  gsb200_cross_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1_rows,
+                           const uint32_t* d_parent2_rows, uint32_t map1, uint32_t map2,
+                           const uint32_t* d_out_rows, const gsb200_draws* draws,
+                           uint32_t n_pool, const uint32_t* d_pool_rows, uint32_t eff_index, double* d_bv);
+
 /* Synchronises and reports whether any gsb200_cross_dev batch since the last check drew more
  * crossovers than its on-chip splice plan holds (probability < 1e-15 per gamete); such a batch
  * must be redone with gsb200_cross, which falls back to the general kernel by itself. */

@@ -300,3 +300,53 @@ def test_store_round_trips_random_alphabets():
             g2[g2 == frm] = to
             np.testing.assert_array_equal(sim.export_group(0)["genotypes"], g2)
         sim.close()
+
+
+@pytest.mark.parametrize("shape", [(40, 3000, 5, 120.0), (64, 50000, 21, 150.0), (7, 130, 3, 400.0)])
+def test_fused_cross_gebv_equals_cross_then_gebv(shape):
+    """gsb200_cross_gebv_dev: the same offspring as gsb200_cross_dev with the same draws, and GEBVs —
+    assembled from the crossover plan and the parents' prefix tables, never reading the offspring —
+    equal to gsb200_gebv_dev on those offspring, which the parity tests hold against the reference."""
+    import torch
+    F, M, n_chr, cm = shape
+    ds = datasets.synthetic(F, M, n_chr, cm, seed=21, spacing="random")
+    sim = make_sim(ds)
+    E, ctx = sim.E, sim.ctx
+    n = 3000
+    assert E.gsb200_store_reserve(ctx, F + 2 * n) == 0
+    rng = np.random.default_rng(5)
+    p1 = rng.integers(0, F, n).astype(np.int32)
+    p2 = rng.integers(0, F, n).astype(np.int32)              # selfed pairs (p1 == p2) included
+    d_p1, d_p2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    d_out_a = torch.arange(F, F + n, dtype=torch.int32, device="cuda")
+    d_out_b = torch.arange(F + n, F + 2 * n, dtype=torch.int32, device="cuda")
+    d_pool = torch.arange(0, F, dtype=torch.int32, device="cuda")
+    d_bv_fused = torch.zeros(n, dtype=torch.float64, device="cuda")
+    d_bv_a = torch.zeros(n, dtype=torch.float64, device="cuda")
+    d_bv_b = torch.zeros(n, dtype=torch.float64, device="cuda")
+    dr = philox(99, stream=3, first_unit=1000)
+    st = E.gsb200_cross_gebv_dev(ctx, n, d_p1.data_ptr(), d_p2.data_ptr(), 0, 0, d_out_a.data_ptr(), C.byref(dr),
+                                 F, d_pool.data_ptr(), 0, d_bv_fused.data_ptr())
+    assert st == 0, E.gsb200_last_error()
+    st = E.gsb200_cross_dev(ctx, n, d_p1.data_ptr(), d_p2.data_ptr(), 0, 0, d_out_b.data_ptr(), C.byref(dr))
+    assert st == 0, E.gsb200_last_error()
+    assert E.gsb200_cross_dev_status(ctx) == 0, E.gsb200_last_error()
+    assert E.gsb200_gebv_dev(ctx, n, d_out_a.data_ptr(), 0, d_bv_a.data_ptr()) == 0
+    assert E.gsb200_gebv_dev(ctx, n, d_out_b.data_ptr(), 0, d_bv_b.data_ptr()) == 0
+    torch.cuda.synchronize()
+    fused, a, b = d_bv_fused.cpu().numpy(), d_bv_a.cpu().numpy(), d_bv_b.cpu().numpy()
+    # same genotypes from both entry points
+    rows = np.arange(F, F + 2 * n, dtype=np.uint32)
+    chars = np.zeros((2 * n, 2 * M), dtype=np.uint8)
+    assert E.gsb200_store_download_chars(ctx, 2 * n, _p(rows), _p(chars)) == 0, E.gsb200_last_error()
+    assert (chars[:n] == chars[n:]).all()
+    assert np.array_equal(a, b)
+    scale = np.abs(a).mean() + np.abs(np.asarray(ds["effects"][0]["eff"])).max()
+    assert np.abs(fused - a).max() <= 1e-11 * scale, (np.abs(fused - a).max(), scale)
+    assert a.std() > 0                                       # the comparison is not vacuous
+    # a parent outside the pool voids the batch and is reported
+    st = E.gsb200_cross_gebv_dev(ctx, n, d_p1.data_ptr(), d_p2.data_ptr(), 0, 0, d_out_a.data_ptr(), C.byref(dr),
+                                 F - 1, d_pool.data_ptr(), 0, d_bv_fused.data_ptr())
+    assert st == 0
+    assert E.gsb200_cross_dev_status(ctx) != 0 and b"pool" in E.gsb200_last_error()
+    sim.close()
