@@ -504,48 +504,55 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
 // Prefix tables of the pool rows, for splice_flat_kernel<true>:
 //   tab[slot][w]                = sum_{m < 32 w} Q_m * (h0(m) - h1(m)),   w = 0 .. plane_words
 //   tab[slot][plane_words + 1]  = sum_m Q_m * h0(m)
-// and slot_of_row[row] = slot.  First every word's own sum (a thread per word), then a scan per row.
-__global__ void parent_words_kernel(const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
-                                    const uint32_t* __restrict__ pool_rows, uint32_t n_pool, const long long* __restrict__ q,
-                                    long long* __restrict__ tab, uint32_t* __restrict__ slot_of_row) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x, slot = blockIdx.y;
-    const uint32_t row = pool_rows[slot];
-    long long* out = tab + (size_t) slot * (plane_words + 2);
-    if (w == 0) slot_of_row[row] = slot;
-    long long d = 0, t0 = 0;
-    if (w < plane_words) {
-        const uint32_t* h0 = store + (uint64_t) row * row_words;
-        const uint32_t x0 = h0[w], x1 = h0[plane_words + w];
-        const long long* qw = q + ((size_t) w << 5);
-        for (uint32_t m = x0 | x1; m;) {
-            uint32_t b[4];
-            long long v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { b[k] = m ? (uint32_t) __ffs((int) m) - 1u : 32u; m &= m - 1; }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = b[k] < 32u ? qw[b[k]] : 0ll;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t in0 = (x0 >> (b[k] & 31u)) & 1u, in1 = (x1 >> (b[k] & 31u)) & 1u;
-                if (in0) t0 += v[k];
-                d += (long long) ((int) in0 - (int) in1) * v[k];
-            }
-        }
-        out[w] = d;
+// and slot_of_row[row] = slot.  First every word's own sum: a block owns 32 marker words, keeps
+// their 1024 Q values in shared memory and walks the pool rows, 8 at a time, a thread per
+// (row, word).  Then one block per row turns the word sums into prefixes.
+constexpr uint32_t kTabWords = 32, kTabRows = 8;
+__global__ void __launch_bounds__(kTabWords * kTabRows) parent_words_kernel(
+        const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
+        const uint32_t* __restrict__ pool_rows, uint32_t n_pool, uint32_t rows_per_block, const long long* __restrict__ q,
+        long long* __restrict__ tab, uint32_t* __restrict__ slot_of_row) {
+    __shared__ long long s_q[kTabWords * 32];
+    const uint32_t w_local = threadIdx.x & (kTabWords - 1), r_local = threadIdx.x / kTabWords;
+    const uint32_t w = blockIdx.x * kTabWords + w_local;
+    for (uint32_t i = threadIdx.x; i < kTabWords * 32; i += kTabWords * kTabRows) {
+        const size_t m = (size_t) blockIdx.x * kTabWords * 32 + i;
+        s_q[i] = m < (size_t) plane_words * 32 ? q[m] : 0ll;
     }
-    // strand 0's total: warp sums, one atomic per warp (the table was cleared before the launch)
+    __syncthreads();
+    const uint32_t slot_lo = blockIdx.y * rows_per_block, slot_hi = min(slot_lo + rows_per_block, n_pool);
+    const long long* qw = s_q + w_local * 32;
+    for (uint32_t slot = slot_lo + r_local; slot < slot_hi; slot += kTabRows) {
+        const uint32_t row = pool_rows[slot];
+        long long* out = tab + (size_t) slot * (plane_words + 2);
+        if (w == 0) slot_of_row[row] = slot;
+        long long d = 0, t0 = 0;
+        if (w < plane_words) {
+            const uint32_t* h0 = store + (uint64_t) row * row_words;
+            const uint32_t x0 = h0[w], x1 = h0[plane_words + w];
+            for (uint32_t m = x0 | x1; m; m &= m - 1) {
+                const uint32_t b = (uint32_t) __ffs((int) m) - 1u;
+                const long long v = qw[b];
+                const uint32_t in0 = (x0 >> b) & 1u, in1 = (x1 >> b) & 1u;
+                if (in0) t0 += v;
+                d += (long long) ((int) in0 - (int) in1) * v;
+            }
+            out[w] = d;
+        }
+        // strand 0's total: one atomic per warp = per row (a warp is the 32 words of one row here)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t0 += __shfl_xor_sync(0xffffffffu, t0, o);
-    if ((threadIdx.x & 31) == 0 && t0) atomicAdd(reinterpret_cast<unsigned long long*>(out + plane_words + 1), (unsigned long long) t0);
+        for (int o = 16; o > 0; o >>= 1) t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        if (w_local == 0 && t0) atomicAdd(reinterpret_cast<unsigned long long*>(out + plane_words + 1), (unsigned long long) t0);
+    }
 }
 
-__global__ void parent_scan_kernel(uint32_t plane_words, uint32_t n_pool, long long* __restrict__ tab) {
-    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (slot >= n_pool) return;
-    long long* out = tab + (size_t) slot * (plane_words + 2);
+__global__ void __launch_bounds__(256) parent_scan_kernel(uint32_t plane_words, long long* __restrict__ tab) {
+    __shared__ long long s_warp[8];
+    long long* out = tab + (size_t) blockIdx.x * (plane_words + 2);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long carry = 0;
-    for (uint32_t w0 = 0; w0 < plane_words; w0 += 32) {
-        const uint32_t w = w0 + lane;
+    for (uint32_t w0 = 0; w0 < plane_words; w0 += 256) {
+        const uint32_t w = w0 + threadIdx.x;
         const long long d = w < plane_words ? out[w] : 0ll;
         long long incl = d;
 #pragma unroll
@@ -553,10 +560,16 @@ __global__ void parent_scan_kernel(uint32_t plane_words, uint32_t n_pool, long l
             const long long v = __shfl_up_sync(0xffffffffu, incl, o);
             if ((int) lane >= o) incl += v;
         }
-        if (w < plane_words) out[w] = carry + incl - d;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        long long before = carry, total = carry;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) { if (k < warp) before += s_warp[k]; total += s_warp[k]; }
+        if (w < plane_words) out[w] = before + incl - d;
+        carry = total;
+        __syncthreads();
     }
-    if (lane == 0) out[plane_words] = carry;
+    if (threadIdx.x == 0) out[plane_words] = carry;
 }
 
 // bv[i] = offset + scale * (sum of the unit's gamete values)
@@ -1066,7 +1079,7 @@ int gsb200_cross_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1
     // The plan-based GEBV needs the flat splice kernel, a one-plane store, the parents' pool and
     // tables that fit; anything else is the two separate passes.
     const size_t tab_bytes = (size_t) n_pool * (ctx->plane_words + 2) * sizeof(long long);
-    const bool fused = ctx->planes == 1 && m1->flat && m2->flat && d_pool_rows && n_pool > 0 && n_pool <= 65535 && tab_bytes <= ((size_t) 2 << 30)
+    const bool fused = ctx->planes == 1 && m1->flat && m2->flat && d_pool_rows && n_pool > 0 && tab_bytes <= ((size_t) 2 << 30)
                        && ctx->n_markers < (1u << 25) && draws->mode == GSB200_DRAWS_PHILOX;
     if (!fused) {
         GSB_TRY(cross_impl(ctx, n, d_parent1_rows, d_parent2_rows, map1, map2, d_out_rows, draws, false, what));
@@ -1086,9 +1099,17 @@ int gsb200_cross_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1
     GSB_CUDA_TRY(cudaMemsetAsync(d_acc, 0, (size_t) n * sizeof(long long), ctx->stream));
     // the per-row totals are accumulated with atomics: clear them first (the slot map reset covers the rest)
     GSB_CUDA_TRY(cudaMemsetAsync(d_tab, 0, tab_bytes, ctx->stream));
-    parent_words_kernel<<<dim3((ctx->plane_words + 127) / 128, n_pool), 128, 0, ctx->stream>>>(
-        ctx->d_store, ctx->row_words(), ctx->plane_words, d_pool_rows, n_pool, e.d_bvq, d_tab, d_slot);
-    parent_scan_kernel<<<(n_pool * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->plane_words, n_pool, d_tab);
+    {
+        // enough blocks along the rows to fill the machine; every block reuses its Q slice for its rows
+        const uint32_t word_blocks = (ctx->plane_words + kTabWords - 1) / kTabWords;
+        uint32_t row_blocks = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) ctx->sm_count * 16 / word_blocks + 1, (n_pool + kTabRows - 1) / kTabRows));
+        row_blocks = std::min<uint32_t>(row_blocks, 65535);
+        const uint32_t rows_per_block = ((n_pool + row_blocks - 1) / row_blocks + kTabRows - 1) / kTabRows * kTabRows;
+        row_blocks = (n_pool + rows_per_block - 1) / rows_per_block;
+        parent_words_kernel<<<dim3(word_blocks, row_blocks), kTabWords * kTabRows, 0, ctx->stream>>>(
+            ctx->d_store, ctx->row_words(), ctx->plane_words, d_pool_rows, n_pool, rows_per_block, e.d_bvq, d_tab, d_slot);
+        parent_scan_kernel<<<n_pool, 256, 0, ctx->stream>>>(ctx->plane_words, d_tab);
+    }
     ctx->launches += 2;
     GSB_CUDA_TRY(cudaGetLastError());
     const FusedBv bv = { d_tab, d_slot, e.d_bvq, d_acc };
