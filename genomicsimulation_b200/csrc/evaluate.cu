@@ -258,6 +258,7 @@ constexpr uint32_t kLocalRowStride = 20;
 constexpr uint32_t kLocalBufWords = 16 * kLocalRowStride;
 constexpr int kLocalWarps = 4;
 constexpr int kLocalMaxSets = 4;
+constexpr uint32_t kLocalTile = 16;             // steps of B fragments per shared-memory tile (4 KB per effect set)
 
 struct LocalSetParams {
     const uint2* bfrag[kLocalMaxSets];     // [n_steps][32]
@@ -273,14 +274,15 @@ __global__ void __launch_bounds__(kLocalWarps * 32) local_gebv_digits_kernel(
         const uint2* __restrict__ steps /* (word, block) */, const uint32_t* __restrict__ range_lo, uint32_t n_ranges,
         const LocalSetParams sp) {
     __shared__ __align__(16) uint32_t s_buf[kLocalWarps][2][kLocalBufWords];
+    // B fragments of kLocalTile steps, shared by the block's warps (same range, 8 individuals each)
+    __shared__ __align__(16) uint4 s_bt[2][kSets][kLocalTile * 16];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t warp_global = blockIdx.x * kLocalWarps + warp;
-    const uint32_t n_groups = (n + 7) / 8;
-    if (warp_global >= n_groups * n_ranges) return;
-    const uint32_t group = warp_global % n_groups, range = warp_global / n_groups;
+    const uint32_t n_groups = (n + 7) / 8, group_blocks = (n_groups + kLocalWarps - 1) / kLocalWarps;
+    const uint32_t range = blockIdx.x / group_blocks, group = (blockIdx.x % group_blocks) * kLocalWarps + warp;
     const uint32_t g = lane >> 2, c = lane & 3;
     const uint32_t s_lo = range_lo[range], s_hi = range_lo[range + 1];
-    if (s_lo >= s_hi) return;
+    if (s_lo >= s_hi) return;                                // whole block
+    // a warp past the last group walks the last rows (it must keep the barriers) and stores nothing
 
     // staging: 16 strand rows x 64 bytes per chunk; copy `it` moves 16 bytes of row it*8 + lane/4
     // (individual r & 7, strand r >> 3)
@@ -325,8 +327,8 @@ __global__ void __launch_bounds__(kLocalWarps * 32) local_gebv_digits_kernel(
     };
 
     uint32_t cur_block = steps[s_lo].y, cur_chunk = 0xffffffffu, staged_next = 0xffffffffu, parity = 0;
-    for (uint32_t s = s_lo; s < s_hi; ++s) {
-        const uint2 st = __ldg(steps + s);
+    // one step, with its descriptor and B fragments already in registers
+    auto step = [&](const uint2 st, const uint2 (&f)[kSets]) {
         if (st.y != cur_block) { flush(cur_block); cur_block = st.y; }
         const uint32_t chunk = st.x / kChunkWords;
         if (chunk != cur_chunk) {
@@ -343,10 +345,56 @@ __global__ void __launch_bounds__(kLocalWarps * 32) local_gebv_digits_kernel(
         const uint32_t x1 = buf[(8 + g) * kLocalRowStride + (st.x % kChunkWords)];
         const uint32_t a0 = x0 & k_lo, a1 = x1 & k_lo, a2 = x0 & k_hi, a3 = x1 & k_hi;
 #pragma unroll
-        for (int q = 0; q < kSets; ++q) {
-            const uint2 f = __ldg(sp.bfrag[q] + (size_t) s * 32 + lane);
-            mma_u8s8(acc[q], a0, a1, a2, a3, f.x, f.y);
+        for (int q = 0; q < kSets; ++q) mma_u8s8(acc[q], a0, a1, a2, a3, f[q].x, f[q].y);
+    };
+    // B fragments go through shared memory a tile of kLocalTile steps at a time: read from global into
+    // registers while the previous tile is being used, stored and published with one barrier per
+    // tile.  (Read per step from L1/L2 straight before the mma, the fragment was half of all stall
+    // samples.)  Step descriptors are requested a step ahead in two alternating register sets.
+    constexpr uint32_t kPieces = kLocalTile * 16 / (kLocalWarps * 32);      // uint4 per thread, set and tile
+    uint4 nxt[kSets][kPieces];
+    auto tile_load = [&](uint32_t t0) {
+#pragma unroll
+        for (int q = 0; q < kSets; ++q)
+#pragma unroll
+            for (uint32_t k = 0; k < kPieces; ++k) {
+                const uint32_t i = threadIdx.x + k * kLocalWarps * 32;                  // uint4 index in the tile
+                const uint32_t sc = min(t0 + i / 16, s_hi - 1);
+                nxt[q][k] = __ldg(reinterpret_cast<const uint4*>(sp.bfrag[q] + (size_t) sc * 32) + (i & 15));
+            }
+    };
+    auto tile_store = [&](uint32_t buf) {
+#pragma unroll
+        for (int q = 0; q < kSets; ++q)
+#pragma unroll
+            for (uint32_t k = 0; k < kPieces; ++k) s_bt[buf][q][threadIdx.x + k * kLocalWarps * 32] = nxt[q][k];
+    };
+    tile_load(s_lo);
+    tile_store(0);
+    __syncthreads();
+    uint2 st_a = __ldg(steps + s_lo), st_b;
+    uint32_t buf = 0;
+    for (uint32_t t0 = s_lo; t0 < s_hi; t0 += kLocalTile, buf ^= 1) {
+        const uint32_t t1 = min(t0 + kLocalTile, s_hi);
+        if (t1 < s_hi) tile_load(t1);
+        for (uint32_t s = t0; s < t1; s += 2) {
+            const uint2* fa = reinterpret_cast<const uint2*>(s_bt[buf][0]) + (s - t0) * 32 + lane;
+            st_b = __ldg(steps + min(s + 1, s_hi - 1));
+            uint2 f[kSets];
+#pragma unroll
+            for (int q = 0; q < kSets; ++q) f[q] = fa[q * kLocalTile * 32];
+            step(st_a, f);
+            if (s + 1 < t1) {
+                st_a = __ldg(steps + min(s + 2, s_hi - 1));
+#pragma unroll
+                for (int q = 0; q < kSets; ++q) f[q] = fa[q * kLocalTile * 32 + 32];
+                step(st_b, f);
+            } else {
+                st_a = st_b;                                     // odd tail (only at the end of the range)
+            }
         }
+        if (t1 < s_hi) tile_store(buf ^ 1);
+        __syncthreads();
     }
     flush(cur_block);
     cp_async_wait<0>();
@@ -763,8 +811,9 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
                 sp.out[q] = device_out ? outs[q0 + q] : (double*) ((char*) ctx->s_eval[1].ptr + slab_bytes * q);
                 GSB_CUDA_TRY(cudaMemsetAsync(sp.out[q], 0, (size_t) cnt * 2 * n_blocks * sizeof(double), ctx->stream));   // empty blocks read 0
             }
-            const uint64_t warps = (uint64_t) ((cnt + 7) / 8) * n_ranges;
-            const unsigned grid = (unsigned) ((warps + kLocalWarps - 1) / kLocalWarps);
+            const uint64_t group_blocks = ((cnt + 7) / 8 + kLocalWarps - 1) / kLocalWarps;
+            GSB_REQUIRE(group_blocks * n_ranges < (1ull << 31), GSB200_ERR_ARG, "%s: too many individuals x blocks for one launch", what);
+            const unsigned grid = (unsigned) (group_blocks * n_ranges);
 #define GSB_LOCAL_LAUNCH(S) local_gebv_digits_kernel<S><<<grid, kLocalWarps * 32, 0, ctx->stream>>>( \
                 ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows + done, cnt, n_blocks, d_steps, d_ranges, n_ranges, sp)
             switch (sets) {
