@@ -255,10 +255,10 @@ __global__ void local_gebv_kernel(const uint32_t* __restrict__ store, uint64_t r
 // kSets effect sets share each A register — with many effect sets this is the dense
 // (strands x markers) x (markers x 8*sets) contraction of BASELINE.json configs[4].
 constexpr uint32_t kLocalRowStride = 20;
-constexpr uint32_t kLocalBufWords = 16 * kLocalRowStride;
+constexpr uint32_t kLocalBufWords = 32 * kLocalRowStride;     // 16 individuals x 2 strands x one 64-byte chunk
 constexpr int kLocalWarps = 4;
 constexpr int kLocalMaxSets = 4;
-constexpr uint32_t kLocalTile = 16;             // steps of B fragments per shared-memory tile (4 KB per effect set)
+constexpr uint32_t kLocalTileBytes = 16 * 1024;  // B fragments per shared-memory tile, all effect sets of the pass
 
 struct LocalSetParams {
     const uint2* bfrag[kLocalMaxSets];     // [n_steps][32]
@@ -274,56 +274,62 @@ __global__ void __launch_bounds__(kLocalWarps * 32) local_gebv_digits_kernel(
         const uint2* __restrict__ steps /* (word, block) */, const uint32_t* __restrict__ range_lo, uint32_t n_ranges,
         const LocalSetParams sp) {
     __shared__ __align__(16) uint32_t s_buf[kLocalWarps][2][kLocalBufWords];
-    // B fragments of kLocalTile steps, shared by the block's warps (same range, 8 individuals each)
+    // B fragments of kLocalTile steps, shared by the block's warps (same range, 16 individuals each)
+    constexpr uint32_t kLocalTile = kSets <= 2 ? 16 : 8;
+    static_assert(2 * kSets * kLocalTile * 256 <= 2 * kLocalTileBytes, "tile too large");
     __shared__ __align__(16) uint4 s_bt[2][kSets][kLocalTile * 16];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t n_groups = (n + 7) / 8, group_blocks = (n_groups + kLocalWarps - 1) / kLocalWarps;
+    const uint32_t n_groups = (n + 15) / 16, group_blocks = (n_groups + kLocalWarps - 1) / kLocalWarps;
     const uint32_t range = blockIdx.x / group_blocks, group = (blockIdx.x % group_blocks) * kLocalWarps + warp;
     const uint32_t g = lane >> 2, c = lane & 3;
     const uint32_t s_lo = range_lo[range], s_hi = range_lo[range + 1];
     if (s_lo >= s_hi) return;                                // whole block
     // a warp past the last group walks the last rows (it must keep the barriers) and stores nothing
 
-    // staging: 16 strand rows x 64 bytes per chunk; copy `it` moves 16 bytes of row it*8 + lane/4
-    // (individual r & 7, strand r >> 3)
-    const uint32_t my_row = rows[min(group * 8 + (lane & 7), n - 1)];
-    uint32_t stage_row[2];
+    // staging: 32 strand rows x 64 bytes per chunk; copy `it` moves 16 bytes of row it*8 + lane/4
+    // (individual r & 15, strand r >> 4)
+    const uint32_t my_row = rows[min(group * 16 + (lane & 15), n - 1)];
+    uint32_t stage_row[4];
 #pragma unroll
-    for (int it = 0; it < 2; ++it) stage_row[it] = __shfl_sync(0xffffffffu, my_row, (it * 8 + (lane >> 2)) & 7);
+    for (int it = 0; it < 4; ++it) stage_row[it] = __shfl_sync(0xffffffffu, my_row, (it * 8 + (lane >> 2)) & 15);
     const uint32_t* stage_base = store + (lane & 3) * 4;
     auto stage = [&](uint32_t chunk, uint32_t* buf) {
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
+        for (int it = 0; it < 4; ++it) {
             const uint32_t r = it * 8 + (lane >> 2);
             cp_async16(buf + r * kLocalRowStride + (lane & 3) * 4,
-                       stage_base + (uint64_t) stage_row[it] * row_words + (r >> 3) * plane_words + chunk * kChunkWords);
+                       stage_base + (uint64_t) stage_row[it] * row_words + (r >> 4) * plane_words + chunk * kChunkWords);
         }
         cp_async_commit();
     };
 
     const uint32_t k_lo = 0x01010101u << c, k_hi = k_lo << 4;
     const uint32_t n_chunks = plane_words / kChunkWords;
-    int acc[kSets][4];
+    // two accumulator sets on the same B registers: individuals ia = 16 * group + g and ib = ia + 8
+    int acc[kSets][4], acc_b[kSets][4];
 #pragma unroll
-    for (int q = 0; q < kSets; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0;
+    for (int q = 0; q < kSets; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[q][k] = acc_b[q][k] = 0;
 
-    const uint32_t ia = group * 8 + g;
+    const uint32_t ia = group * 16 + g, ib = ia + 8;
+    const double w16 = exp2((double) (16 * c));
+    // row g = strand 0 of the individual, row g + 8 = strand 1; this lane: digits 2c, 2c+1
+    auto flush_one = [&](int (&a)[4], uint32_t ind, uint32_t block, int q) {
+        double v0 = ((double) a[0] + 256.0 * (double) a[1]) * w16;
+        double v1 = ((double) a[2] + 256.0 * (double) a[3]) * w16;
+        v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+        v0 += __shfl_xor_sync(0xffffffffu, v0, 2); v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+        if (c == 0 && ind < n) {
+            const double b = sp.base[q][block];
+            sp.out[q][(size_t) (2 * (size_t) ind) * n_blocks + block] = b + v0 * sp.scale[q];
+            sp.out[q][(size_t) (2 * (size_t) ind + 1) * n_blocks + block] = b + v1 * sp.scale[q];
+        }
+        a[0] = a[1] = a[2] = a[3] = 0;
+    };
     auto flush = [&](uint32_t block) {
 #pragma unroll
-        for (int q = 0; q < kSets; ++q) {
-            // row g = strand 0 of individual ia, row g + 8 = strand 1; this lane: digits 2c, 2c+1
-            const double w = exp2((double) (16 * c));
-            double v0 = ((double) acc[q][0] + 256.0 * (double) acc[q][1]) * w;
-            double v1 = ((double) acc[q][2] + 256.0 * (double) acc[q][3]) * w;
-            v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-            v0 += __shfl_xor_sync(0xffffffffu, v0, 2); v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
-            if (c == 0 && ia < n) {
-                const double b = sp.base[q][block];
-                sp.out[q][(size_t) (2 * (size_t) ia) * n_blocks + block] = b + v0 * sp.scale[q];
-                sp.out[q][(size_t) (2 * (size_t) ia + 1) * n_blocks + block] = b + v1 * sp.scale[q];
-            }
-            acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0;
-        }
+        for (int q = 0; q < kSets; ++q) { flush_one(acc[q], ia, block, q); flush_one(acc_b[q], ib, block, q); }
     };
 
     uint32_t cur_block = steps[s_lo].y, cur_chunk = 0xffffffffu, staged_next = 0xffffffffu, parity = 0;
@@ -340,12 +346,16 @@ __global__ void __launch_bounds__(kLocalWarps * 32) local_gebv_digits_kernel(
             else { staged_next = 0xffffffffu; cp_async_wait<0>(); }
             __syncwarp();
         }
-        const uint32_t* buf = s_buf[warp][parity];
-        const uint32_t x0 = buf[g * kLocalRowStride + (st.x % kChunkWords)];
-        const uint32_t x1 = buf[(8 + g) * kLocalRowStride + (st.x % kChunkWords)];
-        const uint32_t a0 = x0 & k_lo, a1 = x1 & k_lo, a2 = x0 & k_hi, a3 = x1 & k_hi;
+        const uint32_t* buf = s_buf[warp][parity] + g * kLocalRowStride + (st.x % kChunkWords);
+        const uint32_t xa0 = buf[0], xa1 = buf[16 * kLocalRowStride];                      // individual ia: strand 0, 1
+        const uint32_t xb0 = buf[8 * kLocalRowStride], xb1 = buf[24 * kLocalRowStride];    // individual ib
+        const uint32_t a0 = xa0 & k_lo, a1 = xa1 & k_lo, a2 = xa0 & k_hi, a3 = xa1 & k_hi;
+        const uint32_t b0 = xb0 & k_lo, b1 = xb1 & k_lo, b2 = xb0 & k_hi, b3 = xb1 & k_hi;
 #pragma unroll
-        for (int q = 0; q < kSets; ++q) mma_u8s8(acc[q], a0, a1, a2, a3, f[q].x, f[q].y);
+        for (int q = 0; q < kSets; ++q) {
+            mma_u8s8(acc[q], a0, a1, a2, a3, f[q].x, f[q].y);
+            mma_u8s8(acc_b[q], b0, b1, b2, b3, f[q].x, f[q].y);
+        }
     };
     // B fragments go through shared memory a tile of kLocalTile steps at a time: read from global into
     // registers while the previous tile is being used, stored and published with one barrier per
@@ -733,8 +743,8 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
     const std::vector<uint2>& steps = sc.steps;
     const std::vector<uint32_t>& block_first = sc.block_first;
     const uint32_t M = ctx->n_markers, n_steps = (uint32_t) steps.size();
-    // block ranges: tasks = (8 individuals) x (range of whole blocks), a few waves over the machine
-    const uint32_t n_groups = (n + 7) / 8;
+    // block ranges: tasks = (16 individuals) x (range of whole blocks), a few waves over the machine
+    const uint32_t n_groups = (n + 15) / 16;
     uint32_t want_ranges = (uint32_t) std::max<uint64_t>(1, ((uint64_t) ctx->sm_count * 48 * 4 + n_groups - 1) / n_groups);
     want_ranges = std::min<uint32_t>(want_ranges, (uint32_t) block_first.size() - 1);
     std::vector<uint32_t> range_lo(1, 0);
@@ -811,7 +821,7 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
                 sp.out[q] = device_out ? outs[q0 + q] : (double*) ((char*) ctx->s_eval[1].ptr + slab_bytes * q);
                 GSB_CUDA_TRY(cudaMemsetAsync(sp.out[q], 0, (size_t) cnt * 2 * n_blocks * sizeof(double), ctx->stream));   // empty blocks read 0
             }
-            const uint64_t group_blocks = ((cnt + 7) / 8 + kLocalWarps - 1) / kLocalWarps;
+            const uint64_t group_blocks = ((cnt + 15) / 16 + kLocalWarps - 1) / kLocalWarps;
             GSB_REQUIRE(group_blocks * n_ranges < (1ull << 31), GSB200_ERR_ARG, "%s: too many individuals x blocks for one launch", what);
             const unsigned grid = (unsigned) (group_blocks * n_ranges);
 #define GSB_LOCAL_LAUNCH(S) local_gebv_digits_kernel<S><<<grid, kLocalWarps * 32, 0, ctx->stream>>>( \
