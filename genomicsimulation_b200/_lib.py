@@ -75,6 +75,8 @@ ENGINE_SYMBOLS = {
     "gsb200_effects_delete": (I32, [VP, U32]),
     "gsb200_cross": (I32, [VP, U32, VP, VP, U32, U32, VP, C.POINTER(Draws)]),
     "gsb200_cross_random_pairs": (I32, [VP, U32, U32, VP, U32, VP, U32, U32, U32, VP, U32, C.POINTER(Draws), VP, VP]),
+    "gsb200_cross_random_pairs_begin": (I32, [VP, U32, U32, VP, U32, VP, U32, U32, U32, VP, U32, C.POINTER(Draws), VP, VP]),
+    "gsb200_cross_random_pairs_end": (I32, [VP]),
     "gsb200_cross_dev": (I32, [VP, U32, VP, VP, U32, U32, VP, C.POINTER(Draws)]),
     "gsb200_cross_gebv_dev": (I32, [VP, U32, VP, VP, U32, U32, VP, C.POINTER(Draws), U32, VP, U32, VP]),
     "gsb200_cross_dev_status": (I32, [VP]),

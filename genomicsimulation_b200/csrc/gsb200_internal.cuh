@@ -137,6 +137,13 @@ struct gsb200_ctx {
     uint64_t capacity = 0;          // rows
     uint32_t* d_store = nullptr;
     uint64_t launches = 0;
+    // gsb200_cross_random_pairs_begin .. _end: what to redo should the splice plan have overflowed
+    struct PendingCross {
+        bool active = false;
+        uint32_t n = 0, map1 = 0, map2 = 0;
+        const uint32_t *d_p1 = nullptr, *d_p2 = nullptr, *d_out = nullptr;
+        gsb200_draws draws;
+    } pending_cross;
     int sm_count = gsb::kNumSMsB200;
     int* d_flag = nullptr;          // kernel-side error flag (capacity overflow in a splice plan)
 

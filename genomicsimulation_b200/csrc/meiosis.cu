@@ -1121,12 +1121,13 @@ int gsb200_cross_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1
     return GSB200_OK;
 }
 
-int gsb200_cross_random_pairs(gsb200_ctx* ctx, uint32_t n_crosses, uint32_t family_size,
+int gsb200_cross_random_pairs_begin(gsb200_ctx* ctx, uint32_t n_crosses, uint32_t family_size,
                               const uint32_t* member_rows1, uint32_t n1, const uint32_t* member_rows2, uint32_t n2,
                               uint32_t map1, uint32_t map2, const uint32_t* out_rows, uint32_t first_out_row,
                               const gsb200_draws* draws, uint32_t* picked1, uint32_t* picked2) {
     GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
     const char* what = "gsb200_cross_random_pairs";
+    GSB_REQUIRE(!ctx->pending_cross.active, GSB200_ERR_ARG, "%s: the previous batch has not been ended", what);
     const uint64_t n64 = (uint64_t) n_crosses * family_size;
     if (n64 == 0) return GSB200_OK;
     GSB_REQUIRE(n64 < (1ull << 31), GSB200_ERR_ARG, "%s: too many offspring in one call", what);
@@ -1156,12 +1157,40 @@ int gsb200_cross_random_pairs(gsb200_ctx* ctx, uint32_t n_crosses, uint32_t fami
     // the offspring of cross i are units i*family_size .. of the same stream
     gsb200_draws per_offspring = *draws;
     per_offspring.first_unit = draws->first_unit * family_size;
-    GSB_TRY(cross_impl(ctx, n, d_p1, d_p2, map1, map2, d_out, &per_offspring, true, what));
+    // the picks leave before the splice kernel is enqueued: the host has them while the offspring are being made
     if (picked1) GSB_CUDA_TRY(cudaMemcpyAsync(picked1, d_k1, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (picked2) GSB_CUDA_TRY(cudaMemcpyAsync(picked2, d_k2, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (picked1 || picked2) GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    GSB_TRY(cross_impl(ctx, n, d_p1, d_p2, map1, map2, d_out, &per_offspring, false, what));
+    gsb200_ctx::PendingCross& pc = ctx->pending_cross;
+    pc.active = true; pc.n = n; pc.map1 = map1; pc.map2 = map2;
+    pc.d_p1 = d_p1; pc.d_p2 = d_p2; pc.d_out = d_out; pc.draws = per_offspring;
+    return GSB200_OK;
+}
+
+int gsb200_cross_random_pairs_end(gsb200_ctx* ctx) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    gsb200_ctx::PendingCross& pc = ctx->pending_cross;
+    if (!pc.active) return GSB200_OK;
+    pc.active = false;
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    int flag = 0;
+    GSB_TRY(check_flag(ctx, &flag));                 // synchronises
+    if (flag)                                        // the on-chip plan overflowed somewhere: same parents, same draws, general kernel
+        GSB_TRY(cross_impl(ctx, pc.n, pc.d_p1, pc.d_p2, pc.map1, pc.map2, pc.d_out, &pc.draws, true, "gsb200_cross_random_pairs"));
     GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return GSB200_OK;
 }
+
+int gsb200_cross_random_pairs(gsb200_ctx* ctx, uint32_t n_crosses, uint32_t family_size,
+                              const uint32_t* member_rows1, uint32_t n1, const uint32_t* member_rows2, uint32_t n2,
+                              uint32_t map1, uint32_t map2, const uint32_t* out_rows, uint32_t first_out_row,
+                              const gsb200_draws* draws, uint32_t* picked1, uint32_t* picked2) {
+    GSB_TRY(gsb200_cross_random_pairs_begin(ctx, n_crosses, family_size, member_rows1, n1, member_rows2, n2, map1, map2,
+                                            out_rows, first_out_row, draws, picked1, picked2));
+    return gsb200_cross_random_pairs_end(ctx);
+}
+
 
 int gsb200_cross_dev_status(gsb200_ctx* ctx) {
     GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");

@@ -159,6 +159,15 @@ int  gsb200_cross_random_pairs(gsb200_ctx* ctx, uint32_t n_crosses, uint32_t fam
                                const uint32_t* member_rows1, uint32_t n1, const uint32_t* member_rows2, uint32_t n2,
                                uint32_t map1, uint32_t map2, const uint32_t* out_rows, uint32_t first_out_row,
                                const gsb200_draws* draws, uint32_t* picked1, uint32_t* picked2);
+/* The same in two halves, for callers with host work that needs only the picks: _begin returns as
+ * soon as the picks are in picked1/2, with the offspring still being made; _end waits for them (and
+ * redoes the batch on the general kernel in the rare case a gamete's plan overflowed).  No other
+ * call may be made on the context between the two. */
+int  gsb200_cross_random_pairs_begin(gsb200_ctx* ctx, uint32_t n_crosses, uint32_t family_size,
+                               const uint32_t* member_rows1, uint32_t n1, const uint32_t* member_rows2, uint32_t n2,
+                               uint32_t map1, uint32_t map2, const uint32_t* out_rows, uint32_t first_out_row,
+                               const gsb200_draws* draws, uint32_t* picked1, uint32_t* picked2);
+int  gsb200_cross_random_pairs_end(gsb200_ctx* ctx);
 
 /* Device-pointer variants for callers that keep index arrays resident (benchmarks,
  * multi-GPU generation loops).  PHILOX draws only.  Asynchronous on the context stream. */
