@@ -183,6 +183,9 @@ def engine_arm(a):
         raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # the per-generation GEBV all-gather is 0.8 MB per rank: with NCCL's default protocol choice it took
+        # 0.19 ms at N = 8, with LL128 0.06 ms (the 12.5 MB pool broadcast is unaffected: 0.045 ms)
+        os.environ.setdefault("NCCL_PROTO", "LL128")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     M, F, n = a.markers, a.founders, a.offspring
@@ -375,6 +378,12 @@ def engine_arm(a):
     except Exception:
         pass
 
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([cross_ms, gebv_ms], dtype=torch.float64, device="cuda")
+        everyone = torch.empty(2 * world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(everyone, mine)
+        per_rank = {"cross": [round(float(x), 4) for x in everyone[0::2].tolist()], "gebv": [round(float(x), 4) for x in everyone[1::2].tolist()]}
     if rank != 0:
         return
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -389,6 +398,7 @@ def engine_arm(a):
                                "api": "gsb200_cross_gebv_dev: same offspring, GEBVs from the crossover plan + per-parent prefix "
                                       "tables (1000-row pool rebuilt every step); NOT the headline value, which keeps the two kernels"}
     if world > 1:
+        out["per_rank_kernel_ms"] = per_rank
         out["collectives"] = {"pool_broadcast_ms": float(np.mean(kernel_ms["broadcast"])), "gebv_allgather_ms": float(np.mean(kernel_ms["allgather"])),
                               "note": "rank 0, CUDA events on the engine's stream; includes waiting for the slowest rank"}
     if world == 1 and not a.no_cpu_baseline:
