@@ -350,3 +350,30 @@ def test_fused_cross_gebv_equals_cross_then_gebv(shape):
     assert st == 0
     assert E.gsb200_cross_dev_status(ctx) != 0 and b"pool" in E.gsb200_last_error()
     sim.close()
+
+
+def test_device_pairs_in_two_halves():
+    """gsb200_cross_random_pairs_begin returns with the picks while the offspring are still being made;
+    _end waits for them; the result equals the one-call form; a second _begin before _end is refused."""
+    ds = datasets.synthetic(12, 900, 4, 100.0, seed=31)
+    sim = make_sim(ds)
+    E, ctx = sim.E, sim.ctx
+    n = 500
+    assert E.gsb200_store_reserve(ctx, 12 + 2 * n) == 0
+    members = np.arange(12, dtype=np.uint32)
+    k1, k2, j1, j2 = (np.zeros(n, dtype=np.uint32) for _ in range(4))
+    dr = philox(4242, stream=1)
+    st = E.gsb200_cross_random_pairs(ctx, n, 1, _p(members), 12, None, 0, 0, 0, None, 12, C.byref(dr), _p(k1), _p(k2))
+    assert st == 0, E.gsb200_last_error()
+    st = E.gsb200_cross_random_pairs_begin(ctx, n, 1, _p(members), 12, None, 0, 0, 0, None, 12 + n, C.byref(dr), _p(j1), _p(j2))
+    assert st == 0, E.gsb200_last_error()
+    assert np.array_equal(k1, j1) and np.array_equal(k2, j2) and (j1 != j2).all()      # the picks are there already
+    assert E.gsb200_cross_random_pairs_begin(ctx, n, 1, _p(members), 12, None, 0, 0, 0, None, 12 + n, C.byref(dr), _p(j1), _p(j2)) != 0
+    assert b"not been ended" in E.gsb200_last_error()
+    assert E.gsb200_cross_random_pairs_end(ctx) == 0, E.gsb200_last_error()
+    assert E.gsb200_cross_random_pairs_end(ctx) == 0                                     # nothing pending: no-op
+    rows = np.arange(12, 12 + 2 * n, dtype=np.uint32)
+    chars = np.zeros((2 * n, 2 * 900), dtype=np.uint8)
+    assert E.gsb200_store_download_chars(ctx, 2 * n, _p(rows), _p(chars)) == 0, E.gsb200_last_error()
+    assert (chars[:n] == chars[n:]).all() and (chars[0] != chars[1]).any()
+    sim.close()
