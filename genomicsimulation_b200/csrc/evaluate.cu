@@ -249,11 +249,17 @@ __global__ void local_gebv_kernel(const uint32_t* __restrict__ store, uint64_t r
 // ------------------------------------------------------------------ local GEBV, tensor path
 // Blocks that are contiguous, ascending, non-overlapping marker ranges (what
 // gsc_create_evenlength_blocks_each_chr produces on a map in marker order) on a one-plane store:
-// the same exact digit contraction as gebv_digits_kernel, with the accumulators flushed at every
-// block boundary.  A rows are the 16 strands of 8 individuals; a "step" is one 32-marker word of
-// one block, with B digits zeroed outside the block (a word straddling two blocks is two steps).
-// kSets effect sets share each A register — with many effect sets this is the dense
-// (strands x markers) x (markers x 8*sets) contraction of BASELINE.json configs[4].
+// the exact digit contraction of the GEBV kernel, per haplotype, with the accumulators flushed at
+// every block boundary.  A rows are strands (the output is per haplotype, so the strands cannot
+// be added first as gebv_counts_kernel does): row g = strand 0, row g + 8 = strand 1 of an
+// individual; byte j of an A register = bit 8j + s of the word at weight 2^s (s = c for a0/a1,
+// c + 4 for a2/a3).  A "step" is one 32-marker word of one block, with B digits zeroed outside
+// the block (a word straddling two blocks is two steps).  A warp owns 16 individuals (two
+// accumulator sets on the same B registers) x a range of whole blocks; its 32 strand rows are
+// staged 64 bytes at a time with cp.async; the B fragments of 8-16 steps are shared by the
+// block's four warps through shared memory.  kSets effect sets share each A register — with many
+// effect sets this is the dense (strands x markers) x (markers x 8*sets) contraction of
+// BASELINE.json configs[4].
 constexpr uint32_t kLocalRowStride = 20;
 constexpr uint32_t kLocalBufWords = 32 * kLocalRowStride;     // 16 individuals x 2 strands x one 64-byte chunk
 constexpr int kLocalWarps = 4;

@@ -1,6 +1,6 @@
 // gebv_tc5.cu — GEBV digit contraction on the 5th-generation tensor cores, second design.
 //
-// Arithmetic as in gebv_digits_kernel (evaluate.cu): BV_i = base + sum_m delta_m * (bit0 + bit1),
+// Arithmetic as in gebv_counts_kernel (evaluate.cu), per strand: BV_i = base + sum_m delta_m * (bit0 + bit1),
 // delta as 8 balanced base-256 digits = the N = 8 columns of B, strand bits expanded to weighted
 // 0 / 2^s bytes = A, int32 accumulation, digit sums recombined in fp64 afterwards.  The legacy
 // mma.sync path is bounded by the IMMA issue rate (11 cycles per m16n8k32 and scheduler:
