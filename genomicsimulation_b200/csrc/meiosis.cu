@@ -86,7 +86,8 @@ struct MeiosisArgs {
     uint32_t warp_smem_words;
     int* flag;
     // fused GEBV (splice_flat_kernel<true>): see parent_tables_kernel
-    const long long* bv_tab;   // [slot][plane_words + 2]
+    const long long* bv_tab;   // [slot][(plane_words * 32 >> bv_shift) + 2]
+    uint32_t bv_shift;         // one table entry per 2^bv_shift markers (3 or 5)
     const uint32_t* bv_slot;   // row -> slot
     const long long* bv_q;     // [plane_words * 32]: fixed-point delta per marker
     unsigned long long* bv_acc;// per unit: sum over its gametes, two's complement
@@ -226,7 +227,7 @@ __device__ __forceinline__ void emit_toggles(uint32_t t, uint32_t lane, const Me
 // With Q_m the fixed-point effect difference of marker m and F_s(x) = sum_{m < x} Q_m * h_s(m) for
 // the parent's strand s, a gamete that runs on strand s_k between toggles t_k and t_{k+1} is worth
 //   sum_k F_{s_k}(t_{k+1}) - F_{s_k}(t_k)  =  F_{s_last}(M) + sum_toggles +-(F_0 - F_1)(t),
-// + when the toggle leaves strand 0, - when it leaves strand 1.  (F_0 - F_1) at every word boundary
+// + when the toggle leaves strand 0, - when it leaves strand 1.  (F_0 - F_1) at every 8- or 32-marker boundary
 // and F_0(M) come from the parent's prefix table (parent_tables_kernel); the < 32 markers between
 // the word boundary and the toggle are summed here from the parent's words.  The strand a toggle
 // leaves = the strand its 128-marker piece starts on, flipped once per earlier toggle in the
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
                 if (lane == 0) atomicExch(a.flag, 4);
                 slot = 0;
             }
-            bv_tab = a.bv_tab + (size_t) slot * (a.plane_words + 2);
+            bv_tab = a.bv_tab + (size_t) slot * (((a.plane_words * 32u) >> a.bv_shift) + 2);
             // pieces holding two or more toggles, and the (few) toggles inside them as keys (position, index)
             for (uint32_t i = lane; i < 2 * a.parity_words; i += 32) piece_seen[i] = 0;
             __syncwarp();
@@ -454,10 +455,12 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
                             leaves ^= (uint32_t) ((kj >> 14) == u && kj < key);
                         }
                     }
-                    const uint32_t wq = (uint32_t) o >> 5, low = (1u << (o & 31)) - 1u;
+                    // the prefix table entry below the toggle, then the markers between that boundary and the toggle
+                    const uint32_t span = (1u << a.bv_shift) - 1u;
+                    const uint32_t wq = (uint32_t) o >> 5, low = ((1u << (o & span)) - 1u) << (o & 31u & ~span);
                     const uint32_t x0 = wq == 0 ? h0.x : wq == 1 ? h0.y : wq == 2 ? h0.z : h0.w;
                     const uint32_t x1 = wq == 0 ? h1.x : wq == 1 ? h1.y : wq == 2 ? h1.z : h1.w;
-                    long long gd = bv_tab[t >> 5];
+                    long long gd = bv_tab[t >> a.bv_shift];
                     // markers below the toggle in its word where the strands differ: four table reads in
                     // flight at a time (one read per trip would cost a full cache latency per marker)
                     const long long* qw = a.bv_q + ((size_t) (t >> 5) << 5);
@@ -493,7 +496,8 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
             for (int o = 16; o > 0; o >>= 1) bv += __shfl_xor_sync(0xffffffffu, bv, o);
             if (lane == 0) {
                 // the walk starts on strand 0; an odd number of toggles leaves it on strand 1 at the end
-                bv += bv_tab[a.plane_words + 1] - ((n_list & 1u) ? bv_tab[a.plane_words] : 0ll);
+                const uint32_t n_tab = (a.plane_words * 32u) >> a.bv_shift;
+                bv += bv_tab[n_tab + 1] - ((n_list & 1u) ? bv_tab[n_tab] : 0ll);
                 atomicAdd(a.bv_acc + unit_local, (unsigned long long) bv);
             }
         }
@@ -501,17 +505,19 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
     }
 }
 
-// Prefix tables of the pool rows, for splice_flat_kernel<true>:
-//   tab[slot][w]                = sum_{m < 32 w} Q_m * (h0(m) - h1(m)),   w = 0 .. plane_words
-//   tab[slot][plane_words + 1]  = sum_m Q_m * h0(m)
-// and slot_of_row[row] = slot.  First every word's own sum: a block owns 32 marker words, keeps
+// Prefix tables of the pool rows, for splice_flat_kernel<true>, one entry per 8 markers while the
+// tables stay small (a coarser table leaves the splice kernel a longer marker-by-marker walk from
+// the boundary to the toggle: half of the fused path's extra instructions at 32), per 32 otherwise:
+//   tab[slot][k]          = sum_{m < G k} Q_m * (h0(m) - h1(m)),   G = 8 or 32, k = 0 .. n_tab = 32 * plane_words / G
+//   tab[slot][n_tab + 1]  = sum_m Q_m * h0(m)
+// and slot_of_row[row] = slot.  First every byte's own sum: a block owns 32 marker words, keeps
 // their 1024 Q values in shared memory and walks the pool rows, 8 at a time, a thread per
-// (row, word).  Then one block per row turns the word sums into prefixes.
+// (row, word).  Then one block per row turns the sums into prefixes.
 constexpr uint32_t kTabWords = 32, kTabRows = 8;
 __global__ void __launch_bounds__(kTabWords * kTabRows) parent_words_kernel(
         const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
         const uint32_t* __restrict__ pool_rows, uint32_t n_pool, uint32_t rows_per_block, const long long* __restrict__ q,
-        long long* __restrict__ tab, uint32_t* __restrict__ slot_of_row) {
+        uint32_t per_word /* table entries per marker word: 1 or 4 */, long long* __restrict__ tab, uint32_t* __restrict__ slot_of_row) {
     __shared__ long long s_q[kTabWords * 32];
     const uint32_t w_local = threadIdx.x & (kTabWords - 1), r_local = threadIdx.x / kTabWords;
     const uint32_t w = blockIdx.x * kTabWords + w_local;
@@ -524,36 +530,43 @@ __global__ void __launch_bounds__(kTabWords * kTabRows) parent_words_kernel(
     const long long* qw = s_q + w_local * 32;
     for (uint32_t slot = slot_lo + r_local; slot < slot_hi; slot += kTabRows) {
         const uint32_t row = pool_rows[slot];
-        long long* out = tab + (size_t) slot * (plane_words + 2);
+        long long* out = tab + (size_t) slot * (per_word * plane_words + 2);
         if (w == 0) slot_of_row[row] = slot;
-        long long d = 0, t0 = 0;
+        long long d[4] = { 0, 0, 0, 0 }, t0 = 0;
         if (w < plane_words) {
             const uint32_t* h0 = store + (uint64_t) row * row_words;
             const uint32_t x0 = h0[w], x1 = h0[plane_words + w];
-            for (uint32_t m = x0 | x1; m; m &= m - 1) {
-                const uint32_t b = (uint32_t) __ffs((int) m) - 1u;
-                const long long v = qw[b];
-                const uint32_t in0 = (x0 >> b) & 1u, in1 = (x1 >> b) & 1u;
-                if (in0) t0 += v;
-                d += (long long) ((int) in0 - (int) in1) * v;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                for (uint32_t m = ((x0 | x1) >> (8 * j)) & 255u; m; m &= m - 1) {
+                    const uint32_t b = 8 * j + (uint32_t) __ffs((int) m) - 1u;
+                    const long long v = qw[b];
+                    const uint32_t in0 = (x0 >> b) & 1u, in1 = (x1 >> b) & 1u;
+                    if (in0) t0 += v;
+                    d[j] += (long long) ((int) in0 - (int) in1) * v;
+                }
+            if (per_word == 4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) out[4 * w + j] = d[j];
+            } else {
+                out[w] = d[0] + d[1] + d[2] + d[3];
             }
-            out[w] = d;
         }
         // strand 0's total: one atomic per warp = per row (a warp is the 32 words of one row here)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t0 += __shfl_xor_sync(0xffffffffu, t0, o);
-        if (w_local == 0 && t0) atomicAdd(reinterpret_cast<unsigned long long*>(out + plane_words + 1), (unsigned long long) t0);
+        if (w_local == 0 && t0) atomicAdd(reinterpret_cast<unsigned long long*>(out + per_word * plane_words + 1), (unsigned long long) t0);
     }
 }
 
-__global__ void __launch_bounds__(256) parent_scan_kernel(uint32_t plane_words, long long* __restrict__ tab) {
+__global__ void __launch_bounds__(256) parent_scan_kernel(uint32_t n_entries, long long* __restrict__ tab) {
     __shared__ long long s_warp[8];
-    long long* out = tab + (size_t) blockIdx.x * (plane_words + 2);
+    long long* out = tab + (size_t) blockIdx.x * (n_entries + 2);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long carry = 0;
-    for (uint32_t w0 = 0; w0 < plane_words; w0 += 256) {
+    for (uint32_t w0 = 0; w0 < n_entries; w0 += 256) {
         const uint32_t w = w0 + threadIdx.x;
-        const long long d = w < plane_words ? out[w] : 0ll;
+        const long long d = w < n_entries ? out[w] : 0ll;
         long long incl = d;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -565,11 +578,11 @@ __global__ void __launch_bounds__(256) parent_scan_kernel(uint32_t plane_words, 
         long long before = carry, total = carry;
 #pragma unroll
         for (uint32_t k = 0; k < 8; ++k) { if (k < warp) before += s_warp[k]; total += s_warp[k]; }
-        if (w < plane_words) out[w] = before + incl - d;
+        if (w < n_entries) out[w] = before + incl - d;
         carry = total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[plane_words] = carry;
+    if (threadIdx.x == 0) out[n_entries] = carry;
 }
 
 // bv[i] = offset + scale * (sum of the unit's gamete values)
@@ -800,6 +813,7 @@ struct Batch {
     // fused GEBV (null: none); only taken on the fast kernel
     const long long* bv_tab = nullptr; const uint32_t* bv_slot = nullptr; const long long* bv_q = nullptr;
     unsigned long long* bv_acc = nullptr;
+    uint32_t bv_shift = 5;
 };
 
 // Philox draws materialised in tape layout on the device (s_plan[4..7]).
@@ -880,7 +894,7 @@ int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
     a.map[1] = view_of(b.gametes_per_unit > 1 ? *b.map1 : *b.map0);
     a.draws = b.draws;
     a.flag = ctx->d_flag;
-    a.bv_tab = b.bv_tab; a.bv_slot = b.bv_slot; a.bv_q = b.bv_q; a.bv_acc = b.bv_acc;
+    a.bv_tab = b.bv_tab; a.bv_slot = b.bv_slot; a.bv_q = b.bv_q; a.bv_acc = b.bv_acc; a.bv_shift = b.bv_shift;
 
     const DeviceMap* maps[2] = { b.map0, b.gametes_per_unit > 1 ? b.map1 : b.map0 };
     if (b.draws.mode == GSB200_DRAWS_PHILOX) {
@@ -1003,7 +1017,7 @@ int make_draw_view(const gsb200_draws* d, DrawView* v, const char* what) {
     return GSB200_OK;
 }
 
-struct FusedBv { const long long* tab; const uint32_t* slot; const long long* q; unsigned long long* acc; };
+struct FusedBv { const long long* tab; const uint32_t* slot; const long long* q; unsigned long long* acc; uint32_t shift; };
 
 int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t* d_p2, uint32_t map1, uint32_t map2,
                const uint32_t* d_out, const gsb200_draws* draws, bool may_sync, const char* what, const FusedBv* bv = nullptr) {
@@ -1016,7 +1030,7 @@ int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t
     b.what = what; b.n_units = n;
     b.src_base = ctx->d_store; b.d_src0 = d_p1; b.d_src1 = d_p2; b.dst_base = ctx->d_store; b.d_dst = d_out;
     b.map0 = m1; b.map1 = m2; b.gametes_per_unit = 2; b.doubled = 0; b.tape_xcap = 0;
-    if (bv) { b.bv_tab = bv->tab; b.bv_slot = bv->slot; b.bv_q = bv->q; b.bv_acc = bv->acc; }
+    if (bv) { b.bv_tab = bv->tab; b.bv_slot = bv->slot; b.bv_q = bv->q; b.bv_acc = bv->acc; b.bv_shift = bv->shift; }
     GSB_TRY(make_draw_view(draws, &b.draws, what));
     if (draws->mode == GSB200_DRAWS_TAPE) {
         GSB_REQUIRE(may_sync, GSB200_ERR_ARG, "%s: device-pointer entry points take PHILOX draws only", what);
@@ -1078,7 +1092,9 @@ int gsb200_cross_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1
     GSB_TRY(get_map(ctx, map2, &m2, what));
     // The plan-based GEBV needs the flat splice kernel, a one-plane store, the parents' pool and
     // tables that fit; anything else is the two separate passes.
-    const size_t tab_bytes = (size_t) n_pool * (ctx->plane_words + 2) * sizeof(long long);
+    // one table entry per 8 markers while all tables together stay well inside L2, per 32 markers otherwise
+    const uint32_t per_word = (size_t) n_pool * (4 * (size_t) ctx->plane_words + 2) * sizeof(long long) <= ((size_t) 64 << 20) ? 4u : 1u;
+    const size_t tab_bytes = (size_t) n_pool * (per_word * (size_t) ctx->plane_words + 2) * sizeof(long long);
     const bool fused = ctx->planes == 1 && m1->flat && m2->flat && d_pool_rows && n_pool > 0 && tab_bytes <= ((size_t) 2 << 30)
                        && ctx->n_markers < (1u << 25) && draws->mode == GSB200_DRAWS_PHILOX;
     if (!fused) {
@@ -1107,12 +1123,12 @@ int gsb200_cross_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1
         const uint32_t rows_per_block = ((n_pool + row_blocks - 1) / row_blocks + kTabRows - 1) / kTabRows * kTabRows;
         row_blocks = (n_pool + rows_per_block - 1) / rows_per_block;
         parent_words_kernel<<<dim3(word_blocks, row_blocks), kTabWords * kTabRows, 0, ctx->stream>>>(
-            ctx->d_store, ctx->row_words(), ctx->plane_words, d_pool_rows, n_pool, rows_per_block, e.d_bvq, d_tab, d_slot);
-        parent_scan_kernel<<<n_pool, 256, 0, ctx->stream>>>(ctx->plane_words, d_tab);
+            ctx->d_store, ctx->row_words(), ctx->plane_words, d_pool_rows, n_pool, rows_per_block, e.d_bvq, per_word, d_tab, d_slot);
+        parent_scan_kernel<<<n_pool, 256, 0, ctx->stream>>>(per_word * ctx->plane_words, d_tab);
     }
     ctx->launches += 2;
     GSB_CUDA_TRY(cudaGetLastError());
-    const FusedBv bv = { d_tab, d_slot, e.d_bvq, d_acc };
+    const FusedBv bv = { d_tab, d_slot, e.d_bvq, d_acc, per_word == 4 ? 3u : 5u };
     GSB_TRY(cross_impl(ctx, n, d_parent1_rows, d_parent2_rows, map1, map2, d_out_rows, draws, false, what, &bv));
     const double centre_sum = e.has_centre ? e.centre_sum : 0.0;
     bv_finish_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const long long*) d_acc, n, e.bvq_scale, e.base_all - centre_sum, d_bv);
