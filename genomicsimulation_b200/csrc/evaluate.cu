@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kGebvWarps * 32, kGebvBlocksPerSm) gebv_counts
         uint32_t n_groups, uint32_t n_segments, uint32_t seg_chunks, unsigned long long* __restrict__ digit_sums,
         unsigned int* __restrict__ next_group /* [n_segments], zeroed */) {
     extern __shared__ __align__(16) uint4 s_seg[];          // seg_chunks (rounded up to even) x 256
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t seg = blockIdx.x % n_segments;
     const uint32_t g = lane >> 2, c = lane & 3;
     const uint32_t ch_lo = seg * seg_chunks, ch_hi = min(ch_lo + seg_chunks, plane_words / kChunkWords);
