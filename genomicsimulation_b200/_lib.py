@@ -136,6 +136,8 @@ HOST_SYMBOLS = {
     "gsb_calculate_allele_counts": (DecimalMatrix, [VP, UINT, C.c_char]),
     "gsb_calculate_local_bvs": (DecimalMatrix, [VP, UINT, MarkerBlocks, UINT]),
     "gsb_create_evenlength_blocks_each_chr": (MarkerBlocks, [VP, UINT, UINT]),
+    "gsb_set_marker_names": (None, [VP, VP]),
+    "gsb_load_blocks": (MarkerBlocks, [VP, C.c_char_p]),
     "gsb_calculate_optimal_haplotype": (None, [VP, UINT, C.c_char, VP]),
     "gsb_calculate_optimal_bv": (C.c_double, [VP, UINT]),
     "gsb_calculate_minimal_bv": (C.c_double, [VP, UINT]),

@@ -38,13 +38,19 @@ class Blocks:
 
     def export(self):
         nb = self.mb.num_blocks
+        if not self.mb.offsets:
+            return np.zeros(1, dtype=np.uint32), np.zeros(0, dtype=np.uint32)
         off = np.ctypeslib.as_array(self.mb.offsets, shape=(nb + 1,)).astype(np.uint32).copy()
         mk = np.ctypeslib.as_array(self.mb.markers, shape=(max(int(off[nb]), 1),)).astype(np.uint32)[:off[nb]].copy()
         return off, mk
 
-    def __del__(self):
+    def free(self):
         if self.owned and self.mb.offsets:
             self.L.gsb_delete_markerblocks(C.byref(self.mb))
+        self.owned = False
+
+    def __del__(self):
+        self.free()
 
 
 class SimData:
@@ -69,6 +75,8 @@ class SimData:
             s.add_map(m)
         for e in ds["effects"]:
             s.add_effects(e)
+        if ds.get("marker_names"):
+            s.set_marker_names(ds["marker_names"])
         return s
 
     def close(self):
@@ -253,6 +261,13 @@ class SimData:
 
     def blocks_evenlength(self, n, map_id=0, n_chr=None):
         return Blocks(self.L, self.L.gsb_create_evenlength_blocks_each_chr(self.d, map_id, n))
+
+    def set_marker_names(self, names):
+        arr = (C.c_char_p * self.M)(*[n if isinstance(n, bytes) else str(n).encode() for n in names])
+        self.L.gsb_set_marker_names(self.d, arr)
+
+    def blocks_from_file(self, path):
+        return Blocks(self.L, self.L.gsb_load_blocks(self.d, path if isinstance(path, bytes) else str(path).encode()))
 
     def optimal_haplotype(self, eff_id, na=b"-"):
         buf = C.create_string_buffer(self.M + 1)

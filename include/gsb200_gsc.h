@@ -138,6 +138,11 @@ unsigned int gsb_get_group_bvs(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID 
 gsb_DecimalMatrix gsb_calculate_allele_counts(gsb_SimData* d, gsb_GroupNum group, char allele);
 gsb_DecimalMatrix gsb_calculate_local_bvs(gsb_SimData* d, gsb_GroupNum group, gsb_MarkerBlocks b, gsb_EffectID effID);
 gsb_MarkerBlocks gsb_create_evenlength_blocks_each_chr(const gsb_SimData* d, gsb_MapID mapid, unsigned int n);
+/* gsc_load_blocks (core.c:9850-9918): one block per row after the header row, `chrom pos name class m1;m2;...`;
+ * names the genome does not know are skipped.  Needs the marker names (the reference keeps them in its
+ * KnownGenome; here the loader hands them over once): names[n_markers], copied. */
+void gsb_set_marker_names(gsb_SimData* d, const char* const* names);
+gsb_MarkerBlocks gsb_load_blocks(const gsb_SimData* d, const char* block_file);
 /* optimal haplotypes / breeding values (core.c:10112-10392); opt_haplotype needs n_markers + 1 chars */
 void gsb_calculate_optimal_haplotype(const gsb_SimData* d, gsb_EffectID effID, char symbol_na, char* opt_haplotype);
 double gsb_calculate_optimal_bv(const gsb_SimData* d, gsb_EffectID effID);

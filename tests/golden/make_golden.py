@@ -53,6 +53,12 @@ def helper():
     blockings["custom"] = dict(offsets=off, markers=mk,
                                local=[r.calculate_local_bvs(g, b, e).tolist(), r.calculate_local_bvs(g, b, e2).tolist()])
     b.free()
+    # gsc_load_blocks on the reference's own block file (test-calculators.R:104-109)
+    b = r.blocks_from_file(T + "helper_blocks.txt")
+    off, mk = b.export()
+    blockings["file"] = dict(offsets=off.tolist(), markers=mk.tolist(), text=open(T + "helper_blocks.txt").read(),
+                             local=[r.calculate_local_bvs(g, b, e).tolist(), r.calculate_local_bvs(g, b, e2).tolist()])
+    b.free()
     out["blockings"] = blockings
     # centred effects (core.c:9603-9612, 10075-10076)
     r.set_centres(e, [0.25, -0.5, 0.125])

@@ -487,3 +487,50 @@ def test_optimal_possible_matches_the_reference(tmp_path):
     assert r.optimal_haplotype(e) == s.optimal_haplotype(1)
     np.testing.assert_allclose([s.optimal_bv(1), s.minimal_bv(1)], [r.optimal_bv(e), r.minimal_bv(e)], rtol=1e-12)
     r.close(); s.close()
+
+
+def test_blocks_from_file(helper, tmp_path):
+    """gsc_load_blocks (core.c:9850-9918): the reference's own block file (golden), then a file with
+    unknown names, empty blocks and a name without its closing semicolon against the unmodified
+    reference; local GEBVs on the loaded blocks.  (A blank line inside the file leaves the reference
+    with an uninitialised trailing block, core.c:9855-9858 — not a case to agree on.)"""
+    ds = datasets.from_jsonable(helper["dataset"])
+    s = engine_from(ds)
+    blk = helper["blockings"]["file"]
+    f = tmp_path / "blocks.txt"
+    f.write_text(blk["text"])
+    b = s.blocks_from_file(str(f))
+    off, mk = b.export()
+    assert off.tolist() == blk["offsets"] and mk.tolist() == blk["markers"]
+    for e in (0, 1):
+        np.testing.assert_allclose(s.calculate_local_bvs(1, b, e + 1), np.array(blk["local"][e]), rtol=RTOL, atol=1e-12)
+    b.free()
+    s.close()
+
+    ds = datasets.synthetic(10, 400, 4, 110.0, seed=77, spacing="random")
+    names = ds["marker_names"]
+    rng = np.random.default_rng(8)
+    lines = ["Chrom\tPos\tName\tClass\tMarkers"]
+    for k in range(9):
+        picks = [names[i] for i in sorted(rng.choice(400, size=int(rng.integers(0, 40)), replace=False))]
+        if k == 3:
+            picks = picks[:5] + ["nosuchmarker", "m"] + picks[5:]
+        text = "".join(p + ";" for p in picks)
+        if k == 5:
+            text += names[7]                                  # no closing semicolon: not a member
+        lines.append("%d\t%.1f\tb%06d\tb\t%s" % (k % 4 + 1, 3.5 * k, k, text))
+    f2 = tmp_path / "blocks2.txt"
+    f2.write_text("\n".join(lines) + "\n")
+    gf, mf, ef = datasets.write_files(ds, str(tmp_path))
+    r = ref.RefSim()
+    g, m, e = r.load(gf, mf, ef)
+    rb = r.blocks_from_file(str(f2))
+    want_off, want_mk = rb.export()
+    s = engine_from(ds)
+    b = s.blocks_from_file(str(f2))
+    off, mk = b.export()
+    assert off.tolist() == want_off.tolist() and mk.tolist() == want_mk.tolist()
+    bv_close(s.calculate_local_bvs(1, b, 1), r.calculate_local_bvs(g, rb, e), scale=1.0)
+    assert s.blocks_from_file(str(tmp_path / "absent.txt")).export()[0].tolist() == [0]
+    rb.free(); b.free()
+    r.close(); s.close()
