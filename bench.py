@@ -396,7 +396,7 @@ def engine_arm(a):
     out["fused_cross_gebv"] = {"ms_per_step": fused_ms, "value": world * n / (fused_ms * 1e-3), "unit": UNIT,
                                "max_rel_diff_vs_two_pass": fused_err,
                                "api": "gsb200_cross_gebv_dev: same offspring, GEBVs from the crossover plan + per-parent prefix "
-                                      "tables (1000-row pool rebuilt every step); NOT the headline value, which keeps the two kernels"}
+                                      "tables (%d-row pool rebuilt every step); NOT the headline value, which keeps the two kernels" % F}
     if world > 1:
         out["per_rank_kernel_ms"] = per_rank
         out["collectives"] = {"pool_broadcast_ms": float(np.mean(kernel_ms["broadcast"])), "gebv_allgather_ms": float(np.mean(kernel_ms["allgather"])),
