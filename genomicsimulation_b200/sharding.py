@@ -119,9 +119,14 @@ class ShardedPopulation:
     def next_generation(self, pool_rows, n_offspring, seed, generation, map_index=0):
         """Every rank makes its own index range of the next generation from the replicated pool."""
         lo, hi = offspring_range(n_offspring, self.rank, self.world)
-        a, b = draw_pairs(len(pool_rows), n_offspring, seed * 1000003 + generation, lo, hi)
         pool_rows = np.asarray(pool_rows)
-        rows = self.backend.cross(pool_rows[a], pool_rows[b], map_index, seed=seed, stream=generation, first_unit=lo)
+        if hasattr(self.backend, "cross_random"):
+            # pairs drawn on the device, indexed by the global offspring number: nothing but the pool's row
+            # list goes up, and the generation does not depend on how it is sharded
+            rows = self.backend.cross_random(pool_rows, hi - lo, map_index, seed=seed, stream=generation, first_unit=lo)
+        else:
+            a, b = draw_pairs(len(pool_rows), n_offspring, seed * 1000003 + generation, lo, hi)
+            rows = self.backend.cross(pool_rows[a], pool_rows[b], map_index, seed=seed, stream=generation, first_unit=lo)
         return ShardedPopulation(self.backend, n_offspring, rows, self.group)
 
 
@@ -183,6 +188,20 @@ class EngineBackend:
             self._check(self.E.gsb200_store_scatter_rows_dev(self.ctx, len(rows), d_rows.data_ptr(), packed.data_ptr()))
             self._check(self.E.gsb200_synchronize(self.ctx))
         return rows
+
+    def cross_random(self, pool_rows, n, map_index, seed, stream, first_unit):
+        """n random crosses among `pool_rows` (distinct parents, the reference's pick rule), pairs drawn on
+        the device from the stream position of global offspring `first_unit` onwards."""
+        from ._lib import Draws
+        out = self._take(n)
+        if n == 0:
+            return out
+        pool = np.ascontiguousarray(pool_rows, dtype=np.uint32)
+        contiguous = n == 1 or bool(np.all(np.diff(out.astype(np.int64)) == 1))
+        dr = Draws(mode=0, seed=seed, stream=stream, first_unit=first_unit)
+        self._check(self.E.gsb200_cross_random_pairs(self.ctx, n, 1, pool.ctypes.data, len(pool), None, 0, map_index, map_index,
+                                                     None if contiguous else out.ctypes.data, int(out[0]), C.byref(dr), None, None))
+        return out
 
     def cross(self, p1_rows, p2_rows, map_index, seed, stream, first_unit):
         from ._lib import Draws
