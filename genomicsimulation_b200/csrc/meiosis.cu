@@ -1095,8 +1095,12 @@ int gsb200_cross_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1
     // one table entry per 8 markers while all tables together stay well inside L2, per 32 markers otherwise
     const uint32_t per_word = (size_t) n_pool * (4 * (size_t) ctx->plane_words + 2) * sizeof(long long) <= ((size_t) 64 << 20) ? 4u : 1u;
     const size_t tab_bytes = (size_t) n_pool * (per_word * (size_t) ctx->plane_words + 2) * sizeof(long long);
+    // the fused kernel ranks the toggles of a gamete with 7-bit indexes: maps that expect anywhere near 128
+    // toggles per gamete (crossovers + chromosome boundaries) take the two passes
+    const double ls = std::max(m1->lambda_sum, m2->lambda_sum);
+    const bool few_toggles = ls + 6.0 * std::sqrt(ls) + (double) std::max(m1->n_chr, m2->n_chr) <= 120.0;
     const bool fused = ctx->planes == 1 && m1->flat && m2->flat && d_pool_rows && n_pool > 0 && tab_bytes <= ((size_t) 2 << 30)
-                       && ctx->n_markers < (1u << 25) && draws->mode == GSB200_DRAWS_PHILOX;
+                       && ctx->n_markers < (1u << 25) && few_toggles && draws->mode == GSB200_DRAWS_PHILOX;
     if (!fused) {
         GSB_TRY(cross_impl(ctx, n, d_parent1_rows, d_parent2_rows, map1, map2, d_out_rows, draws, false, what));
         return gsb200_gebv_dev(ctx, n, d_out_rows, eff_index, d_bv);
