@@ -93,7 +93,25 @@ ENGINE_SYMBOLS = {
     "gsb200_allele_presence": (I32, [VP, U32, VP, VP]),
     "gsb200_top_n": (I32, [VP, U32, VP, U32, I32, VP]),
     "gsb200_kernel_launches": (U64, [VP]),
+    "gsb200_shard_range": (None, [U64, U32, U32, C.POINTER(U64), C.POINTER(U64)]),
+    "gsb200_shard_create": (I32, [VP, U32, U32, U64, U32, C.POINTER(VP)]),
+    "gsb200_shard_destroy": (None, [VP]),
+    "gsb200_shard_handle": (I32, [VP, VP]),
+    "gsb200_shard_connect": (I32, [VP, VP]),
+    "gsb200_shard_select": (I32, [VP, U32, VP, VP, U64, U32, U32, I32]),
+    "gsb200_shard_select_dev": (I32, [VP, U32, VP, VP, U64, U32, U32, I32]),
+    "gsb200_shard_cross": (I32, [VP, U32, U32, VP, C.POINTER(Draws), VP, VP]),
+    "gsb200_shard_cross_dev": (I32, [VP, U32, U32, VP, U32, C.POINTER(Draws), VP]),
+    "gsb200_shard_selected": (I32, [VP, VP, VP, VP]),
+    "gsb200_shard_generation_size": (U64, [VP]),
+    "gsb200_shard_pool_size": (U32, [VP]),
+    "gsb200_shard_pool_device_ptr": (VP, [VP]),
+    "gsb200_shard_set_timing": (I32, [VP, I32]),
+    "gsb200_shard_epoch": (U32, [VP]),
+    "gsb200_shard_phase_ms": (I32, [VP, U32, VP]),
+    "gsb200_shard_status": (I32, [VP]),
 }
+SHARD_HANDLE_BYTES = 128
 
 UNIF_FN = C.CFUNCTYPE(C.c_double)
 RPOIS_FN = C.CFUNCTYPE(C.c_double, C.c_double)
@@ -146,6 +164,11 @@ HOST_SYMBOLS = {
     "gsb_split_by_bv": (UINT, [VP, UINT, UINT, UINT, C.c_bool]),
     "gsb_delete_dmatrix": (None, [C.POINTER(DecimalMatrix)]),
     "gsb_delete_markerblocks": (None, [C.POINTER(MarkerBlocks)]),
+    "gsb_shard_init": (I32, [VP, UINT, UINT, C.c_ulonglong, UINT]),
+    "gsb_shard_handle": (I32, [VP, VP]),
+    "gsb_shard_connect": (I32, [VP, VP]),
+    "gsb_shard_select_and_cross": (UINT, [VP, UINT, C.c_ulonglong, UINT, UINT, C.c_bool, C.c_ulonglong, UINT, GenOptions]),
+    "gsb_shard_last_selection": (UINT, [VP, C.c_ulonglong, VP, UINT, VP]),
 }
 
 

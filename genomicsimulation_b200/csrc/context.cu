@@ -140,6 +140,7 @@ void gsb200_destroy(gsb200_ctx* ctx) {
     for (auto& s : ctx->s_chain) s.release();
     for (auto& s : ctx->s_bv) s.release();
     ctx->s_null.release();
+    ctx->s_select.release();
     ctx->local_sched.d_steps.release();
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->d_store) cudaFree(ctx->d_store);

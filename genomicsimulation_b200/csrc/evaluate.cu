@@ -1,5 +1,5 @@
 // evaluate.cu — genomic evaluation on the bit-packed store (K5 GEBV, K6 local GEBV,
-// K7 allele counts, K9 ranking).
+// K7 allele counts; K9 ranking is select.cu).
 //
 // The reference compares allele CHARS against the effect table per marker
 // (core.c:9587-9597, 10019-10031).  Here the per-marker symbol dictionary turns an effect set
@@ -18,7 +18,6 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
-#include <cub/cub.cuh>
 
 using namespace gsb;
 
@@ -460,19 +459,6 @@ __global__ void presence_kernel(const uint32_t* __restrict__ store, uint64_t row
         }
         if (acc) atomicOr(&present[(size_t) c * plane_words + w], acc);
     }
-}
-
-// ------------------------------------------------------------------ ranking
-// order-preserving map of fp64 to u64, inverted when the highest value is the best, so that an
-// ascending STABLE sort yields best-first with ties in input order.
-__global__ void rank_keys_kernel(const double* __restrict__ values, uint32_t n, int low_is_best,
-                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ pos) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t k = (uint64_t) __double_as_longlong(values[i]);
-    k = (k >> 63) ? ~k : (k | 0x8000000000000000ull);
-    keys[i] = low_is_best ? k : ~k;
-    pos[i] = i;
 }
 
 template <typename T>
@@ -944,25 +930,14 @@ int gsb200_top_n(gsb200_ctx* ctx, uint32_t n, const double* values, uint32_t top
     GSB_REQUIRE(values && out_positions, GSB200_ERR_ARG, "%s: null array", what);
     GSB_REQUIRE(top_n <= n, GSB200_ERR_ARG, "%s: top_n %u exceeds n %u", what, top_n, n);
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
-    // layout of s_eval[3]: values | keys in | keys out | pos in | pos out
-    const size_t bytes = (size_t) n * (8 + 8 + 8 + 4 + 4);
-    GSB_TRY(ctx->s_eval[3].ensure(bytes));
-    char* base = (char*) ctx->s_eval[3].ptr;
-    double* d_val = (double*) base;
-    uint64_t* d_kin = (uint64_t*) (base + (size_t) n * 8);
-    uint64_t* d_kout = (uint64_t*) (base + (size_t) n * 16);
-    uint32_t* d_pin = (uint32_t*) (base + (size_t) n * 24);
-    uint32_t* d_pout = (uint32_t*) (base + (size_t) n * 28);
+    // s_eval[3]: values | selected positions
+    GSB_TRY(ctx->s_eval[3].ensure((size_t) n * 8 + (size_t) top_n * 4));
+    GSB_TRY(ctx->s_select.ensure(select_scratch_bytes(n)));
+    double* d_val = (double*) ctx->s_eval[3].ptr;
+    uint32_t* d_sel = (uint32_t*) ((char*) ctx->s_eval[3].ptr + (size_t) n * 8);
     GSB_CUDA_TRY(cudaMemcpyAsync(d_val, values, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rank_keys_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_val, n, low_is_best, d_kin, d_pin);
-    ++ctx->launches;
-    GSB_CUDA_TRY(cudaGetLastError());
-    size_t tmp = 0;
-    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_kin, d_kout, d_pin, d_pout, (int) n, 0, 64, ctx->stream));
-    GSB_TRY(ctx->s_eval[0].ensure(tmp));
-    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->s_eval[0].ptr, tmp, d_kin, d_kout, d_pin, d_pout, (int) n, 0, 64, ctx->stream));
-    ++ctx->launches;
-    GSB_CUDA_TRY(cudaMemcpyAsync(out_positions, d_pout, (size_t) top_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_TRY(select_top_n(ctx, d_val, n, top_n, low_is_best, ctx->s_select.ptr, d_sel, 0, n));
+    GSB_CUDA_TRY(cudaMemcpyAsync(out_positions, d_sel, (size_t) top_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return GSB200_OK;
 }

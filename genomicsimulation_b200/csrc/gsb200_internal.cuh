@@ -117,6 +117,15 @@ struct DeviceEffects {
     void release();
 };
 
+// State of one radix selection (select.cu), left on the device.
+struct SelectState {
+    unsigned long long prefix;     // key bits decided so far; after the last pass: the key T of the top_n-th best
+    uint32_t remaining;            // still to take among the keys matching the prefix; after the last pass: ties at T taken
+    uint32_t done_blocks;          // last-block-done counter of the pass in flight
+    uint32_t own_lo, own_hi;       // slice [own_lo, own_hi) of the selection that lies in [own_lo_pos, own_hi_pos)
+    uint32_t pad[2];
+};
+
 // Step schedule of the tensor-path local GEBV for the block definition last used.
 struct LocalSchedule {
     bool valid = false, usable = false;
@@ -165,6 +174,7 @@ struct gsb200_ctx {
     gsb::Scratch s_chain[2];        // ping-pong rows of chained selfing
     gsb::Scratch s_bv[3];           // fused cross + GEBV: parent prefix tables, row -> table slot, per-offspring sums
     gsb::LocalSchedule local_sched;
+    gsb::Scratch s_select;          // radix selection: state, histograms, tile counts (select.cu)
     gsb::Scratch s_null;            // per marker: the code that decodes to '\0' (uncovered markers)
     uint64_t null_built_for = ~0ull;
 
@@ -180,4 +190,14 @@ void build_tc5_fragments(const std::vector<double>& delta, uint32_t n_markers, u
 int gebv_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, const uint32_t* d_frag, unsigned long long* d_digits);
 int upload_u32(gsb200_ctx* ctx, Scratch& s, const uint32_t* host, size_t n, uint32_t** out);
 int check_rows(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const char* what);
+// select.cu
+size_t select_scratch_bytes(uint32_t n);
+int select_top_n(gsb200_ctx* ctx, const double* d_values, uint32_t n, uint32_t top_n, int low_is_best, void* scratch,
+                 uint32_t* d_sel, uint32_t own_lo_pos, uint32_t own_hi_pos);
+// meiosis.cu: n random crosses among the n_pool rows of `pool_base` (packed rows in store layout, e.g. a
+// shard's exchanged parent pool), pairs drawn on the device from the stream position draws->first_unit on;
+// d_picks (device, 2n, may be null) receives the pool positions of both parents.  Asynchronous.
+int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_pool, uint32_t n, uint32_t map,
+                      const uint32_t* d_out_rows, uint32_t first_out_row, const gsb200_draws* draws, uint32_t* d_picks,
+                      const char* what);
 }  // namespace gsb

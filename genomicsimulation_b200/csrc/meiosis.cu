@@ -726,11 +726,11 @@ __global__ void random_pairs_kernel(uint32_t n_crosses, uint32_t family_size, co
         b = (uint32_t) rint(u01(r.x, r.y) * (double) (n2 - 1));
         if (b == a) b = (uint32_t) rint(u01(r.z, r.w) * (double) (n2 - 1));
     }
-    const uint32_t ra = members1[a], rb = members2[b];
+    const uint32_t ra = members1 ? members1[a] : a, rb = members2 ? members2[b] : b;    // null: the candidates are rows 0 .. n - 1
     for (uint32_t f = 0; f < family_size; ++f) {
         const uint64_t o = (uint64_t) i * family_size + f;
         p1_rows[o] = ra; p2_rows[o] = rb;
-        picked1[o] = a; picked2[o] = b;
+        if (picked1) { picked1[o] = a; picked2[o] = b; }
         if (out_rows) out_rows[o] = first_out_row + (uint32_t) o;
     }
 }
@@ -1020,7 +1020,8 @@ int make_draw_view(const gsb200_draws* d, DrawView* v, const char* what) {
 struct FusedBv { const long long* tab; const uint32_t* slot; const long long* q; unsigned long long* acc; uint32_t shift; };
 
 int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t* d_p2, uint32_t map1, uint32_t map2,
-               const uint32_t* d_out, const gsb200_draws* draws, bool may_sync, const char* what, const FusedBv* bv = nullptr) {
+               const uint32_t* d_out, const gsb200_draws* draws, bool may_sync, const char* what, const FusedBv* bv = nullptr,
+               const uint32_t* src_base = nullptr /* rows the parents are read from; null: the store */) {
     const DeviceMap *m1, *m2;
     GSB_TRY(get_map(ctx, map1, &m1, what));
     GSB_TRY(get_map(ctx, map2, &m2, what));
@@ -1028,7 +1029,7 @@ int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t
     GSB_TRY(prepare_uncovered(ctx, *m2));
     Batch b;
     b.what = what; b.n_units = n;
-    b.src_base = ctx->d_store; b.d_src0 = d_p1; b.d_src1 = d_p2; b.dst_base = ctx->d_store; b.d_dst = d_out;
+    b.src_base = src_base ? src_base : ctx->d_store; b.d_src0 = d_p1; b.d_src1 = d_p2; b.dst_base = ctx->d_store; b.d_dst = d_out;
     b.map0 = m1; b.map1 = m2; b.gametes_per_unit = 2; b.doubled = 0; b.tape_xcap = 0;
     if (bv) { b.bv_tab = bv->tab; b.bv_slot = bv->slot; b.bv_q = bv->q; b.bv_acc = bv->acc; b.bv_shift = bv->shift; }
     GSB_TRY(make_draw_view(draws, &b.draws, what));
@@ -1047,6 +1048,31 @@ int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t
 }
 
 }  // namespace
+
+namespace gsb {
+
+int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_pool, uint32_t n, uint32_t map,
+                      const uint32_t* d_out_rows, uint32_t first_out_row, const gsb200_draws* draws, uint32_t* d_picks,
+                      const char* what) {
+    if (n == 0) return GSB200_OK;
+    GSB_REQUIRE(n_pool >= 2, GSB200_ERR_ARG, "%s: a pool of %u cannot be crossed at random", what, n_pool);
+    GSB_REQUIRE(draws && draws->mode == GSB200_DRAWS_PHILOX, GSB200_ERR_ARG, "%s: needs PHILOX draws", what);
+    GSB_REQUIRE(n < (1u << 31), GSB200_ERR_ARG, "%s: too many offspring in one call", what);
+    GSB_REQUIRE(d_out_rows || (uint64_t) first_out_row + n <= ctx->capacity, GSB200_ERR_ARG, "%s: offspring rows beyond the store capacity", what);
+    // s_rows[3]: parent 1 | parent 2 | offspring rows (when they are a contiguous run)
+    GSB_TRY(ctx->s_rows[3].ensure((size_t) 4 * n * sizeof(uint32_t)));
+    uint32_t* d_p1 = (uint32_t*) ctx->s_rows[3].ptr;
+    uint32_t *d_p2 = d_p1 + n, *d_run = d_p2 + n;
+    DrawView dv;
+    GSB_TRY(make_draw_view(draws, &dv, what));
+    random_pairs_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, 1, nullptr, n_pool, nullptr, n_pool, 1u, dv, first_out_row, d_p1, d_p2,
+                                                                   d_picks, d_picks ? d_picks + n : nullptr, d_out_rows ? nullptr : d_run);
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    return cross_impl(ctx, n, d_p1, d_p2, map, map, d_out_rows ? d_out_rows : d_run, draws, false, what, nullptr, pool_base);
+}
+
+}  // namespace gsb
 
 extern "C" {
 

@@ -1,0 +1,220 @@
+// select.cu — K9: the ranking step of gsc_split_by_bv (core.c:9489-9508) as a radix SELECT.
+//
+// The reference sorts the whole group by breeding value (qsort of N pointers, core.c:9496) to take
+// the first top_n.  Selection needs the SET, not the order: six histogram passes over the fp64
+// keys (11 + 11 + 11 + 11 + 11 + 9 bits, most significant first) find the key T of the top_n-th
+// best individual and how many of the individuals tied at T still fit; one more sweep writes the
+// selected positions in ascending order — everything strictly better than T plus the first ties
+// by position (the reference leaves tie order to qsort, core.c:1305-1306; here the rule is
+// deterministic, so that every GPU of a sharded generation selects the same set).
+//
+// Each pass is ONE kernel: blocks histogram their slice in shared memory, add it to the global
+// histogram, and the last block to finish scans the 2048 bins and extends the key prefix.  The
+// values stay where they are (8 bytes per individual, L2-resident at any realistic N).
+#include "gsb200_internal.cuh"
+
+#include <algorithm>
+
+namespace gsb {
+
+namespace {
+
+constexpr int kPasses = 6;
+constexpr int kBins = 2048;
+constexpr int kHistThreads = 256;
+constexpr int kItems = 8;                          // consecutive values per thread in the sweeps
+constexpr int kSweepThreads = 256;
+constexpr uint32_t kTile = kItems * kSweepThreads;
+
+__host__ __device__ constexpr int pass_width(int pass) { return pass < 5 ? 11 : 9; }
+__host__ __device__ constexpr int pass_shift(int pass) { return pass < 5 ? 64 - 11 * (pass + 1) : 0; }
+
+// order-preserving map of fp64 to u64; the BEST value gets the SMALLEST key
+__device__ __forceinline__ unsigned long long rank_key(double v, int low_is_best) {
+    unsigned long long k = (unsigned long long) __double_as_longlong(v);
+    k = (k >> 63) ? ~k : (k | 0x8000000000000000ull);
+    return low_is_best ? k : ~k;
+}
+
+__global__ void __launch_bounds__(kHistThreads) select_hist_kernel(const double* __restrict__ values, uint32_t n, int low_is_best,
+                                                                   int pass, uint32_t top_n, SelectState* state,
+                                                                   uint32_t* __restrict__ hist /* [kBins], zeroed */,
+                                                                   uint32_t own_lo_init) {
+    __shared__ uint32_t s_hist[kBins];
+    __shared__ uint32_t s_scan[kHistThreads];
+    __shared__ bool s_last;
+    const int width = pass_width(pass), shift = pass_shift(pass);
+    const uint32_t bins = 1u << width;
+    for (uint32_t b = threadIdx.x; b < bins; b += kHistThreads) s_hist[b] = 0;
+    __syncthreads();
+    const unsigned long long prefix = pass ? state->prefix : 0ull;
+    for (uint32_t i = blockIdx.x * kHistThreads + threadIdx.x; i < n; i += gridDim.x * kHistThreads) {
+        const unsigned long long k = rank_key(values[i], low_is_best);
+        if (pass == 0 || (k >> (shift + width)) == prefix) atomicAdd(&s_hist[(uint32_t) (k >> shift) & (bins - 1)], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < bins; b += kHistThreads) if (s_hist[b]) atomicAdd(&hist[b], s_hist[b]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&state->done_blocks, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    // the last block: find the bin holding the `remaining`-th best key among those matching the prefix
+    __threadfence();
+    const uint32_t remaining = pass ? state->remaining : top_n;
+    const uint32_t per = bins / kHistThreads;                  // 8 or 2 consecutive bins per thread
+    uint32_t mine = 0;
+    for (uint32_t j = 0; j < per; ++j) {
+        const uint32_t v = __ldcg(&hist[threadIdx.x * per + j]);
+        s_hist[threadIdx.x * per + j] = v;
+        mine += v;
+    }
+    s_scan[threadIdx.x] = mine;
+    __syncthreads();
+    for (int o = 1; o < kHistThreads; o <<= 1) {               // inclusive scan over the threads' sums
+        const uint32_t v = (int) threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_scan[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const uint32_t incl = s_scan[threadIdx.x], excl = incl - mine;
+    if (excl < remaining && remaining <= incl) {               // exactly one thread
+        uint32_t before = excl;
+        for (uint32_t j = 0; j < per; ++j) {
+            const uint32_t v = s_hist[threadIdx.x * per + j];
+            if (remaining <= before + v) {
+                state->prefix = (prefix << width) | (threadIdx.x * per + j);
+                state->remaining = remaining - before;
+                break;
+            }
+            before += v;
+        }
+        state->done_blocks = 0;
+        if (pass == 0) { state->own_lo = own_lo_init; state->own_hi = top_n; }
+    }
+}
+
+// per tile of kTile consecutive positions: how many keys are better than T, how many equal it
+__global__ void __launch_bounds__(kSweepThreads) select_count_kernel(const double* __restrict__ values, uint32_t n, int low_is_best,
+                                                                     const SelectState* __restrict__ state, uint2* __restrict__ tile_counts) {
+    __shared__ uint32_t s_less[kSweepThreads / 32], s_eq[kSweepThreads / 32];
+    const unsigned long long T = state->prefix;
+    const uint32_t base = blockIdx.x * kTile + threadIdx.x * kItems;
+    uint32_t less = 0, eq = 0;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        if (base + j < n) {
+            const unsigned long long k = rank_key(values[base + j], low_is_best);
+            less += k < T;
+            eq += k == T;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { less += __shfl_xor_sync(0xffffffffu, less, o); eq += __shfl_xor_sync(0xffffffffu, eq, o); }
+    if ((threadIdx.x & 31) == 0) { s_less[threadIdx.x >> 5] = less; s_eq[threadIdx.x >> 5] = eq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a = 0, b = 0;
+        for (int w = 0; w < kSweepThreads / 32; ++w) { a += s_less[w]; b += s_eq[w]; }
+        tile_counts[blockIdx.x] = make_uint2(a, b);
+    }
+}
+
+// exclusive scan of the tile counts, in place, one block
+__global__ void __launch_bounds__(1024) select_scan_kernel(uint2* __restrict__ tile_counts, uint32_t n_tiles) {
+    __shared__ uint2 s_warp[32];
+    __shared__ uint2 s_carry;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = make_uint2(0, 0);
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const uint32_t t = t0 + threadIdx.x;
+        const uint2 v = t < n_tiles ? tile_counts[t] : make_uint2(0, 0);
+        uint2 incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, incl.x, o), b = __shfl_up_sync(0xffffffffu, incl.y, o);
+            if ((int) lane >= o) { incl.x += a; incl.y += b; }
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint2 before = s_carry;
+        for (uint32_t w = 0; w < warp; ++w) { before.x += s_warp[w].x; before.y += s_warp[w].y; }
+        if (t < n_tiles) tile_counts[t] = make_uint2(before.x + incl.x - v.x, before.y + incl.y - v.y);
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = make_uint2(before.x + incl.x, before.y + incl.y);
+        __syncthreads();
+    }
+}
+
+// selected positions, ascending: key < T, or key == T and fewer than `remaining` ties before it
+__global__ void __launch_bounds__(kSweepThreads) select_scatter_kernel(const double* __restrict__ values, uint32_t n, int low_is_best,
+                                                                       SelectState* __restrict__ state, const uint2* __restrict__ tile_before,
+                                                                       uint32_t* __restrict__ sel, uint32_t own_lo_pos, uint32_t own_hi_pos) {
+    __shared__ uint2 s_warp[kSweepThreads / 32];
+    const unsigned long long T = state->prefix;
+    const uint32_t ties = state->remaining;
+    const uint32_t base = blockIdx.x * kTile + threadIdx.x * kItems;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long key[kItems];
+    uint32_t less = 0, eq = 0;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        key[j] = base + j < n ? rank_key(values[base + j], low_is_best) : ~0ull;
+        if (base + j < n) { less += key[j] < T; eq += key[j] == T; }
+    }
+    uint2 incl = make_uint2(less, eq);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, incl.x, o), b = __shfl_up_sync(0xffffffffu, incl.y, o);
+        if ((int) lane >= o) { incl.x += a; incl.y += b; }
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint2 before = tile_before[blockIdx.x];
+    for (uint32_t w = 0; w < warp; ++w) { before.x += s_warp[w].x; before.y += s_warp[w].y; }
+    uint32_t lb = before.x + incl.x - less, eb = before.y + incl.y - eq;      // better / tied keys at positions before base
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const uint32_t i = base + j;
+        if (i >= n) break;
+        const uint32_t pos = lb + min(eb, ties);                // selected individuals before position i
+        if (i == own_lo_pos) state->own_lo = pos;
+        if (i == own_hi_pos) state->own_hi = pos;
+        if (key[j] < T) { sel[pos] = i; ++lb; }
+        else if (key[j] == T) { if (eb < ties) sel[pos] = i; ++eb; }
+    }
+}
+
+}  // namespace
+
+size_t select_scratch_bytes(uint32_t n) {
+    const size_t tiles = ((size_t) n + kTile - 1) / kTile;
+    return sizeof(SelectState) + (size_t) kPasses * kBins * sizeof(uint32_t) + tiles * sizeof(uint2) + 256;
+}
+
+// d_sel[0 .. top_n) <- positions (0 .. n-1) of the top_n best of d_values, ascending; `scratch` holds
+// select_scratch_bytes(n) bytes and starts with the SelectState (left on the device: own_lo / own_hi are
+// the ranks, within the selection, of positions own_lo_pos / own_hi_pos — the slice of the selection a
+// shard owning [own_lo_pos, own_hi_pos) contributes).  Asynchronous on the context stream.
+int select_top_n(gsb200_ctx* ctx, const double* d_values, uint32_t n, uint32_t top_n, int low_is_best, void* scratch,
+                 uint32_t* d_sel, uint32_t own_lo_pos, uint32_t own_hi_pos) {
+    GSB_REQUIRE(top_n >= 1 && top_n <= n, GSB200_ERR_ARG, "select: top_n %u out of range for %u values", top_n, n);
+    SelectState* state = (SelectState*) scratch;
+    uint32_t* hist = (uint32_t*) ((char*) scratch + sizeof(SelectState));
+    uint2* tiles = (uint2*) (hist + (size_t) kPasses * kBins);
+    const uint32_t n_tiles = (n + kTile - 1) / kTile;
+    GSB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(SelectState) + (size_t) kPasses * kBins * sizeof(uint32_t), ctx->stream));
+    const uint32_t grid = (uint32_t) std::min<uint64_t>(((uint64_t) n + kHistThreads * 4 - 1) / (kHistThreads * 4), (uint64_t) ctx->sm_count * 8);
+    for (int pass = 0; pass < kPasses; ++pass)
+        select_hist_kernel<<<std::max(grid, 1u), kHistThreads, 0, ctx->stream>>>(d_values, n, low_is_best, pass, top_n, state,
+                                                                                hist + (size_t) pass * kBins, own_lo_pos >= n ? top_n : 0u);
+    select_count_kernel<<<n_tiles, kSweepThreads, 0, ctx->stream>>>(d_values, n, low_is_best, state, tiles);
+    select_scan_kernel<<<1, 1024, 0, ctx->stream>>>(tiles, n_tiles);
+    select_scatter_kernel<<<n_tiles, kSweepThreads, 0, ctx->stream>>>(d_values, n, low_is_best, state, tiles, d_sel, own_lo_pos, own_hi_pos);
+    ctx->launches += kPasses + 3;
+    GSB_CUDA_TRY(cudaGetLastError());
+    return GSB200_OK;
+}
+
+}  // namespace gsb

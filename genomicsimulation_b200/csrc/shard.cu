@@ -1,0 +1,451 @@
+// shard.cu — one generation of recurrent selection sharded over the GPUs of a box.
+//
+// One process (or context) per GPU holds a contiguous index range of the generation.  Per
+// generation, all on the context stream and with NO host synchronisation:
+//
+//   select:  GEBV of the local individuals (evaluate.cu)            gsc_calculate_bvs   core.c:9536
+//            -> pushed into every peer's copy of the generation's GEBV vector (P2P stores over
+//               NVLink + a release flag per rank)                    (the "all-gather")
+//            -> replicated radix selection of the global top_n (select.cu): every rank computes
+//               the same ascending list of selected global indexes   gsc_split_by_bv     core.c:9463-9517
+//            -> each rank copies the selected rows it owns out of its packed store straight into
+//               every peer's parent-pool buffer, at their rank in the selection (the "pool
+//               broadcast"), then raises its pool flag
+//   cross:   waits for every rank's pool flag, draws random pairs over the pool on the device
+//            (pick rule of core.c:8556-8581, Philox position = GLOBAL offspring number) and
+//            splices this rank's range of the next generation (meiosis.cu)  gsc_make_random_crosses core.c:8483
+//
+// The exchange buffers of a rank are one cudaMalloc slab, opened by its peers through CUDA IPC
+// (or used directly when two shards live in one process).  Why not NCCL here: the number of pool
+// rows a rank contributes is known only on the device (it depends on the selection), so an
+// all-gather-v would need a host round trip per generation; the push kernels need none, fuse the
+// row gather with the transfer, and are latency-bound at ~7 us per flag hop instead of ~60 us per
+// small NCCL collective (profiles/r2_ipc_probe_2gpu.txt: 642 GB/s per direction for 128 MB).
+//
+// Buffer reuse is safe without extra barriers: a peer can only push generation g+1's GEBVs after its
+// cross(g), which waited for MY pool flag of g, which I raise after my selection of g has read the
+// GEBV vector; and it can only push generation g+1's pool rows after its selection of g+1, which
+// waited for MY GEBV flag of g+1, which I raise after my cross(g) has read the pool.
+#include "gsb200_internal.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <unistd.h>
+
+using namespace gsb;
+
+namespace {
+
+constexpr uint32_t kMaxWorld = 16;
+constexpr uint32_t kHandleMagic = 0x67736232u;
+constexpr uint32_t kTimingRing = 256, kTimingEvents = 7;
+constexpr long long kWaitTimeoutCycles = 40000000000ll;      // ~20 s at 1.9 GHz: a peer that never shows up
+
+struct Peers { char* base[kMaxWorld]; };
+
+struct ShardHandle {                 // what gsb200_shard_handle exports (GSB200_SHARD_HANDLE_BYTES)
+    uint32_t magic, rank, world, device;
+    int32_t pid;
+    uint32_t max_pool;
+    uint64_t slab_bytes, row_bytes, max_total;
+    void* raw;                       // the slab's address in its owner's process
+    cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(ShardHandle) <= GSB200_SHARD_HANDLE_BYTES, "shard handle too large");
+
+// Layout of a slab.  flags[0][r]: epoch of rank r's GEBVs present here; flags[1][r]: of its pool rows.
+constexpr size_t kOffFlags = 0, kOffBv = 512;
+
+__device__ __forceinline__ void raise_flags(const Peers& P, uint32_t world, uint32_t rank, uint32_t which, uint32_t epoch) {
+    for (uint32_t r = 0; r < world; ++r)
+        reinterpret_cast<volatile uint32_t*>(P.base[r] + kOffFlags)[which * kMaxWorld + rank] = epoch;
+}
+
+// my GEBVs (and ids) -> every peer's vector; the last block to finish raises my GEBV flag everywhere
+__global__ void __launch_bounds__(256) shard_push_values_kernel(const __grid_constant__ Peers P, uint32_t world, uint32_t rank, size_t off_ids,
+                                                                uint32_t lo, uint32_t n_local, int with_ids,
+                                                                uint32_t* counter, uint32_t epoch) {
+    const double* bv = reinterpret_cast<const double*>(P.base[rank] + kOffBv) + lo;
+    const uint32_t* ids = reinterpret_cast<const uint32_t*>(P.base[rank] + off_ids) + lo;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += gridDim.x * blockDim.x) {
+        const double v = bv[i];
+        const uint32_t id = with_ids ? ids[i] : 0u;
+        for (uint32_t r = 0; r < world; ++r) {
+            if (r == rank) continue;
+            (reinterpret_cast<double*>(P.base[r] + kOffBv) + lo)[i] = v;
+            if (with_ids) (reinterpret_cast<uint32_t*>(P.base[r] + off_ids) + lo)[i] = id;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(counter, 1u) == gridDim.x - 1) {
+        __threadfence_system();
+        raise_flags(P, world, rank, 0, epoch);
+        *counter = 0;
+    }
+}
+
+// one lane per rank spins on that rank's flag in MY slab
+__global__ void shard_wait_kernel(const volatile uint32_t* flags, uint32_t world, uint32_t epoch, int* err) {
+    if (threadIdx.x < world) {
+        const long long t0 = clock64();
+        while (flags[threadIdx.x] < epoch) {
+            if (clock64() - t0 > kWaitTimeoutCycles) { atomicExch(err, 1); break; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
+// the selected rows I own -> every rank's pool buffer (mine included), at their rank in the selection;
+// ids of the whole selection (local reads); the last block raises my pool flag everywhere
+__global__ void __launch_bounds__(256) shard_push_pool_kernel(const __grid_constant__ Peers P, uint32_t world, uint32_t rank, size_t off_ids, size_t off_pool,
+                                                              const uint32_t* __restrict__ store, uint64_t row_words,
+                                                              const uint32_t* __restrict__ local_rows, uint32_t lo,
+                                                              const SelectState* __restrict__ state, const uint32_t* __restrict__ sel,
+                                                              uint32_t top_n, uint32_t* __restrict__ sel_ids, int with_ids,
+                                                              uint32_t* counter, uint32_t epoch) {
+    const uint32_t own_lo = state->own_lo, own_cnt = state->own_hi - own_lo;
+    const uint32_t pieces = (uint32_t) (row_words / 4);
+    const uint64_t total = (uint64_t) own_cnt * pieces;
+    for (uint64_t flat = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; flat < total; flat += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t p = own_lo + (uint32_t) (flat / pieces), w = (uint32_t) (flat % pieces);
+        const uint32_t row = local_rows[sel[p] - lo];
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(store + (uint64_t) row * row_words) + w);
+        for (uint32_t r = 0; r < world; ++r)
+            reinterpret_cast<uint4*>(P.base[r] + off_pool)[(uint64_t) p * pieces + w] = v;
+    }
+    const uint32_t* all_ids = reinterpret_cast<const uint32_t*>(P.base[rank] + off_ids);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < top_n; p += gridDim.x * blockDim.x)
+        sel_ids[p] = with_ids ? all_ids[sel[p]] : 0u;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(counter, 1u) == gridDim.x - 1) {
+        __threadfence_system();
+        raise_flags(P, world, rank, 1, epoch);
+        *counter = 0;
+    }
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct gsb200_shard;
+static void mark(gsb200_shard* s, uint32_t epoch, uint32_t which);
+
+struct gsb200_shard {
+    gsb200_ctx* ctx = nullptr;
+    uint32_t rank = 0, world = 1;
+    uint64_t max_total = 0;
+    uint32_t max_pool = 0;
+    uint64_t row_words = 0;
+    char* slab = nullptr;
+    size_t slab_bytes = 0, off_ids = 0, off_pool = 0;
+    Peers peers;
+    bool opened[kMaxWorld];
+    bool connected = false;
+    uint32_t epoch = 0, pool_waited = 0;
+    // device state owned by the shard
+    uint32_t* d_counters = nullptr;      // [0] values push, [1] pool push
+    int* d_err = nullptr;
+    uint32_t* d_sel = nullptr;           // [max_pool] selected global indexes, ascending
+    uint32_t* d_sel_ids = nullptr;       // [max_pool]
+    Scratch s_local_rows;
+    // optional phase timing: a ring of CUDA events, one set per generation (epoch)
+    bool timing = false;
+    cudaEvent_t ev[kTimingRing][kTimingEvents];
+    bool ev_made = false;
+    // last selection
+    uint64_t n_total = 0;
+    uint32_t top_n = 0;
+    bool have_selection = false;
+};
+
+static void mark(gsb200_shard* s, uint32_t epoch, uint32_t which) {
+    if (s->timing) cudaEventRecord(s->ev[epoch % kTimingRing][which], s->ctx->stream);
+}
+
+extern "C" {
+
+void gsb200_shard_range(uint64_t n_total, uint32_t rank, uint32_t world, uint64_t* lo, uint64_t* hi) {
+    const uint64_t base = n_total / world, extra = n_total % world;
+    const uint64_t a = rank * base + std::min<uint64_t>(rank, extra);
+    if (lo) *lo = a;
+    if (hi) *hi = a + base + (rank < extra ? 1 : 0);
+}
+
+int gsb200_shard_create(gsb200_ctx* ctx, uint32_t rank, uint32_t world, uint64_t max_total, uint32_t max_pool, gsb200_shard** out) {
+    GSB_REQUIRE(ctx != nullptr && out != nullptr, GSB200_ERR_ARG, "gsb200_shard_create: null argument");
+    *out = nullptr;
+    GSB_REQUIRE(world >= 1 && world <= kMaxWorld && rank < world, GSB200_ERR_ARG, "gsb200_shard_create: rank %u of %u (at most %u ranks)", rank, world, kMaxWorld);
+    GSB_REQUIRE(max_total >= 1 && max_total < 0xffffffffull && max_pool >= 1, GSB200_ERR_ARG, "gsb200_shard_create: bad sizes");
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    gsb200_shard* s = new gsb200_shard();
+    s->ctx = ctx; s->rank = rank; s->world = world; s->max_total = max_total; s->max_pool = max_pool;
+    s->row_words = ctx->row_words();
+    memset(&s->peers, 0, sizeof s->peers);
+    memset(s->opened, 0, sizeof s->opened);
+    s->off_ids = align_up(kOffBv + max_total * sizeof(double), 256);
+    s->off_pool = align_up(s->off_ids + max_total * sizeof(uint32_t), 256);
+    s->slab_bytes = s->off_pool + (size_t) max_pool * s->row_words * sizeof(uint32_t);
+    cudaError_t e = cudaMalloc((void**) &s->slab, s->slab_bytes);
+    if (e == cudaSuccess) e = cudaMemset(s->slab, 0, kOffBv);
+    if (e == cudaSuccess) e = cudaMalloc((void**) &s->d_counters, 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(s->d_counters, 0, 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**) &s->d_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(s->d_err, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**) &s->d_sel, 2 * (size_t) max_pool * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        set_error("gsb200_shard_create: allocating %zu bytes of exchange buffers failed: %s", s->slab_bytes, cudaGetErrorString(e));
+        gsb200_shard_destroy(s);
+        return e == cudaErrorMemoryAllocation ? GSB200_ERR_OOM : GSB200_ERR_CUDA;
+    }
+    s->d_sel_ids = s->d_sel + max_pool;
+    // Every scratch buffer a generation touches is sized here, for the largest generation: nothing is
+    // allocated (and, above all, nothing is cudaFree'd — which waits for the whole device, including a
+    // peer shard of this process that is spinning on OUR next push) while generations are in flight.
+    int st = ctx->s_select.ensure(select_scratch_bytes((uint32_t) max_total));
+    if (st == GSB200_OK) st = s->s_local_rows.ensure(max_total * sizeof(uint32_t));
+    if (st == GSB200_OK) st = ctx->s_eval[2].ensure(max_total * 8 * sizeof(long long) + (size_t) (ctx->plane_words / 16 + 1) * sizeof(unsigned int));
+    if (st == GSB200_OK) st = ctx->s_rows[1].ensure(2 * max_total * sizeof(uint32_t));
+    if (st == GSB200_OK) st = ctx->s_rows[2].ensure(max_total * sizeof(uint32_t));
+    if (st == GSB200_OK) st = ctx->s_rows[3].ensure(4 * max_total * sizeof(uint32_t));
+    if (st != GSB200_OK) { gsb200_shard_destroy(s); return st; }
+    s->peers.base[rank] = s->slab;
+    s->connected = world == 1;
+    *out = s;
+    return GSB200_OK;
+}
+
+void gsb200_shard_destroy(gsb200_shard* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (uint32_t r = 0; r < kMaxWorld; ++r) if (s->opened[r]) cudaIpcCloseMemHandle(s->peers.base[r]);
+    s->s_local_rows.release();
+    if (s->ev_made) for (auto& set : s->ev) for (auto& e : set) cudaEventDestroy(e);
+    if (s->slab) cudaFree(s->slab);
+    if (s->d_counters) cudaFree(s->d_counters);
+    if (s->d_err) cudaFree(s->d_err);
+    if (s->d_sel) cudaFree(s->d_sel);
+    delete s;
+}
+
+int gsb200_shard_handle(gsb200_shard* s, void* handle) {
+    GSB_REQUIRE(s != nullptr && handle != nullptr, GSB200_ERR_ARG, "gsb200_shard_handle: null argument");
+    GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    ShardHandle h;
+    memset(&h, 0, sizeof h);
+    h.magic = kHandleMagic; h.rank = s->rank; h.world = s->world; h.device = (uint32_t) s->ctx->device;
+    h.pid = (int32_t) getpid(); h.max_pool = s->max_pool;
+    h.slab_bytes = s->slab_bytes; h.row_bytes = s->row_words * sizeof(uint32_t); h.max_total = s->max_total;
+    h.raw = s->slab;
+    GSB_CUDA_TRY(cudaIpcGetMemHandle(&h.ipc, s->slab));
+    memset(handle, 0, GSB200_SHARD_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof h);
+    return GSB200_OK;
+}
+
+int gsb200_shard_connect(gsb200_shard* s, const void* handles) {
+    GSB_REQUIRE(s != nullptr && handles != nullptr, GSB200_ERR_ARG, "gsb200_shard_connect: null argument");
+    GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    for (uint32_t r = 0; r < s->world; ++r) {
+        ShardHandle h;
+        memcpy(&h, (const char*) handles + (size_t) r * GSB200_SHARD_HANDLE_BYTES, sizeof h);
+        GSB_REQUIRE(h.magic == kHandleMagic && h.rank == r && h.world == s->world, GSB200_ERR_ARG,
+                    "gsb200_shard_connect: entry %u is not the handle of rank %u of %u", r, r, s->world);
+        GSB_REQUIRE(h.slab_bytes == s->slab_bytes && h.row_bytes == s->row_words * sizeof(uint32_t) && h.max_total == s->max_total
+                    && h.max_pool == s->max_pool, GSB200_ERR_ARG, "gsb200_shard_connect: rank %u was created with different sizes", r);
+        if (r == s->rank) continue;
+        if (s->opened[r]) { cudaIpcCloseMemHandle(s->peers.base[r]); s->opened[r] = false; }
+        if (h.pid == (int32_t) getpid()) {
+            // a shard of this very process: its slab is addressable as it is (peer access between two devices is switched on here)
+            if ((int) h.device != s->ctx->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess((int) h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    set_error("gsb200_shard_connect: no peer access from device %d to device %u: %s", s->ctx->device, h.device, cudaGetErrorString(e));
+                    return GSB200_ERR_CUDA;
+                }
+                cudaGetLastError();
+            }
+            s->peers.base[r] = (char*) h.raw;
+        } else {
+            void* p = nullptr;
+            GSB_CUDA_TRY(cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+            s->peers.base[r] = (char*) p;
+            s->opened[r] = true;
+        }
+    }
+    s->connected = true;
+    return GSB200_OK;
+}
+
+static int shard_select_impl(gsb200_shard* s, uint32_t n_local, const uint32_t* d_local_rows, const uint32_t* local_ids,
+                             uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best, const char* what) {
+    gsb200_ctx* ctx = s->ctx;
+    GSB_REQUIRE(s->connected, GSB200_ERR_ARG, "%s: the shard is not connected to its peers yet", what);
+    GSB_REQUIRE(n_total >= 1 && n_total <= s->max_total, GSB200_ERR_ARG, "%s: generation of %llu exceeds the %llu the shard was created for",
+                what, (unsigned long long) n_total, (unsigned long long) s->max_total);
+    GSB_REQUIRE(top_n >= 1, GSB200_ERR_ARG, "%s: top_n must be positive", what);
+    if (top_n > n_total) top_n = (uint32_t) n_total;            // "move them all" (core.c:9478-9484)
+    GSB_REQUIRE(top_n <= s->max_pool, GSB200_ERR_ARG, "%s: top_n %u exceeds the pool of %u the shard was created for", what, top_n, s->max_pool);
+    GSB_REQUIRE(ctx->row_words() == s->row_words, GSB200_ERR_ARG, "%s: the store changed its width since the shard was created", what);
+    uint64_t lo, hi;
+    gsb200_shard_range(n_total, s->rank, s->world, &lo, &hi);
+    GSB_REQUIRE(n_local == hi - lo, GSB200_ERR_ARG, "%s: rank %u of %u holds individuals %llu..%llu of %llu, not %u", what, s->rank, s->world,
+                (unsigned long long) lo, (unsigned long long) hi, (unsigned long long) n_total, n_local);
+    GSB_REQUIRE(n_local == 0 || d_local_rows, GSB200_ERR_ARG, "%s: null row array", what);
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    GSB_TRY(ctx->s_select.ensure(select_scratch_bytes((uint32_t) n_total)));
+    const uint32_t prev = s->epoch;
+    const uint32_t epoch = ++s->epoch;
+    const volatile uint32_t* my_flags = reinterpret_cast<const volatile uint32_t*>(s->slab + kOffFlags);
+    if (s->world > 1 && s->pool_waited < prev) {
+        // nobody crossed from the previous selection here: make sure every peer is done reading the GEBV vector
+        shard_wait_kernel<<<1, 32, 0, ctx->stream>>>(my_flags + kMaxWorld, s->world, prev, s->d_err);
+        ++ctx->launches;
+        s->pool_waited = prev;
+    }
+    double* all_bv = reinterpret_cast<double*>(s->slab + kOffBv);
+    mark(s, epoch, 0);
+    if (n_local) GSB_TRY(gsb200_gebv_dev(ctx, n_local, d_local_rows, eff_index, all_bv + lo));
+    const int with_ids = local_ids != nullptr;
+    if (with_ids && n_local)
+        GSB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(s->slab + s->off_ids) + lo, local_ids, (size_t) n_local * sizeof(uint32_t),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    mark(s, epoch, 1);
+    if (s->world > 1) {
+        const unsigned grid = (unsigned) std::max<uint32_t>(1, std::min<uint32_t>((n_local + 255) / 256, (uint32_t) ctx->sm_count * 2));
+        shard_push_values_kernel<<<grid, 256, 0, ctx->stream>>>(s->peers, s->world, s->rank, s->off_ids, (uint32_t) lo, n_local, with_ids,
+                                                                s->d_counters, epoch);
+        shard_wait_kernel<<<1, 32, 0, ctx->stream>>>(my_flags, s->world, epoch, s->d_err);
+        ctx->launches += 2;
+    }
+    mark(s, epoch, 2);
+    GSB_TRY(select_top_n(ctx, all_bv, (uint32_t) n_total, top_n, low_is_best, ctx->s_select.ptr, s->d_sel, (uint32_t) lo, (uint32_t) hi));
+    mark(s, epoch, 3);
+    shard_push_pool_kernel<<<(unsigned) ctx->sm_count * 4, 256, 0, ctx->stream>>>(
+        s->peers, s->world, s->rank, s->off_ids, s->off_pool, ctx->d_store, s->row_words, d_local_rows, (uint32_t) lo,
+        (const SelectState*) ctx->s_select.ptr, s->d_sel, top_n, s->d_sel_ids, with_ids, s->d_counters + 1, epoch);
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    mark(s, epoch, 4);
+    s->n_total = n_total;
+    s->top_n = top_n;
+    s->have_selection = true;
+    return GSB200_OK;
+}
+
+int gsb200_shard_select_dev(gsb200_shard* s, uint32_t n_local, const uint32_t* d_local_rows, const uint32_t* local_ids,
+                            uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    return shard_select_impl(s, n_local, d_local_rows, local_ids, n_total, eff_index, top_n, low_is_best, "gsb200_shard_select_dev");
+}
+
+int gsb200_shard_select(gsb200_shard* s, uint32_t n_local, const uint32_t* local_rows, const uint32_t* local_ids,
+                        uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    GSB_TRY(check_rows(s->ctx, n_local, local_rows, "gsb200_shard_select"));
+    GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    // the rows are read again when the pool is pushed: they get a buffer of their own
+    uint32_t* d_rows;
+    GSB_TRY(upload_u32(s->ctx, s->s_local_rows, local_rows, n_local, &d_rows));
+    return shard_select_impl(s, n_local, d_rows, local_ids, n_total, eff_index, top_n, low_is_best, "gsb200_shard_select");
+}
+
+int gsb200_shard_cross_dev(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t* d_out_rows, uint32_t first_out_row,
+                           const gsb200_draws* draws, uint32_t* d_picks) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    const char* what = "gsb200_shard_cross_dev";
+    GSB_REQUIRE(s->have_selection, GSB200_ERR_ARG, "%s: nothing has been selected yet", what);
+    gsb200_ctx* ctx = s->ctx;
+    GSB_REQUIRE(ctx->row_words() == s->row_words, GSB200_ERR_ARG, "%s: the store changed its width since the shard was created", what);
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (s->world > 1 && s->pool_waited < s->epoch) {
+        shard_wait_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const volatile uint32_t*>(s->slab + kOffFlags) + kMaxWorld,
+                                                    s->world, s->epoch, s->d_err);
+        ++ctx->launches;
+        s->pool_waited = s->epoch;
+    }
+    mark(s, s->epoch, 5);
+    GSB_TRY(pool_random_cross(ctx, reinterpret_cast<const uint32_t*>(s->slab + s->off_pool), s->top_n, n, map, d_out_rows, first_out_row,
+                              draws, d_picks, what));
+    mark(s, s->epoch, 6);
+    return GSB200_OK;
+}
+
+int gsb200_shard_cross(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t* out_rows, const gsb200_draws* draws,
+                       uint32_t* picked1, uint32_t* picked2) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    if (n == 0) return GSB200_OK;
+    gsb200_ctx* ctx = s->ctx;
+    GSB_TRY(check_rows(ctx, n, out_rows, "gsb200_shard_cross"));
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint32_t* d_out;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[2], out_rows, n, &d_out));
+    uint32_t* d_picks = nullptr;
+    if (picked1 && picked2) {
+        GSB_TRY(ctx->s_rows[1].ensure((size_t) 2 * n * sizeof(uint32_t)));
+        d_picks = (uint32_t*) ctx->s_rows[1].ptr;
+    }
+    GSB_TRY(gsb200_shard_cross_dev(s, n, map, d_out, 0, draws, d_picks));
+    if (d_picks) {
+        GSB_CUDA_TRY(cudaMemcpyAsync(picked1, d_picks, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        GSB_CUDA_TRY(cudaMemcpyAsync(picked2, d_picks + n, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    GSB_TRY(gsb200_cross_dev_status(ctx));           // synchronises; a plan overflow is reported, not silently kept
+    return gsb200_shard_status(s);
+}
+
+int gsb200_shard_selected(gsb200_shard* s, uint32_t* global_indexes, uint32_t* ids, double* all_bvs) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    GSB_REQUIRE(s->have_selection, GSB200_ERR_ARG, "gsb200_shard_selected: nothing has been selected yet");
+    gsb200_ctx* ctx = s->ctx;
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (global_indexes) GSB_CUDA_TRY(cudaMemcpyAsync(global_indexes, s->d_sel, (size_t) s->top_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ids) GSB_CUDA_TRY(cudaMemcpyAsync(ids, s->d_sel_ids, (size_t) s->top_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (all_bvs) GSB_CUDA_TRY(cudaMemcpyAsync(all_bvs, s->slab + kOffBv, (size_t) s->n_total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return gsb200_shard_status(s);
+}
+
+int gsb200_shard_set_timing(gsb200_shard* s, int enabled) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    if (enabled && !s->ev_made) {
+        for (auto& set : s->ev) for (auto& e : set) GSB_CUDA_TRY(cudaEventCreate(&e));
+        s->ev_made = true;
+    }
+    s->timing = enabled != 0;
+    return GSB200_OK;
+}
+
+uint32_t gsb200_shard_epoch(const gsb200_shard* s) { return s ? s->epoch : 0; }
+
+int gsb200_shard_phase_ms(gsb200_shard* s, uint32_t epoch, float* ms) {
+    GSB_REQUIRE(s != nullptr && ms != nullptr, GSB200_ERR_ARG, "gsb200_shard_phase_ms: null argument");
+    GSB_REQUIRE(s->ev_made && epoch >= 1 && epoch <= s->epoch && s->epoch - epoch < kTimingRing, GSB200_ERR_ARG,
+                "gsb200_shard_phase_ms: generation %u was not timed or is no longer kept", epoch);
+    GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    GSB_CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    cudaEvent_t* e = s->ev[epoch % kTimingRing];
+    for (uint32_t k = 0; k + 1 < kTimingEvents; ++k) GSB_CUDA_TRY(cudaEventElapsedTime(&ms[k], e[k], e[k + 1]));
+    return GSB200_OK;
+}
+
+uint64_t gsb200_shard_generation_size(const gsb200_shard* s) { return s && s->have_selection ? s->n_total : 0; }
+uint32_t gsb200_shard_pool_size(const gsb200_shard* s) { return s && s->have_selection ? s->top_n : 0; }
+void* gsb200_shard_pool_device_ptr(gsb200_shard* s) { return s ? (void*) (s->slab + s->off_pool) : nullptr; }
+
+int gsb200_shard_status(gsb200_shard* s) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    int err = 0;
+    GSB_CUDA_TRY(cudaMemcpyAsync(&err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    GSB_REQUIRE(err == 0, GSB200_ERR_CUDA, "shard %u of %u: a peer did not deliver its part of the exchange in time", s->rank, s->world);
+    return GSB200_OK;
+}
+
+}  // extern "C"

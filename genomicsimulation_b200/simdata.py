@@ -296,6 +296,35 @@ class SimData:
         self._check()
         return g
 
+    # ---- sharded recurrent selection (include/gsb200_gsc.h gsb_shard_*) -------------------
+    def shard_init(self, rank, world, max_generation, max_pool):
+        if self.L.gsb_shard_init(self.d, rank, world, max_generation, max_pool) != 0:
+            self._check()
+
+    def shard_handle(self):
+        buf = C.create_string_buffer(_lib.SHARD_HANDLE_BYTES)
+        if self.L.gsb_shard_handle(self.d, buf) != 0:
+            self._check()
+        return buf.raw
+
+    def shard_connect(self, handles):
+        if self.L.gsb_shard_connect(self.d, handles) != 0:
+            self._check()
+
+    def shard_select_and_cross(self, group, n_total, eff_id, top_n, n_offspring_total, low_is_best=False, map_id=0, **kw):
+        g = self.L.gsb_shard_select_and_cross(self.d, group, n_total, eff_id, top_n, bool(low_is_best), n_offspring_total,
+                                              map_id, _opts(**kw))
+        self._check()
+        return g
+
+    def shard_last_selection(self, n_total, top_n, bvs=True):
+        bv = np.empty(n_total, dtype=np.float64) if bvs else None
+        sel = np.empty(top_n, dtype=np.uint32)
+        got = self.L.gsb_shard_last_selection(self.d, n_total, _p(bv) if bvs else None, top_n, _p(sel))
+        self._check()
+        assert got == top_n
+        return sel, bv
+
     def make_group_from(self, indexes):
         a = np.ascontiguousarray(indexes, dtype=np.uint32)
         return self.L.gsb_make_group_from(self.d, len(a), _p(a))

@@ -236,11 +236,71 @@ int  gsb200_allele_counts(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, cha
  * gsc_calculate_optimal_possible_bv (core.c:10171-10222, 10285-10346) as an OR-reduction. */
 int  gsb200_allele_presence(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint8_t* present);
 
-/* The ranking step of gsc_split_by_bv (core.c:9489-9508): positions (0..n-1) of the
- * `top_n` best values, best first; ties broken by lower position (the reference leaves
- * tie order undefined, core.c:1305-1306). */
+/* The ranking step of gsc_split_by_bv (core.c:9489-9508) as a radix SELECT (no sort): positions
+ * (0..n-1) of the `top_n` best values in ASCENDING POSITION order — the order the members of the
+ * new group have in the reference too (storage order, core.c:9510-9514).  Everything strictly
+ * better than the top_n-th best value is taken, then the ties at that value by lower position (the
+ * reference leaves tie order to qsort, core.c:1305-1306). */
 int  gsb200_top_n(gsb200_ctx* ctx, uint32_t n, const double* values, uint32_t top_n,
                   int low_is_best, uint32_t* out_positions);
+
+/* ------------------------------------------------------------------ sharded generations
+ * Recurrent selection with the generation sharded over the GPUs of one box (the
+ * reference is single-process, so there is no counterpart beyond the calls named below): one
+ * context — normally one process — per GPU holds a contiguous index range of the generation
+ * (gsb200_shard_range).  All of a generation is enqueued on the context stream without any host
+ * synchronisation; GEBVs and the selected parents travel by P2P stores over NVLink into buffers
+ * the peers opened through CUDA IPC.
+ *
+ * Set-up: every rank creates its shard with the SAME sizes, exports a handle, the handles of all
+ * ranks (in rank order) reach every rank by whatever the host has — torch.distributed, MPI, a
+ * pipe — and gsb200_shard_connect opens them. */
+typedef struct gsb200_shard gsb200_shard;
+#define GSB200_SHARD_HANDLE_BYTES 128
+
+/* [lo, hi) of rank's individuals in a generation of n_total: the first n_total % world ranks hold one more */
+void gsb200_shard_range(uint64_t n_total, uint32_t rank, uint32_t world, uint64_t* lo, uint64_t* hi);
+/* max_total: largest generation (all ranks together); max_pool: largest selection */
+int  gsb200_shard_create(gsb200_ctx* ctx, uint32_t rank, uint32_t world, uint64_t max_total, uint32_t max_pool, gsb200_shard** out);
+void gsb200_shard_destroy(gsb200_shard* shard);
+int  gsb200_shard_handle(gsb200_shard* shard, void* handle /* [GSB200_SHARD_HANDLE_BYTES] */);
+int  gsb200_shard_connect(gsb200_shard* shard, const void* handles /* world x GSB200_SHARD_HANDLE_BYTES, rank order */);
+
+/* gsc_split_by_bv (core.c:9463-9517) over the whole sharded generation: GEBVs (effect set eff_index)
+ * of this rank's n_local individuals (rows local_rows, global indexes lo .. hi-1 in that order) are
+ * computed and exchanged, every rank selects the same global top_n (ties by lower global index), and
+ * the selected individuals' packed rows land in every rank's parent pool in ascending global index.
+ * local_ids (host, may be NULL): the individuals' PedigreeIDs, exchanged alongside so that every rank
+ * can name the selected parents.  Every rank must make the same sequence of calls.  Asynchronous. */
+int  gsb200_shard_select(gsb200_shard* shard, uint32_t n_local, const uint32_t* local_rows, const uint32_t* local_ids,
+                         uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best);
+/* ... with the row list already on the device (it must stay valid until the call's work is done) */
+int  gsb200_shard_select_dev(gsb200_shard* shard, uint32_t n_local, const uint32_t* d_local_rows, const uint32_t* local_ids,
+                             uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best);
+/* gsc_make_random_crosses (core.c:8483-8532, no usage cap, one offspring per cross) from the selected
+ * pool: n offspring into out_rows of this rank's store; the pairs are drawn on the device with the pick
+ * rule of core.c:8556-8581 from the stream position draws->first_unit (= the global index of this rank's
+ * first offspring), so the generation does not depend on how it is sharded.  picked1/2 (host, may be
+ * NULL): positions of the parents in the selection.  Synchronises. */
+int  gsb200_shard_cross(gsb200_shard* shard, uint32_t n, uint32_t map, const uint32_t* out_rows, const gsb200_draws* draws,
+                        uint32_t* picked1, uint32_t* picked2);
+/* ... asynchronous: d_out_rows NULL = rows first_out_row, first_out_row + 1, ...; d_picks (device, 2n) may be NULL */
+int  gsb200_shard_cross_dev(gsb200_shard* shard, uint32_t n, uint32_t map, const uint32_t* d_out_rows, uint32_t first_out_row,
+                            const gsb200_draws* draws, uint32_t* d_picks);
+/* the last selection: global indexes (ascending), their ids, the GEBVs of the whole generation; any may be NULL. Synchronises. */
+int  gsb200_shard_selected(gsb200_shard* shard, uint32_t* global_indexes, uint32_t* ids, double* all_bvs);
+uint64_t gsb200_shard_generation_size(const gsb200_shard* shard);   /* n_total of the last selection */
+uint32_t gsb200_shard_pool_size(const gsb200_shard* shard);         /* top_n of the last selection */
+void* gsb200_shard_pool_device_ptr(gsb200_shard* shard);   /* pool rows in store layout, selection order */
+/* Phase timing with CUDA events on the context stream (off by default).  ms[6] of generation `epoch`
+ * (1 = the first gsb200_shard_select since creation; the last 256 are kept): GEBV kernels | GEBV
+ * exchange (push + wait for every rank) | selection | pool push | wait for every rank's pool rows |
+ * pair draw + splice.  The two waits include waiting for the slowest rank.  Synchronises. */
+int  gsb200_shard_set_timing(gsb200_shard* shard, int enabled);
+uint32_t gsb200_shard_epoch(const gsb200_shard* shard);
+int  gsb200_shard_phase_ms(gsb200_shard* shard, uint32_t epoch, float* ms /* [6] */);
+/* synchronises; GSB200_ERR_CUDA if a peer failed to deliver its part of an exchange within ~20 s */
+int  gsb200_shard_status(gsb200_shard* shard);
 
 /* ------------------------------------------------------------------ instrumentation */
 /* number of kernels launched by this context since creation */

@@ -153,6 +153,25 @@ gsb_GroupNum gsb_split_by_bv(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID ef
 void gsb_delete_dmatrix(gsb_DecimalMatrix* m);          /* core.c:4628-4641 */
 void gsb_delete_markerblocks(gsb_MarkerBlocks* b);      /* core.c:4757-4766 */
 
+/* ---- recurrent selection with the generation sharded over the GPUs of a box:
+ *      one SimData per GPU, each holding a contiguous index range of every generation
+ *      (gsb200_shard_range); GSB_DRAWS_NATIVE only.  Set-up: gsb_shard_init on every rank with the
+ *      same sizes, gsb_shard_handle, hand all handles (rank order, GSB200_SHARD_HANDLE_BYTES each) to
+ *      every rank, gsb_shard_connect.  All return 0 on success. */
+int gsb_shard_init(gsb_SimData* d, unsigned int rank, unsigned int world, unsigned long long max_generation, unsigned int max_pool);
+int gsb_shard_handle(gsb_SimData* d, void* handle);
+int gsb_shard_connect(gsb_SimData* d, const void* handles);
+/* gsc_split_by_bv (core.c:9463-9517) + gsc_make_random_crosses (core.c:8483-8532, cap 0, family_size 1) on
+ * the whole sharded generation: `group` = this rank's slice of a generation of n_total (members in global
+ * index order); the global top_n by GEBV are selected, exchanged, and this rank's slice of the
+ * n_offspring_total random crosses among them becomes a new group (returned).  Ids, names and pedigrees
+ * are those one process would have given offspring olo..ohi-1; every rank advances current_id by
+ * n_offspring_total.  Nothing but row lists, ids and (for pedigrees) the picks crosses PCIe. */
+gsb_GroupNum gsb_shard_select_and_cross(gsb_SimData* d, gsb_GroupNum group, unsigned long long n_total, gsb_EffectID effID,
+                                        unsigned int top_n, _Bool lowIsBest, unsigned long long n_offspring_total,
+                                        gsb_MapID which_map, gsb_GenOptions g);
+unsigned int gsb_shard_last_selection(gsb_SimData* d, unsigned long long n_total, double* bvs_out, unsigned int top_n, unsigned int* selected_out);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
