@@ -63,6 +63,7 @@ ENGINE_SYMBOLS = {
     "gsb200_store_device_ptr": (VP, [VP]),
     "gsb200_store_upload_chars": (I32, [VP, U32, VP, VP]),
     "gsb200_store_download_chars": (I32, [VP, U32, VP, VP]),
+    "gsb200_store_download_chars_range": (I32, [VP, U32, VP, U32, U32, VP]),
     "gsb200_store_gather_rows_dev": (I32, [VP, U32, VP, VP]),
     "gsb200_store_scatter_rows_dev": (I32, [VP, U32, VP, VP]),
     "gsb200_store_change_symbol": (I32, [VP, U32, C.c_char, C.c_char]),
@@ -103,6 +104,7 @@ ENGINE_SYMBOLS = {
     "gsb200_shard_cross": (I32, [VP, U32, U32, VP, C.POINTER(Draws), VP, VP]),
     "gsb200_shard_cross_dev": (I32, [VP, U32, U32, VP, U32, C.POINTER(Draws), VP]),
     "gsb200_shard_selected": (I32, [VP, VP, VP, VP]),
+    "gsb200_shard_local_bvs": (I32, [VP, U32, VP]),
     "gsb200_shard_generation_size": (U64, [VP]),
     "gsb200_shard_pool_size": (U32, [VP]),
     "gsb200_shard_pool_device_ptr": (VP, [VP]),
@@ -164,10 +166,16 @@ HOST_SYMBOLS = {
     "gsb_split_by_bv": (UINT, [VP, UINT, UINT, UINT, C.c_bool]),
     "gsb_delete_dmatrix": (None, [C.POINTER(DecimalMatrix)]),
     "gsb_delete_markerblocks": (None, [C.POINTER(MarkerBlocks)]),
+    "gsb_save_genotypes": (None, [C.c_char_p, VP, UINT, C.c_bool]),
+    "gsb_save_allele_counts": (None, [C.c_char_p, VP, UINT, C.c_char, C.c_bool]),
+    "gsb_save_pedigrees": (None, [C.c_char_p, VP, UINT, C.c_bool]),
+    "gsb_save_bvs": (None, [C.c_char_p, VP, UINT, UINT]),
+    "gsb_save_local_bvs": (None, [C.c_char_p, VP, UINT, MarkerBlocks, UINT, C.c_bool]),
     "gsb_shard_init": (I32, [VP, UINT, UINT, C.c_ulonglong, UINT]),
     "gsb_shard_handle": (I32, [VP, VP]),
     "gsb_shard_connect": (I32, [VP, VP]),
     "gsb_shard_select_and_cross": (UINT, [VP, UINT, C.c_ulonglong, UINT, UINT, C.c_bool, C.c_ulonglong, UINT, GenOptions]),
+    "gsb_shard_get_local_bvs": (UINT, [VP, UINT, VP]),
     "gsb_shard_last_selection": (UINT, [VP, C.c_ulonglong, VP, UINT, VP]),
 }
 

@@ -434,6 +434,20 @@ int gsb200_shard_phase_ms(gsb200_shard* s, uint32_t epoch, float* ms) {
     return GSB200_OK;
 }
 
+int gsb200_shard_local_bvs(gsb200_shard* s, uint32_t n_local, double* out) {
+    GSB_REQUIRE(s != nullptr && out != nullptr, GSB200_ERR_ARG, "gsb200_shard_local_bvs: null argument");
+    GSB_REQUIRE(s->have_selection, GSB200_ERR_ARG, "gsb200_shard_local_bvs: nothing has been evaluated yet");
+    uint64_t lo, hi;
+    gsb200_shard_range(s->n_total, s->rank, s->world, &lo, &hi);
+    GSB_REQUIRE(n_local == hi - lo, GSB200_ERR_ARG, "gsb200_shard_local_bvs: this rank evaluated %llu individuals, not %u",
+                (unsigned long long) (hi - lo), n_local);
+    GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    if (n_local) GSB_CUDA_TRY(cudaMemcpyAsync(out, reinterpret_cast<const double*>(s->slab + kOffBv) + lo, (size_t) n_local * sizeof(double),
+                                              cudaMemcpyDeviceToHost, s->ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    return GSB200_OK;
+}
+
 uint64_t gsb200_shard_generation_size(const gsb200_shard* s) { return s && s->have_selection ? s->n_total : 0; }
 uint32_t gsb200_shard_pool_size(const gsb200_shard* s) { return s && s->have_selection ? s->top_n : 0; }
 void* gsb200_shard_pool_device_ptr(gsb200_shard* s) { return s ? (void*) (s->slab + s->off_pool) : nullptr; }

@@ -48,31 +48,31 @@ __global__ void pack_kernel(uint32_t* __restrict__ store, uint64_t row_words, ui
             dst[(uint64_t) (h * planes + p) * plane_words + w] = acc[h][p];
 }
 
-// chars[i] <- rows[i]
+// chars[i] <- markers [m_lo, m_hi) of rows[i]; the output row is 2 * (m_hi - m_lo) chars
 __global__ void unpack_kernel(const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
-                              uint32_t planes, uint32_t n_markers,
+                              uint32_t planes, uint32_t m_lo, uint32_t m_hi,
                               const uint32_t* __restrict__ rows, uint32_t n,
                               uint8_t* __restrict__ chars,
                               const uint8_t* __restrict__ dict_sym) {
-    const uint32_t words = (n_markers + 31) / 32;
+    const uint32_t w_lo = m_lo >> 5, words = ((m_hi + 31) >> 5) - w_lo;
     const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (uint64_t) n * words) return;
-    const uint32_t i = (uint32_t) (tid / words), w = (uint32_t) (tid % words);
+    const uint32_t i = (uint32_t) (tid / words), w = w_lo + (uint32_t) (tid % words);
     const uint32_t* src = store + (uint64_t) rows[i] * row_words;
     uint32_t bits[2][8];
     for (uint32_t h = 0; h < 2; ++h)
         for (uint32_t p = 0; p < 8; ++p)
             bits[h][p] = p < planes ? src[(uint64_t) (h * planes + p) * plane_words + w] : 0u;
-    uint8_t* dst = chars + (size_t) i * 2 * n_markers;
-    const uint32_t m_end = min(n_markers, (w + 1) * 32);
-    for (uint32_t m = w * 32; m < m_end; ++m) {
+    uint8_t* dst = chars + (size_t) i * 2 * (m_hi - m_lo);
+    const uint32_t m_end = min(m_hi, (w + 1) * 32);
+    for (uint32_t m = max(w * 32, m_lo); m < m_end; ++m) {
         const uint8_t* sym = dict_sym + ((size_t) m << planes);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             uint32_t code = 0;
 #pragma unroll
             for (int p = 0; p < 8; ++p) code |= ((bits[h][p] >> (m & 31)) & 1u) << p;
-            dst[2 * (size_t) m + h] = sym[code];
+            dst[2 * (size_t) (m - m_lo) + h] = sym[code];
         }
     }
 }
@@ -312,17 +312,20 @@ int gsb200_store_upload_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows,
     return GSB200_OK;
 }
 
-int gsb200_store_download_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, char* chars) {
+int gsb200_store_download_chars_range(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t first_marker, uint32_t n_markers_out, char* chars) {
     GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
-    if (n == 0) return GSB200_OK;
-    GSB_REQUIRE(chars != nullptr, GSB200_ERR_ARG, "gsb200_store_download_chars: null output");
-    GSB_TRY(check_rows(ctx, n, rows, "gsb200_store_download_chars"));
+    if (n == 0 || n_markers_out == 0) return GSB200_OK;
+    const char* what = "gsb200_store_download_chars";
+    GSB_REQUIRE(chars != nullptr, GSB200_ERR_ARG, "%s: null output", what);
+    GSB_REQUIRE((uint64_t) first_marker + n_markers_out <= ctx->n_markers, GSB200_ERR_ARG, "%s: markers %u..%llu are beyond the genome's %u",
+                what, first_marker, (unsigned long long) first_marker + n_markers_out, ctx->n_markers);
+    GSB_TRY(check_rows(ctx, n, rows, what));
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
     GSB_TRY(sync_dictionary(ctx));
-    const uint32_t M = ctx->n_markers;
-    const size_t row_chars = 2 * (size_t) M;
+    const uint32_t m_lo = first_marker, m_hi = first_marker + n_markers_out;
+    const size_t row_chars = 2 * (size_t) n_markers_out;
     const uint32_t chunk = (uint32_t) std::max<size_t>(1, std::min<size_t>(n, ((size_t) 256 << 20) / row_chars));
-    const uint32_t words = (M + 31) / 32;
+    const uint32_t words = ((m_hi + 31) >> 5) - (m_lo >> 5);
     for (uint32_t done = 0; done < n; done += chunk) {
         const uint32_t cnt = std::min(chunk, n - done);
         uint32_t* d_rows = nullptr;
@@ -330,7 +333,7 @@ int gsb200_store_download_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* row
         GSB_TRY(ctx->s_io.ensure(cnt * row_chars));
         const uint64_t threads = (uint64_t) cnt * words;
         unpack_kernel<<<(unsigned) ((threads + 127) / 128), 128, 0, ctx->stream>>>(
-            ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->planes, M, d_rows, cnt,
+            ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->planes, m_lo, m_hi, d_rows, cnt,
             (uint8_t*) ctx->s_io.ptr, ctx->d_dict_sym);
         ++ctx->launches;
         GSB_CUDA_TRY(cudaGetLastError());
@@ -339,6 +342,11 @@ int gsb200_store_download_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* row
         GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
     return GSB200_OK;
+}
+
+int gsb200_store_download_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, char* chars) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    return gsb200_store_download_chars_range(ctx, n, rows, 0, ctx->n_markers, chars);
 }
 
 int gsb200_store_gather_rows_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, void* d_dense) {

@@ -18,9 +18,11 @@ def _p(a):
 
 
 def _opts(family_size=1, track_pedigree=True, allocate_ids=True, name_offspring=False,
-          retain=True, name_prefix=None):
+          retain=True, name_prefix=None, file_prefix=None, save_pedigree=False, save_bvs=0, save_genotypes=False):
     return GenOptions(bool(name_offspring), name_prefix.encode() if name_prefix is not None else None,
-                      family_size, bool(track_pedigree), bool(allocate_ids), None, False, 0, False, bool(retain))
+                      family_size, bool(track_pedigree), bool(allocate_ids),
+                      file_prefix.encode() if file_prefix is not None else None, bool(save_pedigree), int(save_bvs),
+                      bool(save_genotypes), bool(retain))
 
 
 class Blocks:
@@ -317,6 +319,11 @@ class SimData:
         self._check()
         return g
 
+    def shard_local_bvs(self, out):
+        got = self.L.gsb_shard_get_local_bvs(self.d, len(out), _p(out))
+        self._check()
+        return out[:got]
+
     def shard_last_selection(self, n_total, top_n, bvs=True):
         bv = np.empty(n_total, dtype=np.float64) if bvs else None
         sel = np.empty(top_n, dtype=np.uint32)
@@ -324,6 +331,28 @@ class SimData:
         self._check()
         assert got == top_n
         return sel, bv
+
+    # ---- savers (same method names as oracle/ref.py) -------------------------------------
+    def save_genotypes(self, f, group=0, markers_as_rows=False):
+        self.L.gsb_save_genotypes(str(f).encode(), self.d, group, bool(markers_as_rows))
+        self._check()
+
+    def save_bvs(self, f, group, eff_id):
+        self.L.gsb_save_bvs(str(f).encode(), self.d, group, eff_id)
+        self._check()
+
+    def save_allele_counts(self, f, group, allele, markers_as_rows=False):
+        a = allele if isinstance(allele, bytes) else allele.encode()
+        self.L.gsb_save_allele_counts(str(f).encode(), self.d, group, C.c_char(a), bool(markers_as_rows))
+        self._check()
+
+    def save_local_bvs(self, f, group, blocks, eff_id, headers=True):
+        self.L.gsb_save_local_bvs(str(f).encode(), self.d, group, blocks.mb, eff_id, bool(headers))
+        self._check()
+
+    def save_pedigrees(self, f, group=0, full=True):
+        self.L.gsb_save_pedigrees(str(f).encode(), self.d, group, bool(full))
+        self._check()
 
     def make_group_from(self, indexes):
         a = np.ascontiguousarray(indexes, dtype=np.uint32)

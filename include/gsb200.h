@@ -78,6 +78,11 @@ int  gsb200_store_upload_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows
 /* rows -> chars.  The save/see boundary: gsc_helper_output_genotypematrix_cell
  * (core.c:10951-10958), SXP_see_group_data "G" (r-wrappers.c:815-837). */
 int  gsb200_store_download_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, char* chars);
+/* ... of markers first_marker .. first_marker + n_markers_out - 1 only (chars: n x 2*n_markers_out): the
+ * markers-as-rows orientation of gsc_scaffold_save_genotype_info (core.c:10848-10907) walks one marker
+ * across all genotypes, so the savers take the store a block of markers at a time. */
+int  gsb200_store_download_chars_range(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, uint32_t first_marker,
+                                       uint32_t n_markers_out, char* chars);
 /* Packed rows <-> a dense DEVICE buffer of n x gsb200_store_row_bytes() bytes (16-byte aligned):
  * the send/receive side of the per-generation parent-pool broadcast over NCCL (no reference
  * counterpart: the reference is single-process). `d_rows` is a DEVICE array; asynchronous on the
@@ -289,6 +294,8 @@ int  gsb200_shard_cross_dev(gsb200_shard* shard, uint32_t n, uint32_t map, const
                             const gsb200_draws* draws, uint32_t* d_picks);
 /* the last selection: global indexes (ascending), their ids, the GEBVs of the whole generation; any may be NULL. Synchronises. */
 int  gsb200_shard_selected(gsb200_shard* shard, uint32_t* global_indexes, uint32_t* ids, double* all_bvs);
+/* the GEBVs the last selection computed for THIS rank's n_local individuals, in their order. Synchronises. */
+int  gsb200_shard_local_bvs(gsb200_shard* shard, uint32_t n_local, double* out);
 uint64_t gsb200_shard_generation_size(const gsb200_shard* shard);   /* n_total of the last selection */
 uint32_t gsb200_shard_pool_size(const gsb200_shard* shard);         /* top_n of the last selection */
 void* gsb200_shard_pool_device_ptr(gsb200_shard* shard);   /* pool rows in store layout, selection order */

@@ -153,6 +153,16 @@ gsb_GroupNum gsb_split_by_bv(gsb_SimData* d, gsb_GroupNum group, gsb_EffectID ef
 void gsb_delete_dmatrix(gsb_DecimalMatrix* m);          /* core.c:4628-4641 */
 void gsb_delete_markerblocks(gsb_MarkerBlocks* b);      /* core.c:4757-4766 */
 
+/* ---- savers (core.c:10449-10663): the reference's text formats byte for byte; genotypes leave the store
+ *      1000 genotypes (or a block of markers) at a time.  The crossing functions above also write the
+ *      save-as-you-go files of gsc_GenOptions (`{prefix}-pedigree.txt`, `-bv.txt`, `-genotype.txt`,
+ *      core.c:8058-8163), and honour will_save_to_simdata = FALSE after writing them. */
+void gsb_save_genotypes(const char* fname, gsb_SimData* d, gsb_GroupNum groupID, _Bool markers_as_rows);
+void gsb_save_allele_counts(const char* fname, gsb_SimData* d, gsb_GroupNum groupID, char allele, _Bool markers_as_rows);
+void gsb_save_pedigrees(const char* fname, gsb_SimData* d, gsb_GroupNum groupID, _Bool full_pedigree);
+void gsb_save_bvs(const char* fname, gsb_SimData* d, gsb_GroupNum groupID, gsb_EffectID effID);
+void gsb_save_local_bvs(const char* fname, gsb_SimData* d, gsb_GroupNum groupID, gsb_MarkerBlocks b, gsb_EffectID effID, _Bool headers);
+
 /* ---- recurrent selection with the generation sharded over the GPUs of a box:
  *      one SimData per GPU, each holding a contiguous index range of every generation
  *      (gsb200_shard_range); GSB_DRAWS_NATIVE only.  Set-up: gsb_shard_init on every rank with the
@@ -170,6 +180,7 @@ int gsb_shard_connect(gsb_SimData* d, const void* handles);
 gsb_GroupNum gsb_shard_select_and_cross(gsb_SimData* d, gsb_GroupNum group, unsigned long long n_total, gsb_EffectID effID,
                                         unsigned int top_n, _Bool lowIsBest, unsigned long long n_offspring_total,
                                         gsb_MapID which_map, gsb_GenOptions g);
+unsigned int gsb_shard_get_local_bvs(gsb_SimData* d, unsigned int n_local, double* output);
 unsigned int gsb_shard_last_selection(gsb_SimData* d, unsigned long long n_total, double* bvs_out, unsigned int top_n, unsigned int* selected_out);
 
 #if defined(__GNUC__)

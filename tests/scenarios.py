@@ -61,3 +61,55 @@ def assert_same_state(a, b):
     for key in ("groups", "ids", "ped1", "ped2"):
         np.testing.assert_array_equal(a[key], b[key], err_msg=key)
     np.testing.assert_array_equal(a["genotypes"], b["genotypes"], err_msg="genotype bytes")
+
+
+def saver_scheme(sim, founders, effs, out, big=False):
+    """The save/see boundary: every saver in both orientations, local GEBV
+    tables, and the three save-as-you-go files of the crossing scaffold with and without names, ids
+    and retained offspring (reference tests: test-printers.R:1-65, 67-111, 200-323;
+    test-progression.R:54-109).  `out`: directory (str) the files go to; returns their names in order."""
+    import os
+    m0 = sim.map_arg(0)
+    e0, e1 = effs
+    files = []
+
+    def f(name):
+        files.append(name)
+        return os.path.join(out, name)
+
+    sim.save_genotypes(f("geno-group.txt"), founders, False)
+    sim.save_genotypes(f("geno-all.txt"), 0, False)
+    sim.save_genotypes(f("geno-group-t.txt"), founders, True)
+    sim.save_genotypes(f("geno-all-t.txt"), 0, True)
+    sim.save_allele_counts(f("count-T.txt"), founders, "T", False)
+    sim.save_allele_counts(f("count-A-t.txt"), 0, "A", True)
+    sim.save_bvs(f("bv.txt"), founders, e0)
+    b = sim.blocks_evenlength(3, m0)
+    sim.save_local_bvs(f("local-headers.txt"), founders, b, e0, True)
+    sim.save_local_bvs(f("local-bare.txt"), 0, b, e1, False)
+    b.free()
+    # save-as-you-go, as in test-progression.R:54-109
+    sim.make_clones(founders, True, file_prefix=os.path.join(out, "sayg1"), save_genotypes=True, retain=False)
+    files.append("sayg1-genotype.txt")
+    sim.make_clones(founders, True, file_prefix=os.path.join(out, "sayg2"), save_bvs=e0, retain=False)
+    files.append("sayg2-bv.txt")
+    sim.make_doubled_haploids(founders, m0, file_prefix=os.path.join(out, "sayg3"), save_pedigree=True, retain=False)
+    files.append("sayg3-pedigree.txt")
+    sim.make_clones(founders, False, file_prefix=os.path.join(out, "sayg4"), save_genotypes=True, save_bvs=e0, save_pedigree=True,
+                    allocate_ids=False, retain=False)     # (retained id-less genotypes send the reference's id bisection, core.c:362-418, into a loop)
+    files += ["sayg4-genotype.txt", "sayg4-bv.txt", "sayg4-pedigree.txt"]
+    # crosses whose pedigrees recurse over named and unnamed ancestors
+    n = 600 if big else 5
+    f1 = sim.make_random_crosses(founders, n, 0, m0, family_size=2, name_offspring=True, name_prefix="x",
+                                 file_prefix=os.path.join(out, "c1"), save_genotypes=True, save_bvs=e1, save_pedigree=True)
+    files += ["c1-genotype.txt", "c1-bv.txt", "c1-pedigree.txt"]
+    f2 = sim.self_n_times(2, f1, m0, file_prefix=os.path.join(out, "c2"), save_pedigree=True, save_genotypes=True)
+    files += ["c2-pedigree.txt", "c2-genotype.txt"]
+    f3 = sim.make_random_crosses_between(f1, f2, n, 0, 0, m0, m0, track_pedigree=True, allocate_ids=(not big),
+                                         file_prefix=os.path.join(out, "c3"), save_pedigree=True, save_bvs=e0, retain=False)
+    files += ["c3-pedigree.txt", "c3-bv.txt"]
+    sim.save_pedigrees(f("ped-full.txt"), f2, True)
+    sim.save_pedigrees(f("ped-parents.txt"), 0, False)
+    sim.save_genotypes(f("geno-f2-t.txt"), f2, True)
+    sim.save_bvs(f("bv-all.txt"), 0, e1)
+    return files
