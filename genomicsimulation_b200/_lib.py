@@ -102,6 +102,9 @@ ENGINE_SYMBOLS = {
     "gsb200_shard_select": (I32, [VP, U32, VP, VP, U64, U32, U32, I32]),
     "gsb200_shard_select_dev": (I32, [VP, U32, VP, VP, U64, U32, U32, I32]),
     "gsb200_shard_cross": (I32, [VP, U32, U32, VP, C.POINTER(Draws), VP, VP]),
+    "gsb200_shard_cross_begin": (I32, [VP, U32, U32, VP, C.POINTER(Draws), I32]),
+    "gsb200_shard_cross_picks": (I32, [VP, VP, VP, VP]),
+    "gsb200_shard_finish": (I32, [VP]),
     "gsb200_shard_cross_dev": (I32, [VP, U32, U32, VP, U32, C.POINTER(Draws), VP]),
     "gsb200_shard_selected": (I32, [VP, VP, VP, VP]),
     "gsb200_shard_local_bvs": (I32, [VP, U32, VP]),
@@ -175,6 +178,7 @@ HOST_SYMBOLS = {
     "gsb_shard_handle": (I32, [VP, VP]),
     "gsb_shard_connect": (I32, [VP, VP]),
     "gsb_shard_select_and_cross": (UINT, [VP, UINT, C.c_ulonglong, UINT, UINT, C.c_bool, C.c_ulonglong, UINT, GenOptions]),
+    "gsb_shard_finish": (I32, [VP]),
     "gsb_shard_get_local_bvs": (UINT, [VP, UINT, VP]),
     "gsb_shard_last_selection": (UINT, [VP, C.c_ulonglong, VP, UINT, VP]),
 }

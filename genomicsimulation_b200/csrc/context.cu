@@ -21,20 +21,22 @@ void set_error(const char* fmt, ...) {
 
 int Scratch::ensure(size_t need) {
     if (need <= bytes) return GSB200_OK;
-    if (ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
+    release();
     size_t want = need + need / 4 + 256;
-    cudaError_t e = cudaMalloc(&ptr, want);
+    cudaError_t e = stream ? cudaMallocAsync(&ptr, want, stream) : cudaMalloc(&ptr, want);
     if (e != cudaSuccess) {
         ptr = nullptr;
-        set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cudaGetLastError();
+        set_error("device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
         return e == cudaErrorMemoryAllocation ? GSB200_ERR_OOM : GSB200_ERR_CUDA;
     }
+    ordered = stream != nullptr;
     bytes = want;
     return GSB200_OK;
 }
 
 void Scratch::release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) { if (ordered) cudaFreeAsync(ptr, stream); else cudaFree(ptr); }
     ptr = nullptr;
     bytes = 0;
 }
@@ -115,6 +117,21 @@ int gsb200_create(gsb200_ctx** out, int device_ordinal, uint32_t n_markers) {
         delete ctx;
         return GSB200_ERR_CUDA;
     }
+    // every scratch buffer lives in the stream-ordered pool of this stream; freed blocks stay cached in the pool
+    for (auto& sc : ctx->s_rows) sc.stream = ctx->stream;
+    for (auto& sc : ctx->s_plan) sc.stream = ctx->stream;
+    for (auto& sc : ctx->s_eval) sc.stream = ctx->stream;
+    for (auto& sc : ctx->s_chain) sc.stream = ctx->stream;
+    for (auto& sc : ctx->s_bv) sc.stream = ctx->stream;
+    ctx->s_io.stream = ctx->s_null.stream = ctx->s_select.stream = ctx->local_sched.d_steps.stream = ctx->stream;
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     e = cudaMalloc((void**) &ctx->d_flag, 4 * sizeof(int));      // [0] error flag, [1] task counter of persistent kernels
     if (e == cudaSuccess) e = cudaMemset(ctx->d_flag, 0, 4 * sizeof(int));
     if (e != cudaSuccess) {
@@ -142,6 +159,7 @@ void gsb200_destroy(gsb200_ctx* ctx) {
     ctx->s_null.release();
     ctx->s_select.release();
     ctx->local_sched.d_steps.release();
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);        // the stream-ordered frees above
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->d_store) cudaFree(ctx->d_store);
     if (ctx->d_dict_sym) cudaFree(ctx->d_dict_sym);

@@ -41,10 +41,15 @@ void set_error(const char* fmt, ...);
 constexpr int kNumSMsB200 = 148;
 constexpr uint32_t kPlaneAlignWords = 32;   // planes padded to 128 B
 
-// A device buffer that only ever grows; contents are scratch.
+// A device buffer that only ever grows; contents are scratch.  With a stream (every scratch buffer of a
+// context gets the context's) the memory comes from the stream-ordered allocator: growing a buffer then
+// frees the old one IN STREAM ORDER instead of with cudaFree, which waits for the whole device — including,
+// when several shards share a process, a peer's kernel that is spinning on OUR next push (csrc/shard.cu).
 struct Scratch {
     void* ptr = nullptr;
     size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+    bool ordered = false;       // ptr came from cudaMallocAsync
     int ensure(size_t need);
     void release();
 };
@@ -199,5 +204,5 @@ int select_top_n(gsb200_ctx* ctx, const double* d_values, uint32_t n, uint32_t t
 // d_picks (device, 2n, may be null) receives the pool positions of both parents.  Asynchronous.
 int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_pool, uint32_t n, uint32_t map,
                       const uint32_t* d_out_rows, uint32_t first_out_row, const gsb200_draws* draws, uint32_t* d_picks,
-                      const char* what);
+                      const char* what, uint32_t* h_picks = nullptr /* pinned, 2n: copy of d_picks */, cudaEvent_t picks_ready = nullptr);
 }  // namespace gsb

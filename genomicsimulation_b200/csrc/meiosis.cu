@@ -108,10 +108,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
     return c;
 }
 
-// uniform in the open interval (0,1), 53 random bits
+// uniform in the OPEN interval (0,1): (v + 1/2) / 2^52 with v the top 52 bits, so the extremes are
+// 2^-53 and 1 - 2^-53, both exact in fp64 (with 53 bits, (2^53 - 1) + 1/2 would round up to 2^53 and
+// give exactly 1.0 once in 2^53 draws)
 __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
-    const uint64_t v = (((uint64_t) hi << 32) | lo) >> 11;
-    return ((double) v + 0.5) * (1.0 / 9007199254740992.0);
+    const uint64_t v = (((uint64_t) hi << 32) | lo) >> 12;
+    return ((double) v + 0.5) * (1.0 / 4503599627370496.0);
 }
 
 __device__ __forceinline__ uint4 draw_block(const DrawView& d, uint64_t unit, uint32_t gamete, uint32_t chr, uint32_t index) {
@@ -1053,7 +1055,7 @@ namespace gsb {
 
 int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_pool, uint32_t n, uint32_t map,
                       const uint32_t* d_out_rows, uint32_t first_out_row, const gsb200_draws* draws, uint32_t* d_picks,
-                      const char* what) {
+                      const char* what, uint32_t* h_picks, cudaEvent_t picks_ready) {
     if (n == 0) return GSB200_OK;
     GSB_REQUIRE(n_pool >= 2, GSB200_ERR_ARG, "%s: a pool of %u cannot be crossed at random", what, n_pool);
     GSB_REQUIRE(draws && draws->mode == GSB200_DRAWS_PHILOX, GSB200_ERR_ARG, "%s: needs PHILOX draws", what);
@@ -1069,6 +1071,10 @@ int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_poo
                                                                    d_picks, d_picks ? d_picks + n : nullptr, d_out_rows ? nullptr : d_run);
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
+    if (h_picks && d_picks) {      // the picks leave before the splice is enqueued: the host has them while the offspring are being made
+        GSB_CUDA_TRY(cudaMemcpyAsync(h_picks, d_picks, (size_t) 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (picks_ready) GSB_CUDA_TRY(cudaEventRecord(picks_ready, ctx->stream));
+    }
     return cross_impl(ctx, n, d_p1, d_p2, map, map, d_out_rows ? d_out_rows : d_run, draws, false, what, nullptr, pool_base);
 }
 

@@ -31,8 +31,8 @@ __host__ __device__ constexpr int pass_shift(int pass) { return pass < 5 ? 64 - 
 
 // order-preserving map of fp64 to u64; the BEST value gets the SMALLEST key
 __device__ __forceinline__ unsigned long long rank_key(double v, int low_is_best) {
-    if (v == 0.0) v = 0.0;                         // -0.0 and +0.0 compare equal in the reference's comparators (core.c:1308-1349): one key
     unsigned long long k = (unsigned long long) __double_as_longlong(v);
+    if ((k << 1) == 0ull) k = 0ull;                // -0.0 and +0.0 compare equal in the reference's comparators (core.c:1308-1349): one key
     k = (k >> 63) ? ~k : (k | 0x8000000000000000ull);
     return low_is_best ? k : ~k;
 }

@@ -152,6 +152,12 @@ struct gsb200_shard {
     uint32_t* d_sel = nullptr;           // [max_pool] selected global indexes, ascending
     uint32_t* d_sel_ids = nullptr;       // [max_pool]
     Scratch s_local_rows;
+    // pinned host staging, so that what the host mirror needs of a generation (local GEBVs, the picked pairs, the
+    // selected parents' ids) comes down while the device carries on: [bvs: max_total f64 | picks: 2 max_total u32 | sel ids: max_pool u32]
+    char* h_pin = nullptr;
+    cudaEvent_t ev_bv = nullptr, ev_picks = nullptr;
+    bool bv_staged = false, picks_staged = false;
+    uint32_t staged_local = 0, staged_offspring = 0;
     // optional phase timing: a ring of CUDA events, one set per generation (epoch)
     bool timing = false;
     cudaEvent_t ev[kTimingRing][kTimingEvents];
@@ -196,6 +202,9 @@ int gsb200_shard_create(gsb200_ctx* ctx, uint32_t rank, uint32_t world, uint64_t
     if (e == cudaSuccess) e = cudaMalloc((void**) &s->d_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(s->d_err, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**) &s->d_sel, 2 * (size_t) max_pool * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**) &s->h_pin, max_total * 16 + (size_t) max_pool * 4, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_bv, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_picks, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         set_error("gsb200_shard_create: allocating %zu bytes of exchange buffers failed: %s", s->slab_bytes, cudaGetErrorString(e));
         gsb200_shard_destroy(s);
@@ -205,6 +214,7 @@ int gsb200_shard_create(gsb200_ctx* ctx, uint32_t rank, uint32_t world, uint64_t
     // Every scratch buffer a generation touches is sized here, for the largest generation: nothing is
     // allocated (and, above all, nothing is cudaFree'd — which waits for the whole device, including a
     // peer shard of this process that is spinning on OUR next push) while generations are in flight.
+    s->s_local_rows.stream = ctx->stream;
     int st = ctx->s_select.ensure(select_scratch_bytes((uint32_t) max_total));
     if (st == GSB200_OK) st = s->s_local_rows.ensure(max_total * sizeof(uint32_t));
     if (st == GSB200_OK) st = ctx->s_eval[2].ensure(max_total * 8 * sizeof(long long) + (size_t) (ctx->plane_words / 16 + 1) * sizeof(unsigned int));
@@ -225,6 +235,9 @@ void gsb200_shard_destroy(gsb200_shard* s) {
     for (uint32_t r = 0; r < kMaxWorld; ++r) if (s->opened[r]) cudaIpcCloseMemHandle(s->peers.base[r]);
     s->s_local_rows.release();
     if (s->ev_made) for (auto& set : s->ev) for (auto& e : set) cudaEventDestroy(e);
+    if (s->h_pin) cudaFreeHost(s->h_pin);
+    if (s->ev_bv) cudaEventDestroy(s->ev_bv);
+    if (s->ev_picks) cudaEventDestroy(s->ev_picks);
     if (s->slab) cudaFree(s->slab);
     if (s->d_counters) cudaFree(s->d_counters);
     if (s->d_err) cudaFree(s->d_err);
@@ -284,6 +297,7 @@ int gsb200_shard_connect(gsb200_shard* s, const void* handles) {
 static int shard_select_impl(gsb200_shard* s, uint32_t n_local, const uint32_t* d_local_rows, const uint32_t* local_ids,
                              uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best, const char* what) {
     gsb200_ctx* ctx = s->ctx;
+    s->bv_staged = false;
     GSB_REQUIRE(s->connected, GSB200_ERR_ARG, "%s: the shard is not connected to its peers yet", what);
     GSB_REQUIRE(n_total >= 1 && n_total <= s->max_total, GSB200_ERR_ARG, "%s: generation of %llu exceeds the %llu the shard was created for",
                 what, (unsigned long long) n_total, (unsigned long long) s->max_total);
@@ -310,6 +324,13 @@ static int shard_select_impl(gsb200_shard* s, uint32_t n_local, const uint32_t* 
     double* all_bv = reinterpret_cast<double*>(s->slab + kOffBv);
     mark(s, epoch, 0);
     if (n_local) GSB_TRY(gsb200_gebv_dev(ctx, n_local, d_local_rows, eff_index, all_bv + lo));
+    if (d_local_rows == (const uint32_t*) s->s_local_rows.ptr) {
+        // the host-row entry point: this rank's GEBVs start their way down now, behind nothing but the GEBV kernels
+        if (n_local) GSB_CUDA_TRY(cudaMemcpyAsync(s->h_pin, all_bv + lo, (size_t) n_local * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        GSB_CUDA_TRY(cudaEventRecord(s->ev_bv, ctx->stream));
+        s->bv_staged = true;
+        s->staged_local = n_local;
+    }
     const int with_ids = local_ids != nullptr;
     if (with_ids && n_local)
         GSB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(s->slab + s->off_ids) + lo, local_ids, (size_t) n_local * sizeof(uint32_t),
@@ -354,13 +375,13 @@ int gsb200_shard_select(gsb200_shard* s, uint32_t n_local, const uint32_t* local
     return shard_select_impl(s, n_local, d_rows, local_ids, n_total, eff_index, top_n, low_is_best, "gsb200_shard_select");
 }
 
-int gsb200_shard_cross_dev(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t* d_out_rows, uint32_t first_out_row,
-                           const gsb200_draws* draws, uint32_t* d_picks) {
-    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
-    const char* what = "gsb200_shard_cross_dev";
+static int shard_cross_impl(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t* d_out_rows, uint32_t first_out_row,
+                            const gsb200_draws* draws, uint32_t* d_picks, bool stage_picks, const char* what) {
     GSB_REQUIRE(s->have_selection, GSB200_ERR_ARG, "%s: nothing has been selected yet", what);
     gsb200_ctx* ctx = s->ctx;
     GSB_REQUIRE(ctx->row_words() == s->row_words, GSB200_ERR_ARG, "%s: the store changed its width since the shard was created", what);
+    GSB_REQUIRE(!stage_picks || n <= s->max_total, GSB200_ERR_ARG, "%s: %u offspring exceed the %llu the shard was created for", what, n,
+                (unsigned long long) s->max_total);
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
     if (s->world > 1 && s->pool_waited < s->epoch) {
         shard_wait_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const volatile uint32_t*>(s->slab + kOffFlags) + kMaxWorld,
@@ -369,14 +390,26 @@ int gsb200_shard_cross_dev(gsb200_shard* s, uint32_t n, uint32_t map, const uint
         s->pool_waited = s->epoch;
     }
     mark(s, s->epoch, 5);
+    uint32_t* h_picks = nullptr;
+    if (stage_picks) {
+        h_picks = reinterpret_cast<uint32_t*>(s->h_pin + s->max_total * 8);
+        GSB_CUDA_TRY(cudaMemcpyAsync(s->h_pin + s->max_total * 16, s->d_sel_ids, (size_t) s->top_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     GSB_TRY(pool_random_cross(ctx, reinterpret_cast<const uint32_t*>(s->slab + s->off_pool), s->top_n, n, map, d_out_rows, first_out_row,
-                              draws, d_picks, what));
+                              draws, d_picks, what, h_picks, s->ev_picks));
+    s->picks_staged = stage_picks;
+    s->staged_offspring = n;
     mark(s, s->epoch, 6);
     return GSB200_OK;
 }
 
-int gsb200_shard_cross(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t* out_rows, const gsb200_draws* draws,
-                       uint32_t* picked1, uint32_t* picked2) {
+int gsb200_shard_cross_dev(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t* d_out_rows, uint32_t first_out_row,
+                           const gsb200_draws* draws, uint32_t* d_picks) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    return shard_cross_impl(s, n, map, d_out_rows, first_out_row, draws, d_picks, false, "gsb200_shard_cross_dev");
+}
+
+int gsb200_shard_cross_begin(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t* out_rows, const gsb200_draws* draws, int want_picks) {
     GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
     if (n == 0) return GSB200_OK;
     gsb200_ctx* ctx = s->ctx;
@@ -385,17 +418,44 @@ int gsb200_shard_cross(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t
     uint32_t* d_out;
     GSB_TRY(upload_u32(ctx, ctx->s_rows[2], out_rows, n, &d_out));
     uint32_t* d_picks = nullptr;
-    if (picked1 && picked2) {
+    if (want_picks) {
         GSB_TRY(ctx->s_rows[1].ensure((size_t) 2 * n * sizeof(uint32_t)));
         d_picks = (uint32_t*) ctx->s_rows[1].ptr;
     }
-    GSB_TRY(gsb200_shard_cross_dev(s, n, map, d_out, 0, draws, d_picks));
-    if (d_picks) {
-        GSB_CUDA_TRY(cudaMemcpyAsync(picked1, d_picks, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        GSB_CUDA_TRY(cudaMemcpyAsync(picked2, d_picks + n, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    GSB_TRY(gsb200_cross_dev_status(ctx));           // synchronises; a plan overflow is reported, not silently kept
+    return shard_cross_impl(s, n, map, d_out, 0, draws, d_picks, want_picks != 0, "gsb200_shard_cross");
+}
+
+int gsb200_shard_cross_picks(gsb200_shard* s, const uint32_t** picked1, const uint32_t** picked2, const uint32_t** selected_ids) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    GSB_REQUIRE(s->picks_staged, GSB200_ERR_ARG, "gsb200_shard_cross_picks: the last cross was not asked for its picks");
+    GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    GSB_CUDA_TRY(cudaEventSynchronize(s->ev_picks));
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(s->h_pin + s->max_total * 8);
+    if (picked1) *picked1 = p;
+    if (picked2) *picked2 = p + s->staged_offspring;
+    if (selected_ids) *selected_ids = reinterpret_cast<const uint32_t*>(s->h_pin + s->max_total * 16);
+    return GSB200_OK;
+}
+
+int gsb200_shard_finish(gsb200_shard* s) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    GSB_TRY(gsb200_cross_dev_status(s->ctx));           // synchronises; a plan overflow is reported, not silently kept
     return gsb200_shard_status(s);
+}
+
+int gsb200_shard_cross(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t* out_rows, const gsb200_draws* draws,
+                       uint32_t* picked1, uint32_t* picked2) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    if (n == 0) return GSB200_OK;
+    const int want = picked1 && picked2;
+    GSB_TRY(gsb200_shard_cross_begin(s, n, map, out_rows, draws, want));
+    if (want) {
+        const uint32_t *p1, *p2;
+        GSB_TRY(gsb200_shard_cross_picks(s, &p1, &p2, nullptr));
+        memcpy(picked1, p1, (size_t) n * sizeof(uint32_t));
+        memcpy(picked2, p2, (size_t) n * sizeof(uint32_t));
+    }
+    return gsb200_shard_finish(s);
 }
 
 int gsb200_shard_selected(gsb200_shard* s, uint32_t* global_indexes, uint32_t* ids, double* all_bvs) {
@@ -442,6 +502,11 @@ int gsb200_shard_local_bvs(gsb200_shard* s, uint32_t n_local, double* out) {
     GSB_REQUIRE(n_local == hi - lo, GSB200_ERR_ARG, "gsb200_shard_local_bvs: this rank evaluated %llu individuals, not %u",
                 (unsigned long long) (hi - lo), n_local);
     GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    if (s->bv_staged && s->staged_local == n_local) {           // already on their way since the selection was enqueued
+        GSB_CUDA_TRY(cudaEventSynchronize(s->ev_bv));
+        memcpy(out, s->h_pin, (size_t) n_local * sizeof(double));
+        return GSB200_OK;
+    }
     if (n_local) GSB_CUDA_TRY(cudaMemcpyAsync(out, reinterpret_cast<const double*>(s->slab + kOffBv) + lo, (size_t) n_local * sizeof(double),
                                               cudaMemcpyDeviceToHost, s->ctx->stream));
     GSB_CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));

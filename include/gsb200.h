@@ -289,12 +289,21 @@ int  gsb200_shard_select_dev(gsb200_shard* shard, uint32_t n_local, const uint32
  * NULL): positions of the parents in the selection.  Synchronises. */
 int  gsb200_shard_cross(gsb200_shard* shard, uint32_t n, uint32_t map, const uint32_t* out_rows, const gsb200_draws* draws,
                         uint32_t* picked1, uint32_t* picked2);
+/* The same in three steps, for a host that has work of its own per generation (the host mirror's metadata):
+ * _begin enqueues everything and returns at once; _picks waits only until the pairs have been drawn — long
+ * before the offspring are spliced — and hands out the picks and the selected parents' ids (pinned buffers
+ * owned by the shard, valid until the next _begin); _finish waits for the offspring and reports a splice-plan
+ * overflow or a peer that never delivered.  The next gsb200_shard_select may be enqueued before _finish. */
+int  gsb200_shard_cross_begin(gsb200_shard* shard, uint32_t n, uint32_t map, const uint32_t* out_rows, const gsb200_draws* draws, int want_picks);
+int  gsb200_shard_cross_picks(gsb200_shard* shard, const uint32_t** picked1, const uint32_t** picked2, const uint32_t** selected_ids);
+int  gsb200_shard_finish(gsb200_shard* shard);
 /* ... asynchronous: d_out_rows NULL = rows first_out_row, first_out_row + 1, ...; d_picks (device, 2n) may be NULL */
 int  gsb200_shard_cross_dev(gsb200_shard* shard, uint32_t n, uint32_t map, const uint32_t* d_out_rows, uint32_t first_out_row,
                             const gsb200_draws* draws, uint32_t* d_picks);
 /* the last selection: global indexes (ascending), their ids, the GEBVs of the whole generation; any may be NULL. Synchronises. */
 int  gsb200_shard_selected(gsb200_shard* shard, uint32_t* global_indexes, uint32_t* ids, double* all_bvs);
-/* the GEBVs the last selection computed for THIS rank's n_local individuals, in their order. Synchronises. */
+/* the GEBVs the last selection computed for THIS rank's n_local individuals, in their order.  After
+ * gsb200_shard_select (host rows) they are already on their way down and this waits for that copy only. */
 int  gsb200_shard_local_bvs(gsb200_shard* shard, uint32_t n_local, double* out);
 uint64_t gsb200_shard_generation_size(const gsb200_shard* shard);   /* n_total of the last selection */
 uint32_t gsb200_shard_pool_size(const gsb200_shard* shard);         /* top_n of the last selection */

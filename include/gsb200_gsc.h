@@ -38,7 +38,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-typedef unsigned int gsb_GroupNum;   /* gsc_GroupNum.num  (core.h:557-560); 0 = GSC_NO_GROUP */
+typedef unsigned int gsb_GroupNum;   /* gsc_GroupNum.num  (core.h:561-563); 0 = GSC_NO_GROUP */
 typedef unsigned int gsb_MapID;      /* gsc_MapID.id; 0 = GSC_NO_MAP -> first map (core.c:8514-8520) */
 typedef unsigned int gsb_EffectID;   /* gsc_EffectID.id; 0 = GSC_NO_EFFECTSET */
 #define GSB_NA_GLOBALX ((unsigned int) -1)   /* GSC_NA_GLOBALX (core.h:160) */
@@ -58,7 +58,7 @@ typedef struct {
 } gsb_GenOptions;
 extern const gsb_GenOptions GSB_BASIC_OPT;   /* GSC_BASIC_OPT (core.c:11-23) */
 
-/* gsc_DecimalMatrix (core.h:475-480) with flat row-major storage. Free with gsb_delete_dmatrix. */
+/* gsc_DecimalMatrix (core.h:536-540) with flat row-major storage. Free with gsb_delete_dmatrix. */
 typedef struct {
     unsigned int dim1, dim2;
     double* data;
@@ -180,6 +180,10 @@ int gsb_shard_connect(gsb_SimData* d, const void* handles);
 gsb_GroupNum gsb_shard_select_and_cross(gsb_SimData* d, gsb_GroupNum group, unsigned long long n_total, gsb_EffectID effID,
                                         unsigned int top_n, _Bool lowIsBest, unsigned long long n_offspring_total,
                                         gsb_MapID which_map, gsb_GenOptions g);
+/* The call above returns while the offspring are still being spliced (everything later on this SimData is
+ * ordered behind them); this waits for them and reports a failed exchange or splice.  Called by the next
+ * gsb_shard_select_and_cross and by gsb_delete_simdata by themselves.  0 on success. */
+int gsb_shard_finish(gsb_SimData* d);
 unsigned int gsb_shard_get_local_bvs(gsb_SimData* d, unsigned int n_local, double* output);
 unsigned int gsb_shard_last_selection(gsb_SimData* d, unsigned long long n_total, double* bvs_out, unsigned int top_n, unsigned int* selected_out);
 

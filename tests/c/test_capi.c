@@ -11,7 +11,7 @@
 #define CHECK(cond) do { if (!(cond)) { fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); return 1; } } while (0)
 
 static unsigned long long lcg = 88172645463325252ull;
-static double urand(void) { lcg ^= lcg << 13; lcg ^= lcg >> 7; lcg ^= lcg << 17; return ((lcg >> 11) + 0.5) / 9007199254740992.0; }
+static double urand(void) { lcg ^= lcg << 13; lcg ^= lcg >> 7; lcg ^= lcg << 17; return ((lcg >> 12) + 0.5) / 4503599627370496.0; }
 
 int main(void) {
     enum { F = 16, M = 2000, C = 4 };
