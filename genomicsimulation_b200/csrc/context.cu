@@ -48,7 +48,7 @@ void DeviceMap::release() {
 }
 
 void DeviceEffects::release() {
-    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag, d_digit_tc5, d_local, d_bvq };
+    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag, d_digit_tc5, d_local, d_local_tc5, d_bvq };
     for (void* p : ptrs) if (p) cudaFree(p);
     *this = DeviceEffects();
 }
@@ -123,7 +123,7 @@ int gsb200_create(gsb200_ctx** out, int device_ordinal, uint32_t n_markers) {
     for (auto& sc : ctx->s_eval) sc.stream = ctx->stream;
     for (auto& sc : ctx->s_chain) sc.stream = ctx->stream;
     for (auto& sc : ctx->s_bv) sc.stream = ctx->stream;
-    ctx->s_io.stream = ctx->s_null.stream = ctx->s_select.stream = ctx->local_sched.d_steps.stream = ctx->stream;
+    ctx->s_io.stream = ctx->s_null.stream = ctx->s_select.stream = ctx->local_sched.d_steps.stream = ctx->local_sched.d_steps_tc5.stream = ctx->stream;
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess) {
@@ -159,6 +159,7 @@ void gsb200_destroy(gsb200_ctx* ctx) {
     ctx->s_null.release();
     ctx->s_select.release();
     ctx->local_sched.d_steps.release();
+    ctx->local_sched.d_steps_tc5.release();
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);        // the stream-ordered frees above
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->d_store) cudaFree(ctx->d_store);

@@ -263,7 +263,8 @@ constexpr uint32_t kLocalRowStride = 20;
 constexpr uint32_t kLocalBufWords = 32 * kLocalRowStride;     // 16 individuals x 2 strands x one 64-byte chunk
 constexpr int kLocalWarps = 4;
 constexpr int kLocalMaxSets = 4;
-constexpr uint32_t kLocalTileBytes = 16 * 1024;  // B fragments per shared-memory tile, all effect sets of the pass
+constexpr uint32_t kLocalTileBytes = 16 * 1024;
+constexpr uint32_t kLocalTc5MinSets = 5;         // from this many effect sets on the pass goes to local_tc5_kernel  // B fragments per shared-memory tile, all effect sets of the pass
 
 struct LocalSetParams {
     const uint2* bfrag[kLocalMaxSets];     // [n_steps][32]
@@ -715,6 +716,10 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
         if (sc.usable) {
             GSB_TRY(sc.d_steps.ensure(sc.steps.size() * sizeof(uint2)));
             GSB_CUDA_TRY(cudaMemcpyAsync(sc.d_steps.ptr, sc.steps.data(), sc.steps.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+            std::vector<uint2> flagged(sc.steps);
+            for (size_t b = 0; b + 1 < sc.block_first.size(); ++b) flagged[sc.block_first[b]].y |= 0x80000000u;
+            GSB_TRY(sc.d_steps_tc5.ensure(flagged.size() * sizeof(uint2)));
+            GSB_CUDA_TRY(cudaMemcpyAsync(sc.d_steps_tc5.ptr, flagged.data(), flagged.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
             GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         }
         sc.key = key;
@@ -789,7 +794,57 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
             base[b] = acc;
         }
         GSB_TRY(to_device_vec(frag, &e->d_local));
+        {
+            std::vector<double> delta(M);
+            for (uint32_t m = 0; m < M; ++m) delta[m] = vf[2 * (size_t) m + 1] - vf[2 * (size_t) m];
+            std::vector<uint32_t> frag5;
+            build_local_tc5_fragments(delta, steps, block_offsets, block_markers, exp2v, frag5);
+            GSB_TRY(to_device_vec(frag5, &e->d_local_tc5));
+        }
         e->local_key = key;
+    }
+
+    // Which kernel: with several effect sets the contraction is dense enough for tcgen05 (local_tc5.cu), where
+    // all the sets of a pass share one A operand; GSB200_LOCAL_PATH=mma|tc5 forces either (measurements, tests).
+    static const int forced_path = [] { const char* v = getenv("GSB200_LOCAL_PATH"); return !v ? 0 : strcmp(v, "tc5") == 0 ? 2 : strcmp(v, "mma") == 0 ? 1 : 0; }();
+    const bool use_tc5 = forced_path == 2 || (forced_path == 0 && n_effect_sets >= kLocalTc5MinSets);
+    if (use_tc5) {
+        const size_t out_bytes = (size_t) n * 2 * n_blocks * sizeof(double);
+        for (uint32_t q0 = 0; q0 < n_effect_sets; q0 += kLocalTc5MaxSets) {
+            const uint32_t sets = std::min<uint32_t>(kLocalTc5MaxSets, n_effect_sets - q0);
+            // host output: the pass's matrices are staged on the device in slabs of individuals
+            const size_t slab = device_out ? (size_t) n : std::max<size_t>(64, std::min<size_t>(n, (((size_t) 1 << 30) / (2 * (size_t) n_blocks * sizeof(double))) / sets / 64 * 64));
+            const size_t slab_bytes = slab * 2 * (size_t) n_blocks * sizeof(double);
+            if (!device_out) GSB_TRY(ctx->s_eval[1].ensure(slab_bytes * sets));
+            for (uint32_t done = 0; done < n; done += (uint32_t) slab) {
+                const uint32_t cnt = (uint32_t) std::min<size_t>(slab, n - done);
+                const uint32_t* d_b[kLocalTc5MaxSets];
+                const double* d_base[kLocalTc5MaxSets];
+                double* d_out[kLocalTc5MaxSets];
+                double scale[kLocalTc5MaxSets];
+                for (uint32_t q = 0; q < sets; ++q) {
+                    DeviceEffects* e = effs[q0 + q];
+                    d_b[q] = e->d_local_tc5;
+                    d_base[q] = (const double*) ((const char*) e->d_local + frag_bytes);
+                    scale[q] = e->local_scale;
+                    d_out[q] = device_out ? outs[q0 + q] : (double*) ((char*) ctx->s_eval[1].ptr + slab_bytes * q);
+                    GSB_CUDA_TRY(cudaMemsetAsync(d_out[q], 0, device_out ? out_bytes : (size_t) cnt * 2 * n_blocks * sizeof(double), ctx->stream));
+                }
+                GSB_TRY(local_tc5_launch(ctx, cnt, d_rows + done, n_blocks, (const uint2*) sc.d_steps_tc5.ptr, n_steps, sets, d_b, d_base, d_out, scale));
+                if (!device_out)
+                    for (uint32_t q = 0; q < sets; ++q)
+                        GSB_CUDA_TRY(cudaMemcpyAsync(outs[q0 + q] + (size_t) done * 2 * n_blocks, d_out[q],
+                                                     (size_t) cnt * 2 * n_blocks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                int flag = 0;
+                GSB_CUDA_TRY(cudaMemcpyAsync(&flag, ctx->d_flag + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                if (flag) {
+                    GSB_CUDA_TRY(cudaMemsetAsync(ctx->d_flag + 2, 0, sizeof(int), ctx->stream));
+                    GSB_REQUIRE(false, GSB200_ERR_CUDA, "%s (tcgen05 path): a pipeline wait timed out", what);
+                }
+            }
+        }
+        return GSB200_OK;
     }
 
     const size_t slab_rows = std::max<size_t>(8, std::min<size_t>(n, (((size_t) 1 << 30) / (2 * (size_t) n_blocks * sizeof(double))) / 8 * 8));

@@ -118,6 +118,7 @@ struct DeviceEffects {
     std::vector<double> h_value_first; // host copy of d_value_first (source of the local-GEBV digit fragments)
     uint64_t  local_key = 0;           // block definition d_local was built for
     uint32_t* d_local = nullptr;       // local GEBV: per-step digit fragments, then the per-block bases (fp64)
+    uint32_t* d_local_tc5 = nullptr;   // ... the fragments in the shared-memory layout of local_tc5_kernel
     double    local_scale = 1.0;
     void release();
 };
@@ -138,7 +139,10 @@ struct LocalSchedule {
     std::vector<uint2> steps;           // (marker word, block)
     std::vector<uint32_t> block_first;  // first step of each non-empty block, then n_steps
     Scratch d_steps;
+    Scratch d_steps_tc5;                // the same with bit 31 of .y set on the first step of every block (local_tc5.cu)
 };
+
+constexpr uint32_t kLocalTc5MaxSets = 12;   // effect sets per pass of the tcgen05 local-GEBV kernel (N = 8 * sets <= 96)
 
 }  // namespace gsb
 
@@ -193,6 +197,11 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff);    // evaluate.cu
 void build_tc5_fragments(const std::vector<double>& delta, uint32_t n_markers, uint32_t plane_words, int exp2,
                          std::vector<uint32_t>& frag);     // gebv_tc5.cu
 int gebv_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, const uint32_t* d_frag, unsigned long long* d_digits);
+// local_tc5.cu
+void build_local_tc5_fragments(const std::vector<double>& delta, const std::vector<uint2>& steps, const uint32_t* block_offsets,
+                               const uint32_t* block_markers, int exp2, std::vector<uint32_t>& frag);
+int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t n_blocks, const uint2* d_steps, uint32_t n_steps,
+                     uint32_t n_sets, const uint32_t* const* d_b, const double* const* d_base, double* const* d_out, const double* scale);
 int upload_u32(gsb200_ctx* ctx, Scratch& s, const uint32_t* host, size_t n, uint32_t** out);
 int check_rows(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const char* what);
 // select.cu

@@ -1,0 +1,325 @@
+// local_tc5.cu — local (marker-block) GEBVs for MANY effect sets on the 5th-generation tensor cores:
+// the dense-contraction path of BASELINE.json configs[4] (gsc_calculate_utility_local_bvs,
+// core.c:9979-10090, computed for up to 10 effect sets in one pass over the genotypes).
+//
+// The contraction: (strands x markers) bits  x  (markers x 8 * sets) fixed-point digits, int32
+// accumulation per marker block, recombined in fp64 per (strand, block, set).  gebv_tc5.cu showed
+// that tcgen05.mma with N = 8 is bound by streaming its A operand (~90 cycles per 128 x 32-byte tile
+// whatever N is); with N = 8 * sets the same operand is reused by every effect set — ten sets cost
+// what one does.
+//
+//   * a CTA owns a marker SEGMENT — up to ~200 KB of B digits resident in shared memory — and walks
+//     tiles of 64 individuals (128 strand rows = the 128 TMEM lanes);
+//   * 4 expander warps: thread t loads 32 contiguous bytes (8 marker words) of ITS strand row, turns
+//     each word into 8 operand registers `w & (0x01010101 << s)` (byte b = bit 8b + s at weight 2^s; the
+//     weight is divided out of the digits on the host) and writes them to its own TMEM lane with
+//     tcgen05.st.32x32b — one K = 32 step per word, so a step is 32 CONTIGUOUS markers and block
+//     boundaries cost at most one extra step (the word that straddles them, its B digits zeroed outside
+//     the block), exactly the step schedule of the mma.sync kernel (evaluate.cu);
+//   * 1 issuer thread: per step one tcgen05.mma.kind::i8, M = 128, N = 8 * sets, K = 32, A from TMEM,
+//     B through a shared-memory descriptor; the accumulator switches (double-buffered) at every block
+//     boundary;
+//   * 4 epilogue warps: tcgen05.ld of a finished block's 8 * sets digit sums per strand, Horner in fp64,
+//     scale, add to the output matrices (fp64 atomics: a block may span two segments; the outputs are
+//     zeroed by the caller and the per-block base is added by the segment the block starts in).
+//
+// Every mbarrier wait is bounded (tc5_common.cuh): a protocol bug raises the context's flag instead of
+// hanging the GPU.
+#include "gsb200_internal.cuh"
+#include "tc5_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+using namespace gsb;
+using namespace gsb::tc5;
+
+namespace gsb {
+
+namespace {
+
+constexpr uint32_t kExpanders = 128, kEpilogue = 128;
+constexpr uint32_t kThreads = kExpanders + kEpilogue + 32;
+constexpr uint32_t kAStages = 4;
+constexpr uint32_t kStageCols = 64;            // 8 words x 8 columns
+constexpr uint32_t kDCol1 = 128;               // second accumulator
+constexpr uint32_t kACol0 = 256;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kMaxSegSteps = 256;
+constexpr uint32_t kBBytes = 200 * 1024;         // B digits of a segment (+ 256 bytes of slack)
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// four marker words of this thread's strand row -> 4 K-steps of operand bytes in its TMEM lane
+__device__ __forceinline__ void store_words(uint32_t taddr, const uint4 w) {
+    uint32_t r[32];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const uint32_t m = 0x01010101u << s;
+        r[s] = w.x & m; r[8 + s] = w.y & m; r[16 + s] = w.z & m; r[24 + s] = w.w & m;
+    }
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :: "r"(taddr),
+           "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+struct LocalTc5Params {
+    const uint4* b[kLocalTc5MaxSets];      // per set: [n_steps][16] uint4 = 256 bytes per step, UMMA K-major layout
+    const double* base[kLocalTc5MaxSets];  // [n_blocks]
+    double* out[kLocalTc5MaxSets];         // [(2n) x n_blocks], zeroed
+    double scale[kLocalTc5MaxSets];
+};
+
+// steps[s] = (word, block | first_step_of_block << 31)
+__global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
+        const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
+        const uint32_t* __restrict__ rows, uint32_t n, uint32_t n_blocks,
+        const uint2* __restrict__ steps, uint32_t n_steps, uint32_t seg_steps, uint32_t n_tiles,
+        uint32_t n_items, uint32_t items_per_cta, uint32_t n_sets, const LocalTc5Params P, int* __restrict__ flag) {
+    extern __shared__ __align__(128) uint4 s_b[];                    // seg_steps x n_sets x 256 bytes
+    __shared__ __align__(8) uint64_t s_full[kAStages], s_free[kAStages], s_dready[2], s_dfree[2];
+    __shared__ uint2 s_steps[kMaxSegSteps];
+    __shared__ uint32_t s_tmem;
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (uint32_t i = 0; i < kAStages; ++i) { mbar_init(&s_full[i], kExpanders / 32); mbar_init(&s_free[i], 1); }
+        for (uint32_t i = 0; i < 2; ++i) { mbar_init(&s_dready[i], 1); mbar_init(&s_dfree[i], kEpilogue / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t bar_full = smem_u32(s_full), bar_free = smem_u32(s_free);
+    const uint32_t bar_dready = smem_u32(s_dready), bar_dfree = smem_u32(s_dfree);
+    const uint32_t b_base = smem_u32(s_b);
+    // M = 128 wants N % 16 == 0: an odd number of sets contracts 8 more columns against the bytes that follow
+    // (the next step's first set, or the slack behind the last step) into accumulator columns nobody reads
+    const uint32_t n_cols = (8 * n_sets + 15) & ~15u, step_bytes = 256 * n_sets;
+    const uint32_t idesc = idesc_i8(n_cols);
+    bool ok = true;
+
+    const uint32_t item_lo = min(blockIdx.x * items_per_cta, n_items), item_hi = min(item_lo + items_per_cta, n_items);
+    // running counts over the CTA's whole life: every role walks the same sequence, so each derives the
+    // barrier phases by itself
+    uint32_t q_oct = 0;          // operand stages (octets of 8 words) produced / consumed so far
+    uint32_t q_flush = 0;        // accumulators finished so far
+
+    for (uint32_t item = item_lo; item < item_hi;) {
+        const uint32_t seg = item / n_tiles, run_end = min(item_hi, (seg + 1) * n_tiles);
+        const uint32_t s_lo = seg * seg_steps, s_hi = min(s_lo + seg_steps, n_steps), n_seg = s_hi - s_lo;
+        const uint32_t tile_lo = item - seg * n_tiles, n_run = run_end - item;
+
+        // ---- this segment's step list and B digits -> shared memory (the previous segment's mma have all
+        //      completed: the epilogue warps waited for its last accumulator before coming here)
+        tc_fence_before();
+        __syncthreads();
+        for (uint32_t i = tid; i < n_seg; i += kThreads) s_steps[i] = steps[s_lo + i];
+        for (uint32_t i = tid; i < n_seg * n_sets * 16; i += kThreads) {
+            const uint32_t st = i / (n_sets * 16), r = i % (n_sets * 16), q = r >> 4, k = r & 15;
+            s_b[i] = __ldg(P.b[q] + (size_t) (s_lo + st) * 16 + k);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core's proxy
+        __syncthreads();
+        tc_fence_after();
+        const uint32_t o_first = s_steps[0].x >> 3, o_last = s_steps[n_seg - 1].x >> 3, n_oct = o_last - o_first + 1;
+
+        if (warp < 4) {
+            // ---------------- expanders: thread tid = strand row tid of the tile
+            auto row_ptr = [&](uint32_t tile) -> const uint4* {
+                const uint32_t ind = min(min(tile, n_tiles - 1) * 64 + (tid >> 1), n - 1);
+                return reinterpret_cast<const uint4*>(store + (uint64_t) rows[ind] * row_words + (tid & 1) * plane_words) + 2 * o_first;
+            };
+            const uint32_t total = n_run * n_oct;
+            constexpr uint32_t kDepth = 3;
+            uint4 buf[kDepth][2];
+            uint32_t l_tile = tile_lo, l_oct = 0;
+            const uint4* lptr = row_ptr(l_tile);
+            auto request = [&](uint4 (&b)[2]) {
+                b[0] = ldg_stream(lptr + 2 * l_oct);
+                b[1] = ldg_stream(lptr + 2 * l_oct + 1);
+                if (++l_oct == n_oct) { l_oct = 0; ++l_tile; lptr = row_ptr(l_tile); }
+            };
+#pragma unroll
+            for (uint32_t k = 0; k < kDepth; ++k) if (k < total) request(buf[k]);
+            auto produce = [&](const uint4 (&b)[2]) {
+                const uint32_t stage = q_oct % kAStages, use = q_oct / kAStages;
+                if (use > 0) {                                 // the mma that read this stage kAStages octets ago
+                    mbar_wait(bar_free + 8 * stage, (use - 1) & 1, ok);
+                    tc_fence_after();
+                }
+                const uint32_t taddr = tmem + ((warp * 32) << 16) + kACol0 + kStageCols * stage;
+                store_words(taddr, b[0]);
+                store_words(taddr + 32, b[1]);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+                ++q_oct;
+            };
+            for (uint32_t c0 = 0; c0 < total; c0 += kDepth) {
+#pragma unroll
+                for (uint32_t k = 0; k < kDepth; ++k) {
+                    if (c0 + k < total) {
+                        produce(buf[k]);
+                        if (c0 + k + kDepth < total) request(buf[k]);
+                    }
+                }
+            }
+        } else if (warp < 8) {
+            // ---------------- epilogue: thread (tid - 128) = TMEM lane = strand row of the tile
+            const uint32_t t = tid - kExpanders, wq = warp - 4;
+            for (uint32_t it = 0; it < n_run; ++it) {
+                const uint32_t tile = tile_lo + it;
+                const uint64_t out_row = (uint64_t) tile * 128 + t;          // = 2 * individual + strand
+                const bool live = (tile * 64 + (t >> 1)) < n;
+                uint32_t s = 0;
+                while (s < n_seg) {
+                    const uint32_t blk = s_steps[s].y & 0x7fffffffu, starts = s_steps[s].y >> 31;
+                    while (s < n_seg && (s_steps[s].y & 0x7fffffffu) == blk) ++s;
+                    const uint32_t dbuf = q_flush & 1;
+                    mbar_wait(bar_dready + 8 * dbuf, (q_flush >> 1) & 1, ok);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem + ((wq * 32) << 16) + (dbuf ? kDCol1 : 0u);
+                    for (uint32_t q = 0; q < n_sets; ++q) {
+                        uint32_t d[8];
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+                                     : "r"(taddr + 8 * q) : "memory");
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        double v = (double) (int) d[7];
+#pragma unroll
+                        for (int j = 6; j >= 0; --j) v = v * 256.0 + (double) (int) d[j];
+                        v *= P.scale[q];
+                        if (starts) v += P.base[q][blk];
+                        if (live) atomicAdd(P.out[q] + out_row * n_blocks + blk, v);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_dfree + 8 * dbuf);
+                    ++q_flush;
+                }
+            }
+        } else {
+            // ---------------- issuer
+            if (lane == 0) {
+                for (uint32_t it = 0; it < n_run; ++it) {
+                    uint32_t cur_oct = 0xffffffffu, cur_blk = 0xffffffffu, stage = 0, acc = 0, dbuf = 0;
+                    for (uint32_t s = 0; s < n_seg; ++s) {
+                        const uint2 st = s_steps[s];
+                        const uint32_t oct = st.x >> 3, blk = st.y & 0x7fffffffu;
+                        if (oct != cur_oct) {
+                            // octets between two steps' words (none inside a segment: steps cover every word) are skipped one by one
+                            uint32_t next = cur_oct == 0xffffffffu ? o_first : cur_oct + 1;
+                            for (;;) {
+                                if (cur_oct != 0xffffffffu) tc_commit(bar_free + 8 * stage);
+                                stage = q_oct % kAStages;
+                                mbar_wait(bar_full + 8 * stage, (q_oct / kAStages) & 1, ok);
+                                tc_fence_after();
+                                ++q_oct;
+                                cur_oct = next;
+                                if (next == oct) break;
+                                ++next;
+                            }
+                        }
+                        if (blk != cur_blk) {
+                            if (cur_blk != 0xffffffffu) { tc_commit(bar_dready + 8 * dbuf); ++q_flush; }
+                            dbuf = q_flush & 1;
+                            if (q_flush >= 2) {                      // the epilogue has read this accumulator's previous sums
+                                mbar_wait(bar_dfree + 8 * dbuf, ((q_flush >> 1) - 1) & 1, ok);
+                                tc_fence_after();
+                            }
+                            cur_blk = blk;
+                            acc = 0;
+                        }
+                        umma_i8_ts(tmem + (dbuf ? kDCol1 : 0u), tmem + kACol0 + kStageCols * stage + 8 * (st.x & 7u),
+                                   b_descriptor(b_base + s * step_bytes), idesc, acc);
+                        acc = 1;
+                    }
+                    // octets after the last step's word that the expanders still deliver for this tile: none (o_last is its octet)
+                    tc_commit(bar_free + 8 * stage);
+                    tc_commit(bar_dready + 8 * dbuf);
+                    ++q_flush;
+                }
+            }
+            __syncwarp();
+            // lanes 1..31 of the issuer warp hold no state that matters
+        }
+        item = run_end;
+    }
+    if (!ok) atomicExch(flag, 2);
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+}  // namespace
+
+// B operand of one effect set: 256 bytes per step.  K index k = 4s + b contracts marker bit 8b + s of the
+// step's word (operand byte value 2^s); the byte of (k, digit) sits at (k >> 4) * 128 + digit * 16 + (k & 15).
+// Digits are those of round(delta * 2^(exp2 - s)); markers of the word outside the step's block stay zero.
+void build_local_tc5_fragments(const std::vector<double>& delta /* [M] */, const std::vector<uint2>& steps,
+                               const uint32_t* block_offsets, const uint32_t* block_markers, int exp2, std::vector<uint32_t>& frag) {
+    frag.assign(steps.size() * 64, 0u);
+    uint8_t* bytes = reinterpret_cast<uint8_t*>(frag.data());
+    for (size_t st = 0; st < steps.size(); ++st) {
+        const uint32_t w = steps[st].x, blk = steps[st].y & 0x7fffffffu;
+        const uint32_t m_lo = block_markers[block_offsets[blk]], m_hi = m_lo + (block_offsets[blk + 1] - block_offsets[blk]);
+        for (uint32_t bit = 0; bit < 32; ++bit) {
+            const uint32_t m = w * 32 + bit;
+            if (m < m_lo || m >= m_hi) continue;
+            const uint32_t b = bit >> 3, s = bit & 7, k = 4 * s + b;
+            long long q = std::isfinite(delta[m]) ? std::llrint(std::ldexp(delta[m], exp2 - (int) s)) : 0;
+            for (uint32_t dg = 0; dg < 8; ++dg) {
+                const long long d8 = ((q + 128) & 255) - 128;
+                q = (q - d8) >> 8;
+                bytes[st * 256 + (k >> 4) * 128 + dg * 16 + (k & 15)] = (uint8_t) (int8_t) d8;
+            }
+        }
+    }
+}
+
+// One pass over the genotypes for n_sets (<= kLocalTc5MaxSets) effect sets.  d_steps: the schedule with the
+// first-step-of-block flag in bit 31 of .y; d_b / d_base / d_out / scale per set.  Asynchronous.
+int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t n_blocks, const uint2* d_steps, uint32_t n_steps,
+                     uint32_t n_sets, const uint32_t* const* d_b, const double* const* d_base, double* const* d_out, const double* scale) {
+    GSB_REQUIRE(n_sets >= 1 && n_sets <= kLocalTc5MaxSets, GSB200_ERR_ARG, "local GEBV (tcgen05 path): %u effect sets in one pass", n_sets);
+    LocalTc5Params P;
+    memset(&P, 0, sizeof P);
+    for (uint32_t q = 0; q < n_sets; ++q) { P.b[q] = (const uint4*) d_b[q]; P.base[q] = d_base[q]; P.out[q] = d_out[q]; P.scale[q] = scale[q]; }
+    const uint32_t cap = std::min<uint32_t>(kMaxSegSteps, kBBytes / (256 * n_sets));
+    const uint32_t n_seg = (n_steps + cap - 1) / cap, seg_steps = (n_steps + n_seg - 1) / n_seg;
+    const uint32_t n_tiles = (n + 63) / 64;
+    const uint64_t n_items64 = (uint64_t) n_seg * n_tiles;
+    GSB_REQUIRE(n_items64 < (1ull << 31), GSB200_ERR_ARG, "local GEBV: too many work items");
+    const uint32_t n_items = (uint32_t) n_items64;
+    const uint32_t ctas = std::min<uint32_t>((uint32_t) ctx->sm_count, n_items);
+    const uint32_t items_per_cta = (n_items + ctas - 1) / ctas;
+    const uint32_t grid = (n_items + items_per_cta - 1) / items_per_cta;
+    const uint32_t smem = seg_steps * 256 * n_sets + 256;
+    GSB_CUDA_TRY(cudaFuncSetAttribute(local_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kBBytes + 256));
+    local_tc5_kernel<<<grid, kThreads, smem, ctx->stream>>>(ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, n_blocks, d_steps,
+                                                           n_steps, seg_steps, n_tiles, n_items, items_per_cta, n_sets, P, ctx->d_flag + 2);
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    return GSB200_OK;
+}
+
+}  // namespace gsb

@@ -44,7 +44,7 @@ def test_top_n_is_a_radix_select_with_the_reference_tie_rule():
              np.array([1.0, 3.0, 3.0, -2.0, 0.5, 3.0, -0.0, 0.0]), rng.standard_normal(1) * 1e300, rng.standard_normal(2049) * 1e-300]
     for v in cases:
         v = np.ascontiguousarray(v, dtype=np.float64)
-        for top in sorted({1, 2, len(v) // 100 + 1, len(v) // 2 + 1, len(v)}):
+        for top in sorted(t for t in {1, 2, len(v) // 100 + 1, len(v) // 2 + 1, len(v)} if t <= len(v)):
             for low in (0, 1):
                 out = np.empty(top, dtype=np.uint32)
                 st = sim.E.gsb200_top_n(sim.ctx, len(v), v.ctypes.data, top, low, out.ctypes.data)
