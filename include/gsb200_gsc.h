@@ -103,6 +103,13 @@ void gsb_delete_eff_set(gsb_SimData* d, gsb_EffectID which);          /* core.c:
 
 /* ---- data access (core.c:4190-4420) */
 unsigned int gsb_get_n_genotypes(const gsb_SimData* d);
+unsigned int gsb_get_n_markers(const gsb_SimData* d);
+const char* const* gsb_get_marker_names(const gsb_SimData* d);            /* NULL until gsb_set_marker_names */
+/* ids of the recombination maps / effect sets that exist, in loading order (what gsc_SimData keeps in
+ * genome.map_ids / eff_set_ids, core.h:863-901); out may be NULL; returns how many there are */
+unsigned int gsb_get_map_ids(const gsb_SimData* d, unsigned int cap, gsb_MapID* out);
+unsigned int gsb_get_eff_set_ids(const gsb_SimData* d, unsigned int cap, gsb_EffectID* out);
+unsigned int gsb_get_index_of_name(const gsb_SimData* d, const char* name);   /* gsc_get_index_of_name (core.c:2513-2538): first match, else GSB_NA_GLOBALX */
 unsigned int gsb_get_current_id(const gsb_SimData* d);
 unsigned int gsb_get_group_size(const gsb_SimData* d, gsb_GroupNum group);
 /* storage-order export of a group (0 = everything); any output may be NULL. genotypes is
