@@ -190,7 +190,7 @@ def reference_arm(a):
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "allele_calls_per_s": val * 2 * a.markers}
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 # ---------------------------------------------------------------------------- the other named shapes (N = 1 extras)
@@ -541,7 +541,7 @@ def engine_arm(a):
                                    "sample": "one step of the same loop on %d individuals per generation (gsc_split_by_bv top 1 %% + "
                                              "gsc_make_random_crosses + gsc_delete_group) from the same %d founders, %d chr x %d SNPs, "
                                              "1 thread (the reference is single-threaded), %.1f s" % (n_done, a.founders, a.chr, M, sec)}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if sim is not None:
         sim.close()
     if world > 1:

@@ -138,6 +138,11 @@ HOST_SYMBOLS = {
     "gsb_delete_recombination_map": (None, [VP, UINT]),
     "gsb_delete_eff_set": (None, [VP, UINT]),
     "gsb_get_n_genotypes": (UINT, [VP]),
+    "gsb_get_n_markers": (UINT, [VP]),
+    "gsb_get_marker_names": (VP, [VP]),
+    "gsb_get_map_ids": (UINT, [VP, UINT, VP]),
+    "gsb_get_eff_set_ids": (UINT, [VP, UINT, VP]),
+    "gsb_get_index_of_name": (UINT, [VP, C.c_char_p]),
     "gsb_get_current_id": (UINT, [VP]),
     "gsb_get_group_size": (UINT, [VP, UINT]),
     "gsb_get_group_data": (UINT, [VP, UINT, UINT, VP, VP, VP, VP, VP, VP]),
@@ -187,7 +192,9 @@ HOST_SYMBOLS = {
 def _load(path, table):
     if not os.path.exists(path):
         raise EngineError("%s is not built; run `make -C genomicsimulation_b200` (there is no CPU fallback)" % path)
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    # RTLD_LOCAL: libgsb200_gsc.so exports the reference's own gsc_* names (include/gsb200_compat.h); in a process that also
+    # loads the reference itself (the parity tests) they must not interpose each other
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     for name, (res, args) in table.items():
         fn = getattr(lib, name)          # AttributeError if the C-ABI lost a symbol
         fn.restype = res

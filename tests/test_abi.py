@@ -86,3 +86,23 @@ def test_c_client_runs_a_breeding_scheme(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "capi ok: 216 genotypes" in out.stdout
+
+
+def test_unmodified_r_wrappers_link_against_the_compat_header():
+    """oracle/_ref/libgswrap.so (oracle/Makefile `wrappers`): hot-path functions of the reference's own
+    src/r-wrappers.c, compiled unmodified against include/gsb200_compat.h.  Loading it here proves every
+    gsc_* symbol they call is exported by libgsb200_gsc.so (no compute without a GPU)."""
+    import ctypes as C
+    import pytest
+    path = os.path.join(ROOT, "oracle", "_ref", "libgswrap.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libgswrap.so not built here")
+    from genomicsimulation_b200 import _lib
+    _lib.host()
+    L = C.CDLL(path)
+    for name in ("SXP_make_random_crosses", "SXP_make_random_crosses_between", "SXP_make_targeted_crosses",
+                 "SXP_make_all_unidirectional_crosses", "SXP_self_n_times", "SXP_make_doubled_haploids", "SXP_make_clones",
+                 "SXP_break_group_by_GEBV_num", "SXP_break_group_by_GEBV_percent", "SXP_see_local_gebvs",
+                 "SXP_create_markerblocks_nperchr", "SXP_save_genotypes", "SXP_save_allele_counts", "SXP_save_pedigrees",
+                 "SXP_save_GEBVs", "SXP_save_local_GEBVs", "gsc_compat_attach", "gsc_make_random_crosses", "gsc_calculate_local_bvs"):
+        assert getattr(L, name) is not None
