@@ -812,6 +812,10 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
         const size_t out_bytes = (size_t) n * 2 * n_blocks * sizeof(double);
         for (uint32_t q0 = 0; q0 < n_effect_sets; q0 += kLocalTc5MaxSets) {
             const uint32_t sets = std::min<uint32_t>(kLocalTc5MaxSets, n_effect_sets - q0);
+            std::vector<uint32_t> seg_off;
+            local_tc5_segments(steps, sets, seg_off);
+            uint32_t* d_seg_off;
+            GSB_TRY(upload_u32(ctx, ctx->s_rows[2], seg_off.data(), seg_off.size(), &d_seg_off));
             // host output: the pass's matrices are staged on the device in slabs of individuals
             const size_t slab = device_out ? (size_t) n : std::max<size_t>(64, std::min<size_t>(n, (((size_t) 1 << 30) / (2 * (size_t) n_blocks * sizeof(double))) / sets / 64 * 64));
             const size_t slab_bytes = slab * 2 * (size_t) n_blocks * sizeof(double);
@@ -830,7 +834,7 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
                     d_out[q] = device_out ? outs[q0 + q] : (double*) ((char*) ctx->s_eval[1].ptr + slab_bytes * q);
                     GSB_CUDA_TRY(cudaMemsetAsync(d_out[q], 0, device_out ? out_bytes : (size_t) cnt * 2 * n_blocks * sizeof(double), ctx->stream));
                 }
-                GSB_TRY(local_tc5_launch(ctx, cnt, d_rows + done, n_blocks, (const uint2*) sc.d_steps_tc5.ptr, n_steps, sets, d_b, d_base, d_out, scale));
+                GSB_TRY(local_tc5_launch(ctx, cnt, d_rows + done, n_blocks, (const uint2*) sc.d_steps_tc5.ptr, seg_off, d_seg_off, sets, d_b, d_base, d_out, scale));
                 if (!device_out)
                     for (uint32_t q = 0; q < sets; ++q)
                         GSB_CUDA_TRY(cudaMemcpyAsync(outs[q0 + q] + (size_t) done * 2 * n_blocks, d_out[q],

@@ -200,7 +200,9 @@ int gebv_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, const u
 // local_tc5.cu
 void build_local_tc5_fragments(const std::vector<double>& delta, const std::vector<uint2>& steps, const uint32_t* block_offsets,
                                const uint32_t* block_markers, int exp2, std::vector<uint32_t>& frag);
-int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t n_blocks, const uint2* d_steps, uint32_t n_steps,
+void local_tc5_segments(const std::vector<uint2>& steps, uint32_t n_sets, std::vector<uint32_t>& seg_off);
+int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t n_blocks, const uint2* d_steps,
+                     const std::vector<uint32_t>& seg_off, const uint32_t* d_seg_off,
                      uint32_t n_sets, const uint32_t* const* d_b, const double* const* d_base, double* const* d_out, const double* scale);
 int upload_u32(gsb200_ctx* ctx, Scratch& s, const uint32_t* host, size_t n, uint32_t** out);
 int check_rows(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const char* what);

@@ -46,11 +46,12 @@ constexpr uint32_t kDCol1 = 128;               // second accumulator
 constexpr uint32_t kACol0 = 256;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kMaxSegSteps = 256;
-constexpr uint32_t kBBytes = 200 * 1024;         // B digits of a segment (+ 256 bytes of slack)
+constexpr uint32_t kBBytes = 192 * 1024;         // B digits of a segment (+ 256 bytes of slack)
+constexpr uint32_t kMaxRunBases = 1536;          // doubles of per-run bases kept in shared memory (runs x sets)
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
@@ -85,11 +86,15 @@ struct LocalTc5Params {
 __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
         const uint32_t* __restrict__ rows, uint32_t n, uint32_t n_blocks,
-        const uint2* __restrict__ steps, uint32_t n_steps, uint32_t seg_steps, uint32_t n_tiles,
-        uint32_t n_items, uint32_t items_per_cta, uint32_t n_sets, const LocalTc5Params P, int* __restrict__ flag) {
+        const uint2* __restrict__ steps, const uint32_t* __restrict__ seg_off /* [n_segments + 1] first step of every segment */,
+        uint32_t n_tiles, uint32_t n_items, uint32_t items_per_cta, uint32_t n_sets, const LocalTc5Params P, int* __restrict__ flag) {
     extern __shared__ __align__(128) uint4 s_b[];                    // seg_steps x n_sets x 256 bytes
     __shared__ __align__(8) uint64_t s_full[kAStages], s_free[kAStages], s_dready[2], s_dfree[2];
     __shared__ uint2 s_steps[kMaxSegSteps];
+    // the segment's runs of steps that belong to one block = its accumulators, in order: (block | starts-here << 31, first step)
+    __shared__ uint2 s_runs[kMaxSegSteps];
+    __shared__ double s_base[kMaxRunBases];          // [run][set]: the block's base where the block starts in this segment, else 0
+    __shared__ uint32_t s_n_runs;
     __shared__ uint32_t s_tmem;
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
 
     for (uint32_t item = item_lo; item < item_hi;) {
         const uint32_t seg = item / n_tiles, run_end = min(item_hi, (seg + 1) * n_tiles);
-        const uint32_t s_lo = seg * seg_steps, s_hi = min(s_lo + seg_steps, n_steps), n_seg = s_hi - s_lo;
+        const uint32_t s_lo = seg_off[seg], s_hi = seg_off[seg + 1], n_seg = s_hi - s_lo;
         const uint32_t tile_lo = item - seg * n_tiles, n_run = run_end - item;
 
         // ---- this segment's step list and B digits -> shared memory (the previous segment's mma have all
@@ -137,6 +142,27 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core's proxy
         __syncthreads();
+        if (warp == 8) {
+            // the runs, by one warp: a step opens a run when its block differs from the previous step's
+            uint32_t n_runs = 0;
+            for (uint32_t s0 = 0; s0 < n_seg; s0 += 32) {
+                const uint32_t st = s0 + lane;
+                const bool opens = st < n_seg && (st == 0 || (s_steps[st].y & 0x7fffffffu) != (s_steps[st - 1].y & 0x7fffffffu));
+                const uint32_t ballot = __ballot_sync(0xffffffffu, opens);
+                if (opens) s_runs[n_runs + __popc(ballot & ((1u << lane) - 1u))] = make_uint2(s_steps[st].y, st);
+                n_runs += __popc(ballot);
+            }
+            if (lane == 0) s_n_runs = n_runs;
+        }
+        __syncthreads();
+        const uint32_t n_runs = s_n_runs;
+        const bool bases_in_smem = n_runs * n_sets <= kMaxRunBases;
+        if (bases_in_smem)
+            for (uint32_t i = tid; i < n_runs * n_sets; i += kThreads) {
+                const uint2 run = s_runs[i / n_sets];
+                s_base[i] = (run.x >> 31) ? P.base[i % n_sets][run.x & 0x7fffffffu] : 0.0;
+            }
+        __syncthreads();
         tc_fence_after();
         const uint32_t o_first = s_steps[0].x >> 3, o_last = s_steps[n_seg - 1].x >> 3, n_oct = o_last - o_first + 1;
 
@@ -147,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                 return reinterpret_cast<const uint4*>(store + (uint64_t) rows[ind] * row_words + (tid & 1) * plane_words) + 2 * o_first;
             };
             const uint32_t total = n_run * n_oct;
-            constexpr uint32_t kDepth = 3;
+            constexpr uint32_t kDepth = 4;
             uint4 buf[kDepth][2];
             uint32_t l_tile = tile_lo, l_oct = 0;
             const uint4* lptr = row_ptr(l_tile);
@@ -189,26 +215,25 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                 const uint32_t tile = tile_lo + it;
                 const uint64_t out_row = (uint64_t) tile * 128 + t;          // = 2 * individual + strand
                 const bool live = (tile * 64 + (t >> 1)) < n;
-                uint32_t s = 0;
-                while (s < n_seg) {
-                    const uint32_t blk = s_steps[s].y & 0x7fffffffu, starts = s_steps[s].y >> 31;
-                    while (s < n_seg && (s_steps[s].y & 0x7fffffffu) == blk) ++s;
+                for (uint32_t run = 0; run < n_runs; ++run) {
+                    const uint32_t blk = s_runs[run].x & 0x7fffffffu, starts = s_runs[run].x >> 31;
                     const uint32_t dbuf = q_flush & 1;
                     mbar_wait(bar_dready + 8 * dbuf, (q_flush >> 1) & 1, ok);
                     tc_fence_after();
                     const uint32_t taddr = tmem + ((wq * 32) << 16) + (dbuf ? kDCol1 : 0u);
+                    double* out = P.out[0] + out_row * n_blocks + blk;
                     for (uint32_t q = 0; q < n_sets; ++q) {
                         uint32_t d[8];
                         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                                      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
                                      : "r"(taddr + 8 * q) : "memory");
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        double v = (double) (int) d[7];
-#pragma unroll
-                        for (int j = 6; j >= 0; --j) v = v * 256.0 + (double) (int) d[j];
-                        v *= P.scale[q];
-                        if (starts) v += P.base[q][blk];
-                        if (live) atomicAdd(P.out[q] + out_row * n_blocks + blk, v);
+                        // sum_j d_j 256^j: the two halves are exact in int64 (|d_j| < 2^31), one fp64 fma joins them
+                        const long long lo = (long long) (int) d[0] + ((long long) (int) d[1] << 8) + ((long long) (int) d[2] << 16) + ((long long) (int) d[3] << 24);
+                        const long long hi = (long long) (int) d[4] + ((long long) (int) d[5] << 8) + ((long long) (int) d[6] << 16) + ((long long) (int) d[7] << 24);
+                        double v = fma((double) hi, 4294967296.0, (double) lo) * P.scale[q];
+                        if (starts) v += bases_in_smem ? s_base[run * n_sets + q] : P.base[q][blk];
+                        if (live) atomicAdd(P.out[q] + (out - P.out[0]), v);
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -298,14 +323,38 @@ void build_local_tc5_fragments(const std::vector<double>& delta /* [M] */, const
 
 // One pass over the genotypes for n_sets (<= kLocalTc5MaxSets) effect sets.  d_steps: the schedule with the
 // first-step-of-block flag in bit 31 of .y; d_b / d_base / d_out / scale per set.  Asynchronous.
-int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t n_blocks, const uint2* d_steps, uint32_t n_steps,
+// Marker segments for a pass of n_sets effect sets: consecutive step ranges of at most `cap` steps (their B
+// digits must fit shared memory) that end where a 128-byte line of the strand rows ends (32 marker words),
+// so that every line of the genotypes is fetched from DRAM once; only when not even 32 words' steps fit
+// (blocks of a few markers each) a segment is cut at `cap` steps.
+void local_tc5_segments(const std::vector<uint2>& steps, uint32_t n_sets, std::vector<uint32_t>& seg_off) {
+    const uint32_t cap = std::min<uint32_t>(kMaxSegSteps, kBBytes / (256 * n_sets));
+    const uint32_t n_steps = (uint32_t) steps.size();
+    seg_off.assign(1, 0u);
+    uint32_t pos = 0;
+    while (pos < n_steps) {
+        uint32_t best = 0, end = pos;
+        for (uint32_t end_word = (steps[pos].x / 32 + 1) * 32;; end_word += 32) {
+            while (end < n_steps && steps[end].x < end_word) ++end;
+            if (end - pos > cap) break;
+            best = end;
+            if (end == n_steps) break;
+        }
+        if (best == 0) best = std::min(n_steps, pos + cap);
+        seg_off.push_back(best);
+        pos = best;
+    }
+}
+
+int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t n_blocks, const uint2* d_steps,
+                     const std::vector<uint32_t>& seg_off, const uint32_t* d_seg_off,
                      uint32_t n_sets, const uint32_t* const* d_b, const double* const* d_base, double* const* d_out, const double* scale) {
     GSB_REQUIRE(n_sets >= 1 && n_sets <= kLocalTc5MaxSets, GSB200_ERR_ARG, "local GEBV (tcgen05 path): %u effect sets in one pass", n_sets);
     LocalTc5Params P;
     memset(&P, 0, sizeof P);
     for (uint32_t q = 0; q < n_sets; ++q) { P.b[q] = (const uint4*) d_b[q]; P.base[q] = d_base[q]; P.out[q] = d_out[q]; P.scale[q] = scale[q]; }
     const uint32_t cap = std::min<uint32_t>(kMaxSegSteps, kBBytes / (256 * n_sets));
-    const uint32_t n_seg = (n_steps + cap - 1) / cap, seg_steps = (n_steps + n_seg - 1) / n_seg;
+    const uint32_t n_seg = (uint32_t) seg_off.size() - 1;
     const uint32_t n_tiles = (n + 63) / 64;
     const uint64_t n_items64 = (uint64_t) n_seg * n_tiles;
     GSB_REQUIRE(n_items64 < (1ull << 31), GSB200_ERR_ARG, "local GEBV: too many work items");
@@ -313,10 +362,13 @@ int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32
     const uint32_t ctas = std::min<uint32_t>((uint32_t) ctx->sm_count, n_items);
     const uint32_t items_per_cta = (n_items + ctas - 1) / ctas;
     const uint32_t grid = (n_items + items_per_cta - 1) / items_per_cta;
+    uint32_t seg_steps = 0;
+    for (uint32_t k = 0; k < n_seg; ++k) seg_steps = std::max(seg_steps, seg_off[k + 1] - seg_off[k]);
+    GSB_REQUIRE(seg_steps <= cap, GSB200_ERR_ARG, "local GEBV (tcgen05 path): internal: a segment of %u steps exceeds %u", seg_steps, cap);
     const uint32_t smem = seg_steps * 256 * n_sets + 256;
     GSB_CUDA_TRY(cudaFuncSetAttribute(local_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kBBytes + 256));
     local_tc5_kernel<<<grid, kThreads, smem, ctx->stream>>>(ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, n_blocks, d_steps,
-                                                           n_steps, seg_steps, n_tiles, n_items, items_per_cta, n_sets, P, ctx->d_flag + 2);
+                                                           d_seg_off, n_tiles, n_items, items_per_cta, n_sets, P, ctx->d_flag + 2);
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
     return GSB200_OK;
