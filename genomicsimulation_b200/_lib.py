@@ -100,9 +100,11 @@ ENGINE_SYMBOLS = {
     "gsb200_shard_handle": (I32, [VP, VP]),
     "gsb200_shard_connect": (I32, [VP, VP]),
     "gsb200_shard_select": (I32, [VP, U32, VP, VP, U64, U32, U32, I32]),
+    "gsb200_shard_select_run": (I32, [VP, U32, VP, U32, VP, U64, U32, U32, I32]),
     "gsb200_shard_select_dev": (I32, [VP, U32, VP, VP, U64, U32, U32, I32]),
     "gsb200_shard_cross": (I32, [VP, U32, U32, VP, C.POINTER(Draws), VP, VP]),
     "gsb200_shard_cross_begin": (I32, [VP, U32, U32, VP, C.POINTER(Draws), I32]),
+    "gsb200_shard_cross_begin_run": (I32, [VP, U32, U32, VP, U32, C.POINTER(Draws), I32]),
     "gsb200_shard_cross_picks": (I32, [VP, VP, VP, VP]),
     "gsb200_shard_finish": (I32, [VP]),
     "gsb200_shard_cross_dev": (I32, [VP, U32, U32, VP, U32, C.POINTER(Draws), VP]),

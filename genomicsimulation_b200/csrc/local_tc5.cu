@@ -30,6 +30,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 using namespace gsb;
 using namespace gsb::tc5;
@@ -47,6 +49,7 @@ constexpr uint32_t kACol0 = 256;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kMaxSegSteps = 256;
 constexpr uint32_t kBBytes = 192 * 1024;         // B digits of a segment (+ 256 bytes of slack)
+constexpr uint32_t kTraceLen = 96;               // stages / flushes of CTA 0 whose timestamps GSB200_LOCAL_TRACE records
 constexpr uint32_t kMaxRunBases = 1536;          // doubles of per-run bases kept in shared memory (runs x sets)
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
@@ -87,7 +90,8 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
         const uint32_t* __restrict__ rows, uint32_t n, uint32_t n_blocks,
         const uint2* __restrict__ steps, const uint32_t* __restrict__ seg_off /* [n_segments + 1] first step of every segment */,
-        uint32_t n_tiles, uint32_t n_items, uint32_t items_per_cta, uint32_t n_sets, const LocalTc5Params P, int* __restrict__ flag) {
+        uint32_t n_tiles, uint32_t n_items, uint32_t items_per_cta, uint32_t n_sets, const LocalTc5Params P, int* __restrict__ flag,
+        long long* __restrict__ trace /* debugging: clock64 stamps of CTA 0's first kTraceLen stages per role, or null */) {
     extern __shared__ __align__(128) uint4 s_b[];                    // seg_steps x n_sets x 256 bytes
     __shared__ __align__(8) uint64_t s_full[kAStages], s_free[kAStages], s_dready[2], s_dfree[2];
     __shared__ uint2 s_steps[kMaxSegSteps];
@@ -186,14 +190,19 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
             for (uint32_t k = 0; k < kDepth; ++k) if (k < total) request(buf[k]);
             auto produce = [&](const uint4 (&b)[2]) {
                 const uint32_t stage = q_oct % kAStages, use = q_oct / kAStages;
+                const bool tr = trace && blockIdx.x == 0 && tid == 0 && q_oct < kTraceLen;
+                if (tr) trace[0 * kTraceLen + q_oct] = clock64();
                 if (use > 0) {                                 // the mma that read this stage kAStages octets ago
                     mbar_wait(bar_free + 8 * stage, (use - 1) & 1, ok);
                     tc_fence_after();
                 }
                 const uint32_t taddr = tmem + ((warp * 32) << 16) + kACol0 + kStageCols * stage;
+                if (tr) trace[1 * kTraceLen + q_oct] = clock64();
                 store_words(taddr, b[0]);
+                if (tr) trace[2 * kTraceLen + q_oct] = clock64();
                 store_words(taddr + 32, b[1]);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                if (tr) trace[3 * kTraceLen + q_oct] = clock64();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_full + 8 * stage);
@@ -218,8 +227,11 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                 for (uint32_t run = 0; run < n_runs; ++run) {
                     const uint32_t blk = s_runs[run].x & 0x7fffffffu, starts = s_runs[run].x >> 31;
                     const uint32_t dbuf = q_flush & 1;
+                    const bool tr = trace && blockIdx.x == 0 && t == 0 && q_flush < kTraceLen;
+                    if (tr) trace[6 * kTraceLen + q_flush] = clock64();
                     mbar_wait(bar_dready + 8 * dbuf, (q_flush >> 1) & 1, ok);
                     tc_fence_after();
+                    if (tr) trace[7 * kTraceLen + q_flush] = clock64();
                     const uint32_t taddr = tmem + ((wq * 32) << 16) + (dbuf ? kDCol1 : 0u);
                     double* out = P.out[0] + out_row * n_blocks + blk;
                     for (uint32_t q = 0; q < n_sets; ++q) {
@@ -238,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_dfree + 8 * dbuf);
+                    if (tr) trace[8 * kTraceLen + q_flush] = clock64();
                     ++q_flush;
                 }
             }
@@ -255,8 +268,10 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                             for (;;) {
                                 if (cur_oct != 0xffffffffu) tc_commit(bar_free + 8 * stage);
                                 stage = q_oct % kAStages;
+                                if (trace && blockIdx.x == 0 && q_oct < kTraceLen) trace[4 * kTraceLen + q_oct] = clock64();
                                 mbar_wait(bar_full + 8 * stage, (q_oct / kAStages) & 1, ok);
                                 tc_fence_after();
+                                if (trace && blockIdx.x == 0 && q_oct < kTraceLen) trace[5 * kTraceLen + q_oct] = clock64();
                                 ++q_oct;
                                 cur_oct = next;
                                 if (next == oct) break;
@@ -367,10 +382,33 @@ int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32
     GSB_REQUIRE(seg_steps <= cap, GSB200_ERR_ARG, "local GEBV (tcgen05 path): internal: a segment of %u steps exceeds %u", seg_steps, cap);
     const uint32_t smem = seg_steps * 256 * n_sets + 256;
     GSB_CUDA_TRY(cudaFuncSetAttribute(local_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kBBytes + 256));
+    // GSB200_LOCAL_TRACE=<file>: clock64 stamps of CTA 0's first stages (profiles/scripts/local_trace.py reads them)
+    static const char* trace_path = getenv("GSB200_LOCAL_TRACE");
+    long long* d_trace = nullptr;
+    if (trace_path) {
+        GSB_CUDA_TRY(cudaMalloc((void**) &d_trace, 9 * kTraceLen * sizeof(long long)));
+        GSB_CUDA_TRY(cudaMemsetAsync(d_trace, 0, 9 * kTraceLen * sizeof(long long), ctx->stream));
+    }
     local_tc5_kernel<<<grid, kThreads, smem, ctx->stream>>>(ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, n_blocks, d_steps,
-                                                           d_seg_off, n_tiles, n_items, items_per_cta, n_sets, P, ctx->d_flag + 2);
+                                                           d_seg_off, n_tiles, n_items, items_per_cta, n_sets, P, ctx->d_flag + 2, d_trace);
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
+    if (d_trace) {
+        std::vector<long long> h(9 * kTraceLen);
+        GSB_CUDA_TRY(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_trace);
+        if (FILE* f = fopen(trace_path, "w")) {
+            fprintf(f, "# stage/flush: expander warp 0 (enter, stage free, first store issued, stores done) | issuer (wants stage, has stage) | epilogue warp 0 (wants sums, has sums, done); cycles since the first stamp\n");
+            long long t0 = h[0];
+            for (uint32_t k = 0; k < kTraceLen; ++k) {
+                fprintf(f, "%3u", k);
+                for (uint32_t r = 0; r < 9; ++r) fprintf(f, " %9lld", h[r * kTraceLen + k] ? h[r * kTraceLen + k] - t0 : -1ll);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     return GSB200_OK;
 }
 

@@ -127,6 +127,11 @@ __global__ void __launch_bounds__(256) shard_push_pool_kernel(const __grid_const
     }
 }
 
+__global__ void shard_iota_kernel(uint32_t* out, uint32_t first, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = first + i;
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -364,15 +369,30 @@ int gsb200_shard_select_dev(gsb200_shard* s, uint32_t n_local, const uint32_t* d
     return shard_select_impl(s, n_local, d_local_rows, local_ids, n_total, eff_index, top_n, low_is_best, "gsb200_shard_select_dev");
 }
 
-int gsb200_shard_select(gsb200_shard* s, uint32_t n_local, const uint32_t* local_rows, const uint32_t* local_ids,
-                        uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best) {
+int gsb200_shard_select_run(gsb200_shard* s, uint32_t n_local, const uint32_t* local_rows, uint32_t first_local_row, const uint32_t* local_ids,
+                            uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best) {
     GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
-    GSB_TRY(check_rows(s->ctx, n_local, local_rows, "gsb200_shard_select"));
-    GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    const char* what = "gsb200_shard_select";
+    gsb200_ctx* ctx = s->ctx;
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
     // the rows are read again when the pool is pushed: they get a buffer of their own
     uint32_t* d_rows;
-    GSB_TRY(upload_u32(s->ctx, s->s_local_rows, local_rows, n_local, &d_rows));
-    return shard_select_impl(s, n_local, d_rows, local_ids, n_total, eff_index, top_n, low_is_best, "gsb200_shard_select");
+    if (local_rows) {
+        GSB_TRY(check_rows(ctx, n_local, local_rows, what));
+        GSB_TRY(upload_u32(ctx, s->s_local_rows, local_rows, n_local, &d_rows));
+    } else {
+        GSB_REQUIRE((uint64_t) first_local_row + n_local <= ctx->capacity, GSB200_ERR_ARG, "%s: rows %u.. beyond the store capacity", what, first_local_row);
+        GSB_TRY(s->s_local_rows.ensure(std::max<size_t>(n_local, 1) * sizeof(uint32_t)));
+        d_rows = (uint32_t*) s->s_local_rows.ptr;
+        if (n_local) shard_iota_kernel<<<(n_local + 255) / 256, 256, 0, ctx->stream>>>(d_rows, first_local_row, n_local);
+    }
+    return shard_select_impl(s, n_local, d_rows, local_ids, n_total, eff_index, top_n, low_is_best, what);
+}
+
+int gsb200_shard_select(gsb200_shard* s, uint32_t n_local, const uint32_t* local_rows, const uint32_t* local_ids,
+                        uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best) {
+    GSB_REQUIRE(n_local == 0 || local_rows != nullptr, GSB200_ERR_ARG, "gsb200_shard_select: null row array");
+    return gsb200_shard_select_run(s, n_local, local_rows, 0, local_ids, n_total, eff_index, top_n, low_is_best);
 }
 
 static int shard_cross_impl(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t* d_out_rows, uint32_t first_out_row,
@@ -410,19 +430,27 @@ int gsb200_shard_cross_dev(gsb200_shard* s, uint32_t n, uint32_t map, const uint
 }
 
 int gsb200_shard_cross_begin(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t* out_rows, const gsb200_draws* draws, int want_picks) {
+    GSB_REQUIRE(n == 0 || out_rows != nullptr, GSB200_ERR_ARG, "gsb200_shard_cross: null row array");
+    return gsb200_shard_cross_begin_run(s, n, map, out_rows, 0, draws, want_picks);
+}
+
+int gsb200_shard_cross_begin_run(gsb200_shard* s, uint32_t n, uint32_t map, const uint32_t* out_rows, uint32_t first_out_row,
+                                 const gsb200_draws* draws, int want_picks) {
     GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
     if (n == 0) return GSB200_OK;
     gsb200_ctx* ctx = s->ctx;
-    GSB_TRY(check_rows(ctx, n, out_rows, "gsb200_shard_cross"));
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
-    uint32_t* d_out;
-    GSB_TRY(upload_u32(ctx, ctx->s_rows[2], out_rows, n, &d_out));
+    uint32_t* d_out = nullptr;
+    if (out_rows) {
+        GSB_TRY(check_rows(ctx, n, out_rows, "gsb200_shard_cross"));
+        GSB_TRY(upload_u32(ctx, ctx->s_rows[2], out_rows, n, &d_out));
+    }
     uint32_t* d_picks = nullptr;
     if (want_picks) {
         GSB_TRY(ctx->s_rows[1].ensure((size_t) 2 * n * sizeof(uint32_t)));
         d_picks = (uint32_t*) ctx->s_rows[1].ptr;
     }
-    return shard_cross_impl(s, n, map, d_out, 0, draws, d_picks, want_picks != 0, "gsb200_shard_cross");
+    return shard_cross_impl(s, n, map, d_out, first_out_row, draws, d_picks, want_picks != 0, "gsb200_shard_cross");
 }
 
 int gsb200_shard_cross_picks(gsb200_shard* s, const uint32_t** picked1, const uint32_t** picked2, const uint32_t** selected_ids) {

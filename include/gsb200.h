@@ -279,6 +279,9 @@ int  gsb200_shard_connect(gsb200_shard* shard, const void* handles /* world x GS
  * can name the selected parents.  Every rank must make the same sequence of calls.  Asynchronous. */
 int  gsb200_shard_select(gsb200_shard* shard, uint32_t n_local, const uint32_t* local_rows, const uint32_t* local_ids,
                          uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best);
+/* ... local_rows == NULL: the individuals are rows first_local_row, first_local_row + 1, ... (no list crosses PCIe) */
+int  gsb200_shard_select_run(gsb200_shard* shard, uint32_t n_local, const uint32_t* local_rows, uint32_t first_local_row,
+                             const uint32_t* local_ids, uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best);
 /* ... with the row list already on the device (it must stay valid until the call's work is done) */
 int  gsb200_shard_select_dev(gsb200_shard* shard, uint32_t n_local, const uint32_t* d_local_rows, const uint32_t* local_ids,
                              uint64_t n_total, uint32_t eff_index, uint32_t top_n, int low_is_best);
@@ -295,6 +298,9 @@ int  gsb200_shard_cross(gsb200_shard* shard, uint32_t n, uint32_t map, const uin
  * owned by the shard, valid until the next _begin); _finish waits for the offspring and reports a splice-plan
  * overflow or a peer that never delivered.  The next gsb200_shard_select may be enqueued before _finish. */
 int  gsb200_shard_cross_begin(gsb200_shard* shard, uint32_t n, uint32_t map, const uint32_t* out_rows, const gsb200_draws* draws, int want_picks);
+/* ... out_rows == NULL: the offspring go to rows first_out_row, first_out_row + 1, ... */
+int  gsb200_shard_cross_begin_run(gsb200_shard* shard, uint32_t n, uint32_t map, const uint32_t* out_rows, uint32_t first_out_row,
+                                  const gsb200_draws* draws, int want_picks);
 int  gsb200_shard_cross_picks(gsb200_shard* shard, const uint32_t** picked1, const uint32_t** picked2, const uint32_t** selected_ids);
 int  gsb200_shard_finish(gsb200_shard* shard);
 /* ... asynchronous: d_out_rows NULL = rows first_out_row, first_out_row + 1, ...; d_picks (device, 2n) may be NULL */
