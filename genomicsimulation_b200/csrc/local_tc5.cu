@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
     // the segment's runs of steps that belong to one block = its accumulators, in order: (block | starts-here << 31, first step)
     __shared__ uint2 s_runs[kMaxSegSteps];
     __shared__ double s_base[kMaxRunBases];          // [run][set]: the block's base where the block starts in this segment, else 0
+    // per step, for the issuer: word & 7 | 8 if the step opens an operand stage (octet) | 16 if it opens an accumulator
+    // (block) | octets to advance << 8 — precomputed so that the single issuing thread does next to nothing per MMA
+    __shared__ uint32_t s_rec[kMaxSegSteps + 1];
     __shared__ uint32_t s_n_runs;
     __shared__ uint32_t s_tmem;
 
@@ -146,6 +149,15 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core's proxy
         __syncthreads();
+        for (uint32_t st = tid; st <= n_seg; st += kThreads) {
+            uint32_t rec = 0;
+            if (st < n_seg) {
+                const uint32_t oct = s_steps[st].x >> 3, blk = s_steps[st].y & 0x7fffffffu;
+                const uint32_t adv = st == 0 ? 1u : oct - (s_steps[st - 1].x >> 3);
+                rec = (s_steps[st].x & 7u) | (adv ? 8u : 0u) | ((st == 0 || blk != (s_steps[st - 1].y & 0x7fffffffu)) ? 16u : 0u) | (adv << 8);
+            }
+            s_rec[st] = rec;
+        }
         if (warp == 8) {
             // the runs, by one warp: a step opens a run when its block differs from the previous step's
             uint32_t n_runs = 0;
@@ -234,18 +246,27 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                     if (tr) trace[7 * kTraceLen + q_flush] = clock64();
                     const uint32_t taddr = tmem + ((wq * 32) << 16) + (dbuf ? kDCol1 : 0u);
                     double* out = P.out[0] + out_row * n_blocks + blk;
-                    for (uint32_t q = 0; q < n_sets; ++q) {
-                        uint32_t d[8];
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                     : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
-                                     : "r"(taddr + 8 * q) : "memory");
+                    for (uint32_t q0 = 0; q0 < n_sets; q0 += 4) {
+                        // four sets at a time: the loads first, then four independent recombinations
+                        uint32_t d[4][8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=r"(d[j][0]), "=r"(d[j][1]), "=r"(d[j][2]), "=r"(d[j][3]), "=r"(d[j][4]), "=r"(d[j][5]), "=r"(d[j][6]), "=r"(d[j][7])
+                                         : "r"(taddr + 8 * min(q0 + j, n_sets - 1)) : "memory");
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        // sum_j d_j 256^j: the two halves are exact in int64 (|d_j| < 2^31), one fp64 fma joins them
-                        const long long lo = (long long) (int) d[0] + ((long long) (int) d[1] << 8) + ((long long) (int) d[2] << 16) + ((long long) (int) d[3] << 24);
-                        const long long hi = (long long) (int) d[4] + ((long long) (int) d[5] << 8) + ((long long) (int) d[6] << 16) + ((long long) (int) d[7] << 24);
-                        double v = fma((double) hi, 4294967296.0, (double) lo) * P.scale[q];
-                        if (starts) v += bases_in_smem ? s_base[run * n_sets + q] : P.base[q][blk];
-                        if (live) atomicAdd(P.out[q] + (out - P.out[0]), v);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t q = q0 + j;
+                            // sum_k d_k 256^k: the two halves are exact in int64 (|d_k| < 2^31), one fp64 fma joins them
+                            const long long lo = (long long) (int) d[j][0] + ((long long) (int) d[j][1] << 8) + ((long long) (int) d[j][2] << 16) + ((long long) (int) d[j][3] << 24);
+                            const long long hi = (long long) (int) d[j][4] + ((long long) (int) d[j][5] << 8) + ((long long) (int) d[j][6] << 16) + ((long long) (int) d[j][7] << 24);
+                            if (q < n_sets) {
+                                double v = fma((double) hi, 4294967296.0, (double) lo) * P.scale[q];
+                                if (starts) v += bases_in_smem ? s_base[run * n_sets + q] : P.base[q][blk];
+                                if (live) atomicAdd(P.out[q] + (out - P.out[0]), v);
+                            }
+                        }
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -255,51 +276,51 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                 }
             }
         } else {
-            // ---------------- issuer
+            // ---------------- issuer: one thread; per step a prefetched record, two rarely taken branches, one MMA
             if (lane == 0) {
+                const uint64_t desc0 = b_descriptor(b_base);
+                const uint32_t desc_step = step_bytes >> 4;          // the start-address field counts 16-byte units; all of shared memory fits its 14 bits
                 for (uint32_t it = 0; it < n_run; ++it) {
-                    uint32_t cur_oct = 0xffffffffu, cur_blk = 0xffffffffu, stage = 0, acc = 0, dbuf = 0;
+                    uint32_t stage = 0, acc = 0, dbuf = 0, a_base = 0, d_addr = 0;
+                    bool have_oct = false, have_blk = false;
+                    uint32_t rec = s_rec[0];
                     for (uint32_t s = 0; s < n_seg; ++s) {
-                        const uint2 st = s_steps[s];
-                        const uint32_t oct = st.x >> 3, blk = st.y & 0x7fffffffu;
-                        if (oct != cur_oct) {
-                            // octets between two steps' words (none inside a segment: steps cover every word) are skipped one by one
-                            uint32_t next = cur_oct == 0xffffffffu ? o_first : cur_oct + 1;
-                            for (;;) {
-                                if (cur_oct != 0xffffffffu) tc_commit(bar_free + 8 * stage);
+                        const uint32_t nxt = s_rec[s + 1];
+                        if (rec & 8u) {
+                            // (a gap between two blocks may skip whole octets; the expanders deliver every octet of the segment)
+                            for (uint32_t adv = rec >> 8; adv; --adv) {
+                                if (have_oct) tc_commit(bar_free + 8 * stage);
+                                have_oct = true;
                                 stage = q_oct % kAStages;
                                 if (trace && blockIdx.x == 0 && q_oct < kTraceLen) trace[4 * kTraceLen + q_oct] = clock64();
                                 mbar_wait(bar_full + 8 * stage, (q_oct / kAStages) & 1, ok);
                                 tc_fence_after();
                                 if (trace && blockIdx.x == 0 && q_oct < kTraceLen) trace[5 * kTraceLen + q_oct] = clock64();
                                 ++q_oct;
-                                cur_oct = next;
-                                if (next == oct) break;
-                                ++next;
                             }
+                            a_base = tmem + kACol0 + kStageCols * stage;
                         }
-                        if (blk != cur_blk) {
-                            if (cur_blk != 0xffffffffu) { tc_commit(bar_dready + 8 * dbuf); ++q_flush; }
+                        if (rec & 16u) {
+                            if (have_blk) { tc_commit(bar_dready + 8 * dbuf); ++q_flush; }
+                            have_blk = true;
                             dbuf = q_flush & 1;
                             if (q_flush >= 2) {                      // the epilogue has read this accumulator's previous sums
                                 mbar_wait(bar_dfree + 8 * dbuf, ((q_flush >> 1) - 1) & 1, ok);
                                 tc_fence_after();
                             }
-                            cur_blk = blk;
+                            d_addr = tmem + (dbuf ? kDCol1 : 0u);
                             acc = 0;
                         }
-                        umma_i8_ts(tmem + (dbuf ? kDCol1 : 0u), tmem + kACol0 + kStageCols * stage + 8 * (st.x & 7u),
-                                   b_descriptor(b_base + s * step_bytes), idesc, acc);
+                        umma_i8_ts(d_addr, a_base + 8 * (rec & 7u), desc0 + (uint64_t) (s * desc_step), idesc, acc);
                         acc = 1;
+                        rec = nxt;
                     }
-                    // octets after the last step's word that the expanders still deliver for this tile: none (o_last is its octet)
                     tc_commit(bar_free + 8 * stage);
                     tc_commit(bar_dready + 8 * dbuf);
                     ++q_flush;
                 }
             }
             __syncwarp();
-            // lanes 1..31 of the issuer warp hold no state that matters
         }
         item = run_end;
     }
