@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         const uint32_t* __restrict__ rows, uint32_t n, uint32_t n_blocks,
         const uint2* __restrict__ steps, const uint32_t* __restrict__ seg_off /* [n_segments + 1] first step of every segment */,
         uint32_t n_tiles, uint32_t n_items, uint32_t items_per_cta, uint32_t n_sets, const LocalTc5Params P, int* __restrict__ flag,
+        uint32_t dbg /* GSB200_LOCAL_DEBUG bits, measurements only: 1 no operand stores, 2 no mma, 4 no epilogue work, 8 no row loads */,
         long long* __restrict__ trace /* debugging: clock64 stamps of CTA 0's first kTraceLen stages per role, or null */) {
     extern __shared__ __align__(128) uint4 s_b[];                    // seg_steps x n_sets x 256 bytes
     __shared__ __align__(8) uint64_t s_full[kAStages], s_free[kAStages], s_dready[2], s_dfree[2];
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core's proxy
         __syncthreads();
         for (uint32_t st = tid; st <= n_seg; st += kThreads) {
-            uint32_t rec = 0;
+            uint32_t rec = 24u;                                  // the sentinel behind the last step ends the issuer's fast loop
             if (st < n_seg) {
                 const uint32_t oct = s_steps[st].x >> 3, blk = s_steps[st].y & 0x7fffffffu;
                 const uint32_t adv = st == 0 ? 1u : oct - (s_steps[st - 1].x >> 3);
@@ -194,8 +195,8 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
             uint32_t l_tile = tile_lo, l_oct = 0;
             const uint4* lptr = row_ptr(l_tile);
             auto request = [&](uint4 (&b)[2]) {
-                b[0] = ldg_stream(lptr + 2 * l_oct);
-                b[1] = ldg_stream(lptr + 2 * l_oct + 1);
+                if (!(dbg & 8u)) { b[0] = ldg_stream(lptr + 2 * l_oct); b[1] = ldg_stream(lptr + 2 * l_oct + 1); }
+                else b[0] = b[1] = make_uint4(l_oct, tid, 3u, 4u);
                 if (++l_oct == n_oct) { l_oct = 0; ++l_tile; lptr = row_ptr(l_tile); }
             };
 #pragma unroll
@@ -210,9 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                 }
                 const uint32_t taddr = tmem + ((warp * 32) << 16) + kACol0 + kStageCols * stage;
                 if (tr) trace[1 * kTraceLen + q_oct] = clock64();
-                store_words(taddr, b[0]);
+                if (!(dbg & 1u)) store_words(taddr, b[0]);
                 if (tr) trace[2 * kTraceLen + q_oct] = clock64();
-                store_words(taddr + 32, b[1]);
+                if (!(dbg & 1u)) store_words(taddr + 32, b[1]);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 if (tr) trace[3 * kTraceLen + q_oct] = clock64();
                 tc_fence_before();
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                     if (tr) trace[7 * kTraceLen + q_flush] = clock64();
                     const uint32_t taddr = tmem + ((wq * 32) << 16) + (dbuf ? kDCol1 : 0u);
                     double* out = P.out[0] + out_row * n_blocks + blk;
-                    for (uint32_t q0 = 0; q0 < n_sets; q0 += 4) {
+                    for (uint32_t q0 = 0; q0 < ((dbg & 4u) ? 0u : n_sets); q0 += 4) {
                         // four sets at a time: the loads first, then four independent recombinations
                         uint32_t d[4][8];
 #pragma unroll
@@ -276,16 +277,21 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                 }
             }
         } else {
-            // ---------------- issuer: one thread; per step a prefetched record, two rarely taken branches, one MMA
+            // ---------------- issuer: one thread.  A lone thread retires an instruction every ~4 cycles, so the
+            // step loop is kept to a dozen instructions (record prefetch, operand column, descriptor bump, mma) —
+            // a first version with the stage / accumulator bookkeeping inline spent ~300 cycles per step, three
+            // times what the mma itself takes (profiles/r2_local_tc5.txt).  Octet and block changes, flagged in
+            // the precomputed records, leave the fast loop.
             if (lane == 0) {
                 const uint64_t desc0 = b_descriptor(b_base);
                 const uint32_t desc_step = step_bytes >> 4;          // the start-address field counts 16-byte units; all of shared memory fits its 14 bits
                 for (uint32_t it = 0; it < n_run; ++it) {
-                    uint32_t stage = 0, acc = 0, dbuf = 0, a_base = 0, d_addr = 0;
+                    uint32_t stage = 0, dbuf = 0, a_base = 0, d_addr = 0, s = 0;
                     bool have_oct = false, have_blk = false;
+                    uint64_t desc = desc0;
                     uint32_t rec = s_rec[0];
-                    for (uint32_t s = 0; s < n_seg; ++s) {
-                        const uint32_t nxt = s_rec[s + 1];
+                    while (s < n_seg) {
+                        uint32_t acc = 1;
                         if (rec & 8u) {
                             // (a gap between two blocks may skip whole octets; the expanders deliver every octet of the segment)
                             for (uint32_t adv = rec >> 8; adv; --adv) {
@@ -311,9 +317,13 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                             d_addr = tmem + (dbuf ? kDCol1 : 0u);
                             acc = 0;
                         }
-                        umma_i8_ts(d_addr, a_base + 8 * (rec & 7u), desc0 + (uint64_t) (s * desc_step), idesc, acc);
-                        acc = 1;
-                        rec = nxt;
+                        // the steps up to the next octet or block change (the record behind the last step has both flags set)
+                        do {
+                            if (!(dbg & 2u)) umma_i8_ts(d_addr, a_base + 8 * (rec & 7u), desc, idesc, acc);
+                            acc = 1;
+                            desc += desc_step;
+                            rec = s_rec[++s];
+                        } while (!(rec & 24u));
                     }
                     tc_commit(bar_free + 8 * stage);
                     tc_commit(bar_dready + 8 * dbuf);
@@ -405,13 +415,14 @@ int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32
     GSB_CUDA_TRY(cudaFuncSetAttribute(local_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kBBytes + 256));
     // GSB200_LOCAL_TRACE=<file>: clock64 stamps of CTA 0's first stages (profiles/scripts/local_trace.py reads them)
     static const char* trace_path = getenv("GSB200_LOCAL_TRACE");
+    static const uint32_t dbg = getenv("GSB200_LOCAL_DEBUG") ? (uint32_t) atoi(getenv("GSB200_LOCAL_DEBUG")) : 0u;
     long long* d_trace = nullptr;
     if (trace_path) {
         GSB_CUDA_TRY(cudaMalloc((void**) &d_trace, 9 * kTraceLen * sizeof(long long)));
         GSB_CUDA_TRY(cudaMemsetAsync(d_trace, 0, 9 * kTraceLen * sizeof(long long), ctx->stream));
     }
     local_tc5_kernel<<<grid, kThreads, smem, ctx->stream>>>(ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, n_blocks, d_steps,
-                                                           d_seg_off, n_tiles, n_items, items_per_cta, n_sets, P, ctx->d_flag + 2, d_trace);
+                                                           d_seg_off, n_tiles, n_items, items_per_cta, n_sets, P, ctx->d_flag + 2, dbg, d_trace);
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
     if (d_trace) {
