@@ -89,7 +89,7 @@ struct LocalTc5Params {
 __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
         const uint32_t* __restrict__ rows, uint32_t n, uint32_t n_blocks,
-        const uint2* __restrict__ steps, const uint32_t* __restrict__ seg_off /* [n_segments + 1] first step of every segment */,
+        const uint2* __restrict__ steps, uint32_t n_steps, const uint32_t* __restrict__ seg_off /* [n_segments + 1] first step of every segment */,
         uint32_t n_tiles, uint32_t n_items, uint32_t items_per_cta, uint32_t n_sets, const LocalTc5Params P, int* __restrict__ flag,
         uint32_t dbg /* GSB200_LOCAL_DEBUG bits, measurements only: 1 no operand stores, 2 no mma, 4 no epilogue work, 8 no row loads */,
         long long* __restrict__ trace /* debugging: clock64 stamps of CTA 0's first kTraceLen stages per role, or null */) {
@@ -173,6 +173,8 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         }
         __syncthreads();
         const uint32_t n_runs = s_n_runs;
+        // does the segment's first run start its block, does its last run end it?  (every other run is a whole block)
+        const bool last_run_ends = s_hi == n_steps || (steps[s_hi].y & 0x7fffffffu) != (s_steps[n_seg - 1].y & 0x7fffffffu);
         const bool bases_in_smem = n_runs * n_sets <= kMaxRunBases;
         if (bases_in_smem)
             for (uint32_t i = tid; i < n_runs * n_sets; i += kThreads) {
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                 return reinterpret_cast<const uint4*>(store + (uint64_t) rows[ind] * row_words + (tid & 1) * plane_words) + 2 * o_first;
             };
             const uint32_t total = n_run * n_oct;
-            constexpr uint32_t kDepth = 4;
+            constexpr uint32_t kDepth = 6;
             uint4 buf[kDepth][2];
             uint32_t l_tile = tile_lo, l_oct = 0;
             const uint4* lptr = row_ptr(l_tile);
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                 const bool live = (tile * 64 + (t >> 1)) < n;
                 for (uint32_t run = 0; run < n_runs; ++run) {
                     const uint32_t blk = s_runs[run].x & 0x7fffffffu, starts = s_runs[run].x >> 31;
+                    const bool whole = starts && (run + 1 < n_runs || last_run_ends);      // complete sums: plain stores, no atomics
                     const uint32_t dbuf = q_flush & 1;
                     const bool tr = trace && blockIdx.x == 0 && t == 0 && q_flush < kTraceLen;
                     if (tr) trace[6 * kTraceLen + q_flush] = clock64();
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                             if (q < n_sets) {
                                 double v = fma((double) hi, 4294967296.0, (double) lo) * P.scale[q];
                                 if (starts) v += bases_in_smem ? s_base[run * n_sets + q] : P.base[q][blk];
-                                if (live) atomicAdd(P.out[q] + (out - P.out[0]), v);
+                                if (live) { if (whole) P.out[q][out - P.out[0]] = v; else atomicAdd(P.out[q] + (out - P.out[0]), v); }
                             }
                         }
                     }
@@ -370,23 +373,23 @@ void build_local_tc5_fragments(const std::vector<double>& delta /* [M] */, const
 // One pass over the genotypes for n_sets (<= kLocalTc5MaxSets) effect sets.  d_steps: the schedule with the
 // first-step-of-block flag in bit 31 of .y; d_b / d_base / d_out / scale per set.  Asynchronous.
 // Marker segments for a pass of n_sets effect sets: consecutive step ranges of at most `cap` steps (their B
-// digits must fit shared memory) that end where a 128-byte line of the strand rows ends (32 marker words),
-// so that every line of the genotypes is fetched from DRAM once; only when not even 32 words' steps fit
-// (blocks of a few markers each) a segment is cut at `cap` steps.
+// digits must fit shared memory) made of WHOLE blocks wherever a block fits, so that a block's sums are
+// complete in one accumulator and stored plainly; only a block longer than `cap` steps is cut (its parts
+// are then added to the output with fp64 atomics).  steps[].y carries the first-step-of-block flag in bit 31.
 void local_tc5_segments(const std::vector<uint2>& steps, uint32_t n_sets, std::vector<uint32_t>& seg_off) {
     const uint32_t cap = std::min<uint32_t>(kMaxSegSteps, kBBytes / (256 * n_sets));
     const uint32_t n_steps = (uint32_t) steps.size();
     seg_off.assign(1, 0u);
     uint32_t pos = 0;
     while (pos < n_steps) {
-        uint32_t best = 0, end = pos;
-        for (uint32_t end_word = (steps[pos].x / 32 + 1) * 32;; end_word += 32) {
-            while (end < n_steps && steps[end].x < end_word) ++end;
-            if (end - pos > cap) break;
-            best = end;
-            if (end == n_steps) break;
+        uint32_t end = pos, best = 0;
+        while (end < n_steps) {                             // extend block by block
+            uint32_t e = end + 1;
+            while (e < n_steps && (steps[e].y & 0x7fffffffu) == (steps[end].y & 0x7fffffffu)) ++e;
+            if (e - pos > cap) break;
+            best = end = e;
         }
-        if (best == 0) best = std::min(n_steps, pos + cap);
+        if (best == 0) best = std::min(n_steps, pos + cap); // the block at `pos` alone is longer than a segment: cut it
         seg_off.push_back(best);
         pos = best;
     }
@@ -422,7 +425,7 @@ int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32
         GSB_CUDA_TRY(cudaMemsetAsync(d_trace, 0, 9 * kTraceLen * sizeof(long long), ctx->stream));
     }
     local_tc5_kernel<<<grid, kThreads, smem, ctx->stream>>>(ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, n_blocks, d_steps,
-                                                           d_seg_off, n_tiles, n_items, items_per_cta, n_sets, P, ctx->d_flag + 2, dbg, d_trace);
+                                                           (uint32_t) seg_off.back(), d_seg_off, n_tiles, n_items, items_per_cta, n_sets, P, ctx->d_flag + 2, dbg, d_trace);
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
     if (d_trace) {
