@@ -373,23 +373,25 @@ void build_local_tc5_fragments(const std::vector<double>& delta /* [M] */, const
 // One pass over the genotypes for n_sets (<= kLocalTc5MaxSets) effect sets.  d_steps: the schedule with the
 // first-step-of-block flag in bit 31 of .y; d_b / d_base / d_out / scale per set.  Asynchronous.
 // Marker segments for a pass of n_sets effect sets: consecutive step ranges of at most `cap` steps (their B
-// digits must fit shared memory) made of WHOLE blocks wherever a block fits, so that a block's sums are
-// complete in one accumulator and stored plainly; only a block longer than `cap` steps is cut (its parts
-// are then added to the output with fp64 atomics).  steps[].y carries the first-step-of-block flag in bit 31.
+// digits must fit shared memory) that end where a 128-byte line of the strand rows ends (32 marker words),
+// so that every line of the genotypes is fetched from DRAM by one segment only; when not even 32 words'
+// steps fit (blocks of a few markers each) a segment is cut at `cap` steps.  A block that a segment boundary
+// cuts is summed in two parts (fp64 atomics on the output); whole blocks are stored plainly.  Cutting at block
+// boundaries instead was measured and is slower: segments then start inside a line, which two segments fetch.
 void local_tc5_segments(const std::vector<uint2>& steps, uint32_t n_sets, std::vector<uint32_t>& seg_off) {
     const uint32_t cap = std::min<uint32_t>(kMaxSegSteps, kBBytes / (256 * n_sets));
     const uint32_t n_steps = (uint32_t) steps.size();
     seg_off.assign(1, 0u);
     uint32_t pos = 0;
     while (pos < n_steps) {
-        uint32_t end = pos, best = 0;
-        while (end < n_steps) {                             // extend block by block
-            uint32_t e = end + 1;
-            while (e < n_steps && (steps[e].y & 0x7fffffffu) == (steps[end].y & 0x7fffffffu)) ++e;
-            if (e - pos > cap) break;
-            best = end = e;
+        uint32_t best = 0, end = pos;
+        for (uint32_t end_word = (steps[pos].x / 32 + 1) * 32;; end_word += 32) {
+            while (end < n_steps && steps[end].x < end_word) ++end;
+            if (end - pos > cap) break;
+            best = end;
+            if (end == n_steps) break;
         }
-        if (best == 0) best = std::min(n_steps, pos + cap); // the block at `pos` alone is longer than a segment: cut it
+        if (best == 0) best = std::min(n_steps, pos + cap);
         seg_off.push_back(best);
         pos = best;
     }
