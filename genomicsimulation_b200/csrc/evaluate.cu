@@ -523,7 +523,11 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
         // gebv_counts_kernel: lane = 4 * digit + c holds, for mma (i, p) of a chunk, register `half`
         // whose byte j is the digit of marker bit 8j + 2p + half of word 4c + i.
         double maxabs = 0.0;
-        for (uint32_t m = 0; m < M; ++m) maxabs = std::max(maxabs, std::fabs(delta[m]));
+        e.all_finite = true;
+        for (uint32_t m = 0; m < M; ++m) {
+            maxabs = std::max(maxabs, std::fabs(delta[m]));
+            e.all_finite = e.all_finite && std::isfinite(delta[m]) && std::isfinite(all[2 * (size_t) m]);
+        }
         int exp2 = 0;
         if (maxabs > 0.0 && std::isfinite(maxabs)) exp2 = 61 - std::ilogb(maxabs);
         // the kernel leaves the count of marker bit (8j + sft) of a word at weight 2^(sft & 6), so
@@ -571,7 +575,9 @@ int gebv_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t ef
     DeviceEffects* e;
     GSB_TRY(get_effects(ctx, eff_index, &e, what));
     const double centre_sum = e->has_centre ? e->centre_sum : 0.0;
-    if (ctx->planes == 1 && ctx->n_markers <= kGebvMaxMarkers) {
+    // an effect set with NaN / Inf entries has no fixed-point image: it goes through the fp64 table kernel, which
+    // propagates them into the breeding values as the reference's sum does (core.c:9587-9597)
+    if (ctx->planes == 1 && ctx->n_markers <= kGebvMaxMarkers && e->all_finite) {
         const size_t counters = (size_t) (ctx->plane_words / kChunkWords + 1) * sizeof(unsigned int);
         GSB_TRY(ctx->s_eval[2].ensure((size_t) n * 8 * sizeof(long long) + counters));
         unsigned long long* d_digits = (unsigned long long*) ctx->s_eval[2].ptr;
@@ -725,7 +731,9 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
         sc.key = key;
         sc.valid = true;
     }
-    if (!sc.usable) {
+    bool finite = true;
+    for (DeviceEffects* e : effs) finite = finite && e->all_finite;
+    if (!sc.usable || !finite) {
         GSB_REQUIRE(!device_out, GSB200_ERR_UNSUPPORTED,
                     "%s: device output needs blocks that are contiguous, ascending, non-overlapping marker ranges on a one-plane store", what);
         uint32_t *d_off, *d_mk;

@@ -110,6 +110,7 @@ struct DeviceEffects {
     double* d_centre = nullptr;       // [M] or null
     double* d_delta = nullptr;        // planes == 1: value_all[m][1] - value_all[m][0]
     double  base_all = 0.0;           // planes == 1: sum_m 2 * value_all[m][0]
+    bool    all_finite = true;        // planes == 1: no NaN / Inf among the effects (else the fixed-point kernels do not apply)
     uint32_t* d_digit_frag = nullptr; // planes == 1: fixed-point digits of delta as mma B fragments
     uint32_t* d_digit_tc5 = nullptr;  // ... in the shared-memory layout of gebv_tc5_kernel
     double  digit_scale = 1.0;        // value of one fixed-point unit

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                 return reinterpret_cast<const uint4*>(store + (uint64_t) rows[ind] * row_words + (tid & 1) * plane_words) + 2 * o_first;
             };
             const uint32_t total = n_run * n_oct;
-            constexpr uint32_t kDepth = 6;
+            constexpr uint32_t kDepth = 4;
             uint4 buf[kDepth][2];
             uint32_t l_tile = tile_lo, l_oct = 0;
             const uint4* lptr = row_ptr(l_tile);

@@ -1131,8 +1131,10 @@ int gsb200_cross_gebv_dev(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_parent1
     // toggles per gamete (crossovers + chromosome boundaries) take the two passes
     const double ls = std::max(m1->lambda_sum, m2->lambda_sum);
     const bool few_toggles = ls + 6.0 * std::sqrt(ls) + (double) std::max(m1->n_chr, m2->n_chr) <= 120.0;
+    GSB_TRY(ensure_effect_tables(ctx, eff_index));
     const bool fused = ctx->planes == 1 && m1->flat && m2->flat && d_pool_rows && n_pool > 0 && tab_bytes <= ((size_t) 2 << 30)
-                       && ctx->n_markers < (1u << 25) && few_toggles && draws->mode == GSB200_DRAWS_PHILOX;
+                       && ctx->n_markers < (1u << 25) && few_toggles && draws->mode == GSB200_DRAWS_PHILOX
+                       && ctx->effects[eff_index].all_finite;
     if (!fused) {
         GSB_TRY(cross_impl(ctx, n, d_parent1_rows, d_parent2_rows, map1, map2, d_out_rows, draws, false, what));
         return gsb200_gebv_dev(ctx, n, d_out_rows, eff_index, d_bv);

@@ -536,3 +536,22 @@ def test_blocks_from_file(helper, tmp_path):
     assert s.blocks_from_file(str(tmp_path / "absent.txt")).export()[0].tolist() == [0]
     rb.free(); b.free()
     r.close(); s.close()
+
+
+def test_non_finite_effects_propagate_like_the_reference():
+    """An effect set holding NaN / Inf has no fixed-point image: GEBVs and local GEBVs then come from the fp64
+    table kernels and carry the NaN / Inf exactly where the oracle's sequential sums do (core.c:9587-9597)."""
+    ds = datasets.synthetic(10, 400, 2, 100.0, seed=23)
+    ds["effects"][0]["eff"][6] = np.nan          # allele 'A' of marker 3
+    ds["effects"][0]["eff"][101] = np.inf        # allele 'T' of marker 50
+    p = port.PortSim.from_dataset(ds)
+    s = engine_from(ds)
+    want, got = p.calculate_bvs(1, 0), s.calculate_bvs(1, 1)
+    assert np.array_equal(np.isnan(want), np.isnan(got)) and np.array_equal(np.isposinf(want), np.isposinf(got))
+    ok = np.isfinite(want)
+    bv_close(got[ok], want[ok], scale=1.0)
+    off, mk = p.blocks_evenlength(4, 0, n_chr=2)
+    wl, gl = p.calculate_local_bvs(1, off, mk, 0), s.calculate_local_bvs(1, off, mk, 1)
+    assert np.array_equal(np.isnan(wl), np.isnan(gl)) and np.array_equal(np.isinf(wl), np.isinf(gl))
+    p.close()
+    s.close()
