@@ -135,6 +135,7 @@ HOST_SYMBOLS = {
     "gsb_set_draw_mode": (None, [VP, I32, U64]),
     "gsb_set_draw_source": (None, [VP, VP, VP]),
     "gsb_load_genotypes": (UINT, [VP, UINT, VP, VP]),
+    "gsb_load_genotype_file": (UINT, [VP, C.c_char_p]),
     "gsb_load_map": (UINT, [VP, UINT, VP, VP, VP, VP, VP]),
     "gsb_load_effects": (UINT, [VP, VP, VP, VP, VP]),
     "gsb_delete_recombination_map": (None, [VP, UINT]),

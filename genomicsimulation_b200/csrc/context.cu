@@ -48,7 +48,7 @@ void DeviceMap::release() {
 }
 
 void DeviceEffects::release() {
-    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag, d_digit_tc5, d_local, d_local_tc5, d_bvq };
+    void* ptrs[] = { d_value_all, d_value_first, d_centre, d_delta, d_digit_frag, d_digit_tc5, d_local, d_local_tc5, d_bvq, d_nonfinite };
     for (void* p : ptrs) if (p) cudaFree(p);
     *this = DeviceEffects();
 }

@@ -187,15 +187,30 @@ __global__ void gebv_finish_kernel(const long long* __restrict__ digit_sums, uin
     out[i] = offset + v * scale;
 }
 
+struct NonFiniteEntry { uint32_t marker; uint8_t allele; double eff; };
+
 // ------------------------------------------------------------------ GEBV, any number of planes
 // Warp per individual, lane per marker of a word; table lookups by code.
 __global__ void gebv_generic_kernel(const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
                                     uint32_t planes, uint32_t n_markers, const uint32_t* __restrict__ rows, uint32_t n,
-                                    const double* __restrict__ value, double offset, double* __restrict__ out) {
+                                    const double* __restrict__ value, double offset, double* __restrict__ out,
+                                    const uint8_t* __restrict__ dict_sym, const NonFiniteEntry* __restrict__ odd, uint32_t n_odd) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
     const uint32_t* row = store + (uint64_t) rows[warp] * row_words;
     double acc = 0.0;
+    // NaN / Inf effect entries are kept out of the tables and multiplied by their count here, as the reference does
+    // (count * eff, core.c:9590-9594): an allele the individual does NOT carry then contributes 0 * Inf = NaN
+    for (uint32_t j = lane; j < n_odd; j += 32) {
+        const uint32_t m = odd[j].marker;
+        uint32_t c0 = 0, c1 = 0;
+        for (uint32_t p = 0; p < planes; ++p) {
+            c0 |= ((row[(uint64_t) p * plane_words + (m >> 5)] >> (m & 31)) & 1u) << p;
+            c1 |= ((row[(uint64_t) (planes + p) * plane_words + (m >> 5)] >> (m & 31)) & 1u) << p;
+        }
+        const uint8_t* sym = dict_sym + ((size_t) m << planes);
+        acc += (double) ((sym[c0] == odd[j].allele) + (sym[c1] == odd[j].allele)) * odd[j].eff;
+    }
     for (uint32_t m = lane; m < n_markers; m += 32) {
         uint32_t c0 = 0, c1 = 0;
         for (uint32_t p = 0; p < planes; ++p) {
@@ -499,13 +514,24 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
             bool got = false;
             for (uint32_t x = lo; x < hi; ++x) {
                 if (e.allele[x] != sym[c]) continue;
-                sum += e.eff[x];
+                if (std::isfinite(e.eff[x])) sum += e.eff[x];          // non-finite entries: see e.nonfinite below
                 if (!got) { first[((size_t) m << planes) + c] = e.eff[x]; got = true; }
             }
             all[((size_t) m << planes) + c] = sum;
         }
     }
+    // entries the whole-genome sum multiplies by their count (gebv_generic_kernel)
+    std::vector<NonFiniteEntry> odd;
+    for (uint32_t m = 0; m < M; ++m)
+        for (uint32_t x = m ? e.cumn[m - 1] : 0; x < e.cumn[m]; ++x)
+            if (!std::isfinite(e.eff[x])) odd.push_back(NonFiniteEntry{ m, e.allele[x], e.eff[x] });
+    e.n_nonfinite = (uint32_t) odd.size();
     cudaStreamSynchronize(ctx->stream);
+    {
+        NonFiniteEntry* d_odd = (NonFiniteEntry*) e.d_nonfinite;
+        GSB_TRY(to_device_vec(odd, &d_odd));
+        e.d_nonfinite = d_odd;
+    }
     GSB_TRY(to_device_vec(all, &e.d_value_all));
     GSB_TRY(to_device_vec(first, &e.d_value_first));
     e.h_value_first = first;
@@ -528,6 +554,7 @@ int ensure_effect_tables(gsb200_ctx* ctx, uint32_t eff_index) {
             maxabs = std::max(maxabs, std::fabs(delta[m]));
             e.all_finite = e.all_finite && std::isfinite(delta[m]) && std::isfinite(all[2 * (size_t) m]);
         }
+        e.all_finite = e.all_finite && e.n_nonfinite == 0;
         int exp2 = 0;
         if (maxabs > 0.0 && std::isfinite(maxabs)) exp2 = 61 - std::ilogb(maxabs);
         // the kernel leaves the count of marker bit (8j + sft) of a word at weight 2^(sft & 6), so
@@ -603,10 +630,11 @@ int gebv_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t ef
         gebv_finish_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const long long*) d_digits, n, e->digit_scale,
                                                                     e->base_all - centre_sum, d_out);
     } else {
+        GSB_TRY(sync_dictionary(ctx));
         const uint64_t threads = (uint64_t) n * 32;
         gebv_generic_kernel<<<(unsigned) ((threads + 127) / 128), 128, 0, ctx->stream>>>(
             ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->planes, ctx->n_markers, d_rows, n,
-            e->d_value_all, -centre_sum, d_out);
+            e->d_value_all, -centre_sum, d_out, ctx->d_dict_sym, (const NonFiniteEntry*) e->d_nonfinite, e->n_nonfinite);
     }
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());

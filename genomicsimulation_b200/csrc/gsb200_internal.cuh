@@ -110,6 +110,8 @@ struct DeviceEffects {
     double* d_centre = nullptr;       // [M] or null
     double* d_delta = nullptr;        // planes == 1: value_all[m][1] - value_all[m][0]
     double  base_all = 0.0;           // planes == 1: sum_m 2 * value_all[m][0]
+    void*   d_nonfinite = nullptr;    // NaN / Inf effect entries (marker, allele, effect), multiplied by their count like the reference does
+    uint32_t n_nonfinite = 0;
     bool    all_finite = true;        // planes == 1: no NaN / Inf among the effects (else the fixed-point kernels do not apply)
     uint32_t* d_digit_frag = nullptr; // planes == 1: fixed-point digits of delta as mma B fragments
     uint32_t* d_digit_tc5 = nullptr;  // ... in the shared-memory layout of gebv_tc5_kernel

@@ -18,7 +18,8 @@ __global__ void pack_kernel(uint32_t* __restrict__ store, uint64_t row_words, ui
                             uint32_t planes, uint32_t n_markers,
                             const uint32_t* __restrict__ rows, uint32_t n,
                             const uint8_t* __restrict__ chars,
-                            const uint8_t* __restrict__ dict_sym, const uint16_t* __restrict__ dict_n) {
+                            const uint8_t* __restrict__ dict_sym, const uint16_t* __restrict__ dict_n,
+                            int* __restrict__ unknown /* raised when a symbol is not in its marker's dictionary */) {
     const uint32_t words = (n_markers + 31) / 32;
     const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (uint64_t) n * words) return;
@@ -36,8 +37,9 @@ __global__ void pack_kernel(uint32_t* __restrict__ store, uint64_t row_words, ui
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const uint8_t a = src[2 * (size_t) m + h];
-            uint32_t code = 0;
+            uint32_t code = 0xffffffffu;
             for (uint32_t c = 0; c < nc; ++c) if (sym[c] == a) { code = c; break; }
+            if (code == 0xffffffffu) { *unknown = 1; code = 0; }
 #pragma unroll
             for (int p = 0; p < 8; ++p) acc[h][p] |= ((code >> p) & 1u) << (m & 31);
         }
@@ -225,17 +227,12 @@ uint32_t gsb200_store_plane_words(const gsb200_ctx* ctx) { return ctx ? ctx->pla
 uint64_t gsb200_store_row_bytes(const gsb200_ctx* ctx) { return ctx ? ctx->row_words() * sizeof(uint32_t) : 0; }
 void* gsb200_store_device_ptr(gsb200_ctx* ctx) { return ctx ? (void*) ctx->d_store : nullptr; }
 
-int gsb200_store_upload_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const char* chars) {
-    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
-    if (n == 0) return GSB200_OK;
-    GSB_REQUIRE(chars != nullptr, GSB200_ERR_ARG, "gsb200_store_upload_chars: null chars");
-    GSB_TRY(check_rows(ctx, n, rows, "gsb200_store_upload_chars"));
-    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+// Symbols of rows [lo, hi) that their marker's dictionary does not hold yet are added in order of first
+// appearance (row by row, marker by marker, strand 0 before strand 1), widening the store when a marker runs
+// out of codes.  Rows whose symbols are all known are cleared by a vectorisable pass against the two commonest
+// symbols per marker; only rows that fail it take the slow scan.
+static int extend_dictionary(gsb200_ctx* ctx, uint32_t lo, uint32_t hi, const char* chars, bool* changed_out) {
     const uint32_t M = ctx->n_markers;
-
-    // 1. extend the dictionary with any symbol not seen before at its marker.  Rows whose symbols
-    //    are all known (every row but the first few) are cleared by a vectorisable pass against
-    //    the two commonest symbols per marker; only rows that fail it take the slow scan.
     uint32_t planes = ctx->planes;
     bool changed = false;
     std::vector<uint8_t> e0(2 * (size_t) M), e1(2 * (size_t) M);
@@ -243,8 +240,6 @@ int gsb200_store_upload_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows,
         for (uint32_t m = 0; m < M; ++m) {
             const uint8_t* sym = &ctx->dict_sym[(size_t) m << ctx->planes];
             const uint32_t nc = ctx->dict_n[m];
-            // a marker nobody uploaded yet matches nothing: both slots hold a value the row
-            // cannot equal in both... so force the slow scan by using two different sentinels
             const uint8_t a0 = nc > 0 ? sym[0] : 0, a1 = nc > 1 ? sym[1] : a0;
             e0[2 * (size_t) m] = e0[2 * (size_t) m + 1] = a0;
             e1[2 * (size_t) m] = e1[2 * (size_t) m + 1] = a1;
@@ -253,7 +248,7 @@ int gsb200_store_upload_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows,
     refresh_expanded();
     bool any_empty = false;
     for (uint32_t m = 0; m < M && !any_empty; ++m) any_empty = ctx->dict_n[m] == 0;
-    for (uint32_t i = 0; i < n; ++i) {
+    for (uint32_t i = lo; i < hi; ++i) {
         const uint8_t* g = (const uint8_t*) chars + (size_t) i * 2 * M;
         if (!any_empty) {
             uint8_t bad = 0;
@@ -288,26 +283,57 @@ int gsb200_store_upload_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows,
         }
     }
     if (changed) { ctx->dict_dirty = true; ++ctx->dict_version; }
-    GSB_TRY(sync_dictionary(ctx));
+    *changed_out = changed;
+    return GSB200_OK;
+}
 
-    // 2. stage chars on the device in bounded chunks and pack
+// chars of rows[0 .. n) -> the packed store, in bounded chunks staged on the device; *unknown (host) tells
+// whether the pack kernel met a symbol its dictionary does not hold
+static int pack_rows(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const char* chars, int* unknown) {
+    const uint32_t M = ctx->n_markers;
     const size_t row_chars = 2 * (size_t) M;
     const uint32_t chunk = (uint32_t) std::max<size_t>(1, std::min<size_t>(n, ((size_t) 256 << 20) / row_chars));
     const uint32_t words = (M + 31) / 32;
+    GSB_TRY(sync_dictionary(ctx));
+    GSB_CUDA_TRY(cudaMemsetAsync(ctx->d_flag + 3, 0, sizeof(int), ctx->stream));
+    uint32_t* d_rows = nullptr;
+    GSB_TRY(upload_u32(ctx, ctx->s_rows[0], rows, n, &d_rows));
+    GSB_TRY(ctx->s_io.ensure((size_t) chunk * row_chars));
     for (uint32_t done = 0; done < n; done += chunk) {
         const uint32_t cnt = std::min(chunk, n - done);
-        uint32_t* d_rows = nullptr;
-        GSB_TRY(upload_u32(ctx, ctx->s_rows[0], rows + done, cnt, &d_rows));
-        GSB_TRY(ctx->s_io.ensure(cnt * row_chars));
-        GSB_CUDA_TRY(cudaMemcpyAsync(ctx->s_io.ptr, chars + (size_t) done * row_chars, cnt * row_chars,
-                                     cudaMemcpyHostToDevice, ctx->stream));
+        // stream-ordered: the copy of chunk k + 1 waits for the pack of chunk k by itself
+        GSB_CUDA_TRY(cudaMemcpyAsync(ctx->s_io.ptr, chars + (size_t) done * row_chars, cnt * row_chars, cudaMemcpyHostToDevice, ctx->stream));
         const uint64_t threads = (uint64_t) cnt * words;
         pack_kernel<<<(unsigned) ((threads + 127) / 128), 128, 0, ctx->stream>>>(
-            ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->planes, M, d_rows, cnt,
-            (const uint8_t*) ctx->s_io.ptr, ctx->d_dict_sym, ctx->d_dict_n);
+            ctx->d_store, ctx->row_words(), ctx->plane_words, ctx->planes, M, d_rows + done, cnt,
+            (const uint8_t*) ctx->s_io.ptr, ctx->d_dict_sym, ctx->d_dict_n, ctx->d_flag + 3);
         ++ctx->launches;
         GSB_CUDA_TRY(cudaGetLastError());
-        GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    GSB_CUDA_TRY(cudaMemcpyAsync(unknown, ctx->d_flag + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GSB200_OK;
+}
+
+int gsb200_store_upload_chars(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const char* chars) {
+    GSB_REQUIRE(ctx != nullptr, GSB200_ERR_ARG, "null context");
+    if (n == 0) return GSB200_OK;
+    GSB_REQUIRE(chars != nullptr, GSB200_ERR_ARG, "gsb200_store_upload_chars: null chars");
+    GSB_TRY(check_rows(ctx, n, rows, "gsb200_store_upload_chars"));
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    // The dictionary is seeded from the first few rows on the host; everything else is packed OPTIMISTICALLY: the
+    // pack kernel looks every symbol up on the device and raises a flag for one it does not know, and only then
+    // (a new symbol deep inside a batch: rare after the founders' first rows) the host scans the whole batch, extends
+    // the dictionary in order of first appearance — the codes come out exactly as a row-by-row scan gives them —
+    // and the batch is packed again.  The common case crosses the chars once, at the speed of the PCIe copy.
+    bool changed = false;
+    GSB_TRY(extend_dictionary(ctx, 0, std::min<uint32_t>(n, 8), chars, &changed));
+    int unknown = 0;
+    GSB_TRY(pack_rows(ctx, n, rows, chars, &unknown));
+    if (unknown) {
+        GSB_TRY(extend_dictionary(ctx, 0, n, chars, &changed));
+        GSB_TRY(pack_rows(ctx, n, rows, chars, &unknown));
+        GSB_REQUIRE(!unknown, GSB200_ERR_ARG, "gsb200_store_upload_chars: internal: a symbol is still missing from the dictionary");
     }
     return GSB200_OK;
 }

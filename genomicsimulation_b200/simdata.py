@@ -119,6 +119,11 @@ class SimData:
         self._check()
         return grp
 
+    def load_genotype_file(self, path):
+        grp = self.L.gsb_load_genotype_file(self.d, str(path).encode())
+        self._check()
+        return grp
+
     def add_map(self, m):
         lam = np.ascontiguousarray(m["lam"], dtype=np.float64)
         off = np.ascontiguousarray(m["chr_offset"], dtype=np.uint32)

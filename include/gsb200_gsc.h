@@ -93,6 +93,10 @@ void gsb_set_draw_source(gsb_SimData* d, double (*unif)(void), double (*rpois)(d
 /* ---- setup: the payload side of gsc_load_data_files (core.c:7453-7496) */
 /* n genotypes, chars = n x 2M in the reference's layout; names may be NULL. New group. */
 gsb_GroupNum gsb_load_genotypes(gsb_SimData* d, unsigned int n, const char* chars, const char* const* names);
+/* gsc_load_genotypefile_matrix (core.c:7085-7428) for a simulation whose marker names are known (gsb_set_marker_names):
+ * the reference's own detection of cell style, header row, orientation and corner cell; the parsed block goes to
+ * the device in one piece.  New group, or 0 with a NOTE. */
+gsb_GroupNum gsb_load_genotype_file(gsb_SimData* d, const char* filename);
 gsb_MapID gsb_load_map(gsb_SimData* d, unsigned int n_chr, const double* expected_n_crossovers,
                        const unsigned int* chr_offset, const double* dists, const unsigned int* marker_index,
                        const unsigned char* has_dists);
