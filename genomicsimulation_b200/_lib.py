@@ -107,6 +107,7 @@ ENGINE_SYMBOLS = {
     "gsb200_shard_cross_begin_run": (I32, [VP, U32, U32, VP, U32, C.POINTER(Draws), I32]),
     "gsb200_shard_cross_picks": (I32, [VP, VP, VP, VP]),
     "gsb200_shard_finish": (I32, [VP]),
+    "gsb200_shard_poll": (I32, [VP]),
     "gsb200_shard_cross_dev": (I32, [VP, U32, U32, VP, U32, C.POINTER(Draws), VP]),
     "gsb200_shard_selected": (I32, [VP, VP, VP, VP]),
     "gsb200_shard_local_bvs": (I32, [VP, U32, VP]),

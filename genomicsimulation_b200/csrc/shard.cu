@@ -160,7 +160,9 @@ struct gsb200_shard {
     // pinned host staging, so that what the host mirror needs of a generation (local GEBVs, the picked pairs, the
     // selected parents' ids) comes down while the device carries on: [bvs: max_total f64 | picks: 2 max_total u32 | sel ids: max_pool u32]
     char* h_pin = nullptr;
-    cudaEvent_t ev_bv = nullptr, ev_picks = nullptr;
+    cudaEvent_t ev_bv = nullptr, ev_picks = nullptr, ev_flags = nullptr;
+    int* h_flags = nullptr;              // pinned: [0] the shard's exchange flag, [1] the context's splice flag, as of the last poll
+    bool poll_pending = false;
     bool bv_staged = false, picks_staged = false;
     uint32_t staged_local = 0, staged_offspring = 0;
     // optional phase timing: a ring of CUDA events, one set per generation (epoch)
@@ -210,6 +212,8 @@ int gsb200_shard_create(gsb200_ctx* ctx, uint32_t rank, uint32_t world, uint64_t
     if (e == cudaSuccess) e = cudaHostAlloc((void**) &s->h_pin, max_total * 16 + (size_t) max_pool * 4, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_bv, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_picks, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_flags, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**) &s->h_flags, 2 * sizeof(int), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         set_error("gsb200_shard_create: allocating %zu bytes of exchange buffers failed: %s", s->slab_bytes, cudaGetErrorString(e));
         gsb200_shard_destroy(s);
@@ -243,6 +247,8 @@ void gsb200_shard_destroy(gsb200_shard* s) {
     if (s->h_pin) cudaFreeHost(s->h_pin);
     if (s->ev_bv) cudaEventDestroy(s->ev_bv);
     if (s->ev_picks) cudaEventDestroy(s->ev_picks);
+    if (s->ev_flags) cudaEventDestroy(s->ev_flags);
+    if (s->h_flags) cudaFreeHost(s->h_flags);
     if (s->slab) cudaFree(s->slab);
     if (s->d_counters) cudaFree(s->d_counters);
     if (s->d_err) cudaFree(s->d_err);
@@ -462,6 +468,24 @@ int gsb200_shard_cross_picks(gsb200_shard* s, const uint32_t** picked1, const ui
     if (picked1) *picked1 = p;
     if (picked2) *picked2 = p + s->staged_offspring;
     if (selected_ids) *selected_ids = reinterpret_cast<const uint32_t*>(s->h_pin + s->max_total * 16);
+    return GSB200_OK;
+}
+
+int gsb200_shard_poll(gsb200_shard* s) {
+    GSB_REQUIRE(s != nullptr, GSB200_ERR_ARG, "null shard");
+    gsb200_ctx* ctx = s->ctx;
+    GSB_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (s->poll_pending && cudaEventQuery(s->ev_flags) == cudaSuccess) {
+        s->poll_pending = false;
+        if (s->h_flags[0] || s->h_flags[1]) return gsb200_shard_finish(s);      // something went wrong: the blocking path words it (and clears the flags)
+    }
+    cudaGetLastError();
+    if (!s->poll_pending) {
+        GSB_CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GSB_CUDA_TRY(cudaMemcpyAsync(s->h_flags + 1, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GSB_CUDA_TRY(cudaEventRecord(s->ev_flags, ctx->stream));
+        s->poll_pending = true;
+    }
     return GSB200_OK;
 }
 

@@ -303,6 +303,9 @@ int  gsb200_shard_cross_begin_run(gsb200_shard* shard, uint32_t n, uint32_t map,
                                   const gsb200_draws* draws, int want_picks);
 int  gsb200_shard_cross_picks(gsb200_shard* shard, const uint32_t** picked1, const uint32_t** picked2, const uint32_t** selected_ids);
 int  gsb200_shard_finish(gsb200_shard* shard);
+/* ... without waiting: reports a failure of an EARLIER generation once its flags have come down (they are sticky),
+ * and asks for the current ones.  For a host that enqueues generation g + 1 while g is still being spliced. */
+int  gsb200_shard_poll(gsb200_shard* shard);
 /* ... asynchronous: d_out_rows NULL = rows first_out_row, first_out_row + 1, ...; d_picks (device, 2n) may be NULL */
 int  gsb200_shard_cross_dev(gsb200_shard* shard, uint32_t n, uint32_t map, const uint32_t* d_out_rows, uint32_t first_out_row,
                             const gsb200_draws* draws, uint32_t* d_picks);

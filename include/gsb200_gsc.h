@@ -192,8 +192,9 @@ gsb_GroupNum gsb_shard_select_and_cross(gsb_SimData* d, gsb_GroupNum group, unsi
                                         unsigned int top_n, _Bool lowIsBest, unsigned long long n_offspring_total,
                                         gsb_MapID which_map, gsb_GenOptions g);
 /* The call above returns while the offspring are still being spliced (everything later on this SimData is
- * ordered behind them); this waits for them and reports a failed exchange or splice.  Called by the next
- * gsb_shard_select_and_cross and by gsb_delete_simdata by themselves.  0 on success. */
+ * ordered behind them); this waits for them and reports a failed exchange or splice.  The next
+ * gsb_shard_select_and_cross only POLLS for such a failure (it queues its own work behind the generation in
+ * flight), gsb_delete_simdata waits.  0 on success. */
 int gsb_shard_finish(gsb_SimData* d);
 unsigned int gsb_shard_get_local_bvs(gsb_SimData* d, unsigned int n_local, double* output);
 unsigned int gsb_shard_last_selection(gsb_SimData* d, unsigned long long n_total, double* bvs_out, unsigned int top_n, unsigned int* selected_out);
