@@ -460,12 +460,17 @@ def engine_arm(a):
             dist.barrier()
         t = time.perf_counter()
         new = sim.shard_select_and_cross(g, n_total, 1, top, n_total)      # pedigrees tracked, ids allocated
+        ta = time.perf_counter()
         bv = sim.shard_local_bvs(bv_host)
+        tb = time.perf_counter()
         sim.delete_group(g)
         g = new
         if world > 1:
             dist.barrier()
         e2e_t.append(time.perf_counter() - t)
+        if os.environ.get("GSB200_BENCH_VERBOSE") and rank == 0:
+            print("e2e step %d: select_and_cross %.3f ms, local_bvs %.3f ms, delete_group %.3f ms" %
+                  (i, (ta - t) * 1e3, (tb - ta) * 1e3, (time.perf_counter() - tb) * 1e3), file=sys.stderr)
         assert bv.shape[0] == n
     te = torch.tensor([float(np.mean(e2e_t[2:]))], dtype=torch.float64, device="cuda")
     if world > 1:
