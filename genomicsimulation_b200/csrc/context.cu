@@ -126,7 +126,7 @@ int gsb200_create(gsb200_ctx** out, int device_ordinal, uint32_t n_markers) {
     for (auto& sc : ctx->s_eval) sc.stream = ctx->stream;
     for (auto& sc : ctx->s_chain) sc.stream = ctx->stream;
     for (auto& sc : ctx->s_bv) sc.stream = ctx->stream;
-    ctx->s_io.stream = ctx->s_null.stream = ctx->s_select.stream = ctx->local_sched.d_steps.stream = ctx->local_sched.d_steps_tc5.stream = ctx->stream;
+    ctx->s_io.stream = ctx->s_null.stream = ctx->s_select.stream = ctx->local_sched.d_steps.stream = ctx->local_sched.d_plan.stream = ctx->local_sched.d_bstream.stream = ctx->stream;
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess) {
@@ -162,7 +162,8 @@ void gsb200_destroy(gsb200_ctx* ctx) {
     ctx->s_null.release();
     ctx->s_select.release();
     ctx->local_sched.d_steps.release();
-    ctx->local_sched.d_steps_tc5.release();
+    ctx->local_sched.d_plan.release();
+    ctx->local_sched.d_bstream.release();
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);        // the stream-ordered frees above
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->d_store) cudaFree(ctx->d_store);

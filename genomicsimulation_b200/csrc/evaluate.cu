@@ -750,10 +750,6 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
         if (sc.usable) {
             GSB_TRY(sc.d_steps.ensure(sc.steps.size() * sizeof(uint2)));
             GSB_CUDA_TRY(cudaMemcpyAsync(sc.d_steps.ptr, sc.steps.data(), sc.steps.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-            std::vector<uint2> flagged(sc.steps);
-            for (size_t b = 0; b + 1 < sc.block_first.size(); ++b) flagged[sc.block_first[b]].y |= 0x80000000u;
-            GSB_TRY(sc.d_steps_tc5.ensure(flagged.size() * sizeof(uint2)));
-            GSB_CUDA_TRY(cudaMemcpyAsync(sc.d_steps_tc5.ptr, flagged.data(), flagged.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
             GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         }
         sc.key = key;
@@ -845,13 +841,8 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
     static const int forced_path = [] { const char* v = getenv("GSB200_LOCAL_PATH"); return !v ? 0 : strcmp(v, "tc5") == 0 ? 2 : strcmp(v, "mma") == 0 ? 1 : 0; }();
     const bool use_tc5 = forced_path == 2 || (forced_path == 0 && n_effect_sets >= kLocalTc5MinSets);
     if (use_tc5) {
-        const size_t out_bytes = (size_t) n * 2 * n_blocks * sizeof(double);
         for (uint32_t q0 = 0; q0 < n_effect_sets; q0 += kLocalTc5MaxSets) {
             const uint32_t sets = std::min<uint32_t>(kLocalTc5MaxSets, n_effect_sets - q0);
-            std::vector<uint32_t> seg_off;
-            local_tc5_segments(steps, sets, seg_off);
-            uint32_t* d_seg_off;
-            GSB_TRY(upload_u32(ctx, ctx->s_rows[2], seg_off.data(), seg_off.size(), &d_seg_off));
             // host output: the pass's matrices are staged on the device in slabs of individuals
             const size_t slab = device_out ? (size_t) n : std::max<size_t>(64, std::min<size_t>(n, (((size_t) 1 << 30) / (2 * (size_t) n_blocks * sizeof(double))) / sets / 64 * 64));
             const size_t slab_bytes = slab * 2 * (size_t) n_blocks * sizeof(double);
@@ -868,9 +859,8 @@ static int local_gebv_multi_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* ro
                     d_base[q] = (const double*) ((const char*) e->d_local + frag_bytes);
                     scale[q] = e->local_scale;
                     d_out[q] = device_out ? outs[q0 + q] : (double*) ((char*) ctx->s_eval[1].ptr + slab_bytes * q);
-                    GSB_CUDA_TRY(cudaMemsetAsync(d_out[q], 0, device_out ? out_bytes : (size_t) cnt * 2 * n_blocks * sizeof(double), ctx->stream));
                 }
-                GSB_TRY(local_tc5_launch(ctx, cnt, d_rows + done, n_blocks, (const uint2*) sc.d_steps_tc5.ptr, seg_off, d_seg_off, sets, d_b, d_base, d_out, scale));
+                GSB_TRY(local_tc5_launch(ctx, cnt, d_rows + done, n_blocks, steps, block_first, sets, d_b, d_base, d_out, scale));
                 if (!device_out)
                     for (uint32_t q = 0; q < sets; ++q)
                         GSB_CUDA_TRY(cudaMemcpyAsync(outs[q0 + q] + (size_t) done * 2 * n_blocks, d_out[q],

@@ -142,10 +142,11 @@ struct LocalSchedule {
     std::vector<uint2> steps;           // (marker word, block)
     std::vector<uint32_t> block_first;  // first step of each non-empty block, then n_steps
     Scratch d_steps;
-    Scratch d_steps_tc5;                // the same with bit 31 of .y set on the first step of every block (local_tc5.cu)
+    Scratch d_plan;                     // local_tc5.cu: block ranges, runs, step records of the last launch
+    Scratch d_bstream;                  // local_tc5.cu: the B digits of the pass's effect sets, interleaved per group of 8 steps
 };
 
-constexpr uint32_t kLocalTc5MaxSets = 12;   // effect sets per pass of the tcgen05 local-GEBV kernel (N = 8 * sets <= 96)
+constexpr uint32_t kLocalTc5MaxSets = 10;   // effect sets per pass of the tcgen05 local-GEBV kernel (N = 8 * sets <= 80: three accumulators in TMEM)
 
 }  // namespace gsb
 
@@ -203,9 +204,8 @@ int gebv_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, const u
 // local_tc5.cu
 void build_local_tc5_fragments(const std::vector<double>& delta, const std::vector<uint2>& steps, const uint32_t* block_offsets,
                                const uint32_t* block_markers, int exp2, std::vector<uint32_t>& frag);
-void local_tc5_segments(const std::vector<uint2>& steps, uint32_t n_sets, std::vector<uint32_t>& seg_off);
-int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t n_blocks, const uint2* d_steps,
-                     const std::vector<uint32_t>& seg_off, const uint32_t* d_seg_off,
+int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t n_blocks,
+                     const std::vector<uint2>& steps, const std::vector<uint32_t>& block_first,
                      uint32_t n_sets, const uint32_t* const* d_b, const double* const* d_base, double* const* d_out, const double* scale);
 int upload_u32(gsb200_ctx* ctx, Scratch& s, const uint32_t* host, size_t n, uint32_t** out);
 int check_rows(gsb200_ctx* ctx, uint32_t n, const uint32_t* rows, const char* what);

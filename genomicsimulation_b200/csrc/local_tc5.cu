@@ -3,25 +3,35 @@
 // core.c:9979-10090, computed for up to 10 effect sets in one pass over the genotypes).
 //
 // The contraction: (strands x markers) bits  x  (markers x 8 * sets) fixed-point digits, int32
-// accumulation per marker block, recombined in fp64 per (strand, block, set).  gebv_tc5.cu showed
-// that tcgen05.mma with N = 8 is bound by streaming its A operand (~90 cycles per 128 x 32-byte tile
-// whatever N is); with N = 8 * sets the same operand is reused by every effect set — ten sets cost
-// what one does.
+// accumulation per marker block, recombined in fp64 per (strand, block, set).  With N = 8 * sets columns
+// one A operand serves every effect set.  What the instructions cost decided the structure
+// (profiles/r2_umma_i8_probe2.txt, r2_commit_probe.txt, r2_tmem_bw_probe.txt): a tcgen05.mma.kind::i8 of
+// M = 128, K = 32 takes 47 cycles up to N = 96 (then 128 N / 256) — ten sets cost what one does — but a
+// tcgen05.commit stalls the issuing thread ~300-400 cycles, so everything that is recycled behind the MMAs
+// is recycled in UNITS of up to 20 steps with ONE commit per unit.
 //
-//   * a CTA owns a marker SEGMENT — up to ~200 KB of B digits resident in shared memory — and walks
-//     tiles of 64 individuals (128 strand rows = the 128 TMEM lanes);
-//   * 4 expander warps: thread t loads 32 contiguous bytes (8 marker words) of ITS strand row, turns
-//     each word into 8 operand registers `w & (0x01010101 << s)` (byte b = bit 8b + s at weight 2^s; the
-//     weight is divided out of the digits on the host) and writes them to its own TMEM lane with
-//     tcgen05.st.32x32b — one K = 32 step per word, so a step is 32 CONTIGUOUS markers and block
-//     boundaries cost at most one extra step (the word that straddles them, its B digits zeroed outside
-//     the block), exactly the step schedule of the mma.sync kernel (evaluate.cu);
-//   * 1 issuer thread: per step one tcgen05.mma.kind::i8, M = 128, N = 8 * sets, K = 32, A from TMEM,
-//     B through a shared-memory descriptor; the accumulator switches (double-buffered) at every block
-//     boundary;
-//   * 4 epilogue warps: tcgen05.ld of a finished block's 8 * sets digit sums per strand, Horner in fp64,
-//     scale, add to the output matrices (fp64 atomics: a block may span two segments; the outputs are
-//     zeroed by the caller and the per-block base is added by the segment the block starts in).
+// Work item = (tile of 64 individuals = 128 strand rows = the 128 TMEM lanes) x (range of whole blocks).
+// A CTA walks its items; inside an item everything streams:
+//   * A-loader warp: cp.async, 8 lanes per strand row and 128-byte line (32 marker words), into a ring
+//     of 3 lines in shared memory — the rows of a tile are 2 x plane_words apart, so a lane per row (the
+//     first version) made every warp request touch 32 different lines;
+//   * a unit = the steps of one 16-word half line (cut at 20 steps); 4 expander warps: thread t reads ITS
+//     row's 64 bytes of the half line, turns each word into 8 operand registers `w & (0x01010101 << s)`
+//     (byte b = bit 8b + s at weight 2^s; the weight is divided out of the digits on the host) and writes them
+//     to its TMEM lane with tcgen05.st.32x32b into one of two operand stages — one K = 32 step per word, so a
+//     step is 32 CONTIGUOUS markers and a block boundary costs at most one extra step (the word that
+//     straddles it, B digits zeroed outside the block);
+//   * B-loader thread: a unit's step records and digits in one cp.async.bulk into a ring of stages; B is
+//     re-read from L2 for every tile (2 560 bytes per step at 10 sets), which keeps every block's sum in
+//     ONE accumulator — the first version kept a marker segment's B resident instead and paid for it with
+//     fp64 atomics on every block that a segment boundary cut;
+//   * issuer thread: per step one tcgen05.mma.kind::i8, M = 128, N = 8 * sets (padded to 16), K = 32, A from
+//     TMEM, B through a shared-memory descriptor; three accumulators in rotation, one per block in flight;
+//     a commit when a block ends (its sums are ready) and one per unit (operand and B stage are free);
+//   * 4 epilogue warps: tcgen05.ld of a finished block's 8 * sets digit sums per strand, exact integer
+//     recombination, scale + base in fp64, then four blocks at a time are transposed through shared memory
+//     so that a warp store writes 32 contiguous bytes per strand row instead of 8; blocks without markers
+//     are written as 0 here (no memset of the outputs).
 //
 // Every mbarrier wait is bounded (tc5_common.cuh): a protocol bug raises the context's flag instead of
 // hanging the GPU.
@@ -40,23 +50,74 @@ namespace gsb {
 
 namespace {
 
-constexpr uint32_t kExpanders = 128, kEpilogue = 128;
-constexpr uint32_t kThreads = kExpanders + kEpilogue + 32;
-constexpr uint32_t kAStages = 4;
-constexpr uint32_t kStageCols = 64;            // 8 words x 8 columns
-constexpr uint32_t kDCol1 = 128;               // second accumulator
-constexpr uint32_t kACol0 = 256;
+constexpr uint32_t kWarpIssuer = 8, kWarpALoader = 9, kWarpBLoader = 10;
+constexpr uint32_t kThreads = 11 * 32;           // 4 expander + 4 epilogue warps, issuer, A loader, B loader
+constexpr uint32_t kALines = 3;                  // ring of 128-byte lines (32 marker words x 128 strand rows) in shared memory
+constexpr uint32_t kARowBytes = 144;             // 128 + 16: the expanders' 16-byte reads of 8 different rows hit different banks
+constexpr uint32_t kALineBytes = 128 * kARowBytes;
+constexpr uint32_t kUnitWords = 16, kUnitSteps = 20;
+constexpr uint32_t kStageCols = 8 * kUnitWords;  // an operand stage in TMEM: 16 words x 8 columns
+constexpr uint32_t kACol0 = 256;                 // two operand stages: columns 256..511
+constexpr uint32_t kSlots = 3, kSlotCols = 80;   // three accumulators: columns 0..239
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kMaxSegSteps = 256;
-constexpr uint32_t kBBytes = 192 * 1024;         // B digits of a segment (+ 256 bytes of slack)
-constexpr uint32_t kTraceLen = 96;               // stages / flushes of CTA 0 whose timestamps GSB200_LOCAL_TRACE records
-constexpr uint32_t kMaxRunBases = 1536;          // doubles of per-run bases kept in shared memory (runs x sets)
+constexpr uint32_t kUnitHead = 256;              // in front of a unit's digits: n_segments, its segment records (zero-padded)
+constexpr uint32_t kStageSlack = 256;             // an odd number of sets: the mma's 16-column granule reads 256 bytes past the last step
+constexpr uint32_t kMaxBStages = 4;
+constexpr uint32_t kOutRow = 5;                  // staging: 4 blocks per strand row + 1 double of padding
+constexpr uint32_t kSmemBudget = 227 * 1024 - 2048;
+// segment record (consecutive words of one block within a unit): first word within the half line (4 bits) | steps << 4 |
+// 512 the block starts here | 1024 the block ends here
+constexpr uint32_t kSegFirst = 512u, kSegLast = 1024u;
+static_assert(kLocalTc5MaxSets * 8 <= kSlotCols, "an accumulator holds 8 columns per effect set");
 
-__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+struct Tc5Range {          // the whole blocks [blk_lo, blk_hi) = runs [run_lo, run_hi) of non-empty blocks
+    uint32_t unit_lo, n_units;
+    uint32_t run_lo, run_hi;
+    uint32_t line_lo, n_lines;  // 128-byte lines of the strand rows its steps read
+    uint32_t blk_lo, blk_hi;
+};
+struct Tc5Unit {
+    uint32_t b_off16, b_bytes;  // the unit in the B stream (offset in 16-byte units): head + n_steps x 256 x sets
+    uint32_t line_adv_half;     // lines to advance before the unit << 1 | which half of the line
+    uint32_t pad;
+};
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    return leader != 0;
+}
+// the kind::i8 MMA of tc5_common.cuh under a predicate of its own
+__device__ __forceinline__ void umma_i8_ts_if(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(issue) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const uint32_t* gmem_src) {
+    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" :: "r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
 
 // four marker words of this thread's strand row -> 4 K-steps of operand bytes in its TMEM lane
@@ -81,37 +142,54 @@ __device__ __forceinline__ void store_words(uint32_t taddr, const uint4 w) {
 struct LocalTc5Params {
     const uint4* b[kLocalTc5MaxSets];      // per set: [n_steps][16] uint4 = 256 bytes per step, UMMA K-major layout
     const double* base[kLocalTc5MaxSets];  // [n_blocks]
-    double* out[kLocalTc5MaxSets];         // [(2n) x n_blocks], zeroed
+    double* out[kLocalTc5MaxSets];         // [(2n) x n_blocks]
     double scale[kLocalTc5MaxSets];
 };
 
-// steps[s] = (word, block | first_step_of_block << 31)
+// The B stream: per unit a 256-byte head (n_steps, the step records) then [step][set][256 bytes of digits].
+// One thread block per unit.
+__global__ void local_tc5_pack_kernel(uint4* __restrict__ bstream, const Tc5Unit* __restrict__ units, uint32_t n_sets,
+                                      const uint32_t* __restrict__ unit_step /* [n_units + 1] first step of every unit */,
+                                      const uint32_t* __restrict__ heads /* [64 n_units] */, const LocalTc5Params P) {
+    const Tc5Unit u = units[blockIdx.x];
+    uint4* dst = bstream + u.b_off16;
+    const uint32_t s0 = unit_step[blockIdx.x], total = u.b_bytes / 16;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        uint4 v;
+        if (i < kUnitHead / 16) {
+            const uint32_t* hp = heads + blockIdx.x * (kUnitHead / 4) + i * 4;
+            v = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        } else {
+            const uint32_t r0 = i - kUnitHead / 16, pos = r0 / (n_sets * 16), r = r0 % (n_sets * 16), q = r >> 4, k = r & 15;
+            v = __ldg(P.b[q] + (size_t) (s0 + pos) * 16 + k);
+        }
+        dst[i] = v;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
         const uint32_t* __restrict__ rows, uint32_t n, uint32_t n_blocks,
-        const uint2* __restrict__ steps, uint32_t n_steps, const uint32_t* __restrict__ seg_off /* [n_segments + 1] first step of every segment */,
-        uint32_t n_tiles, uint32_t n_items, uint32_t items_per_cta, uint32_t n_sets, const LocalTc5Params P, int* __restrict__ flag,
-        uint32_t dbg /* GSB200_LOCAL_DEBUG bits, measurements only: 1 no operand stores, 2 no mma, 4 no epilogue work, 8 no row loads */,
-        long long* __restrict__ trace /* debugging: clock64 stamps of CTA 0's first kTraceLen stages per role, or null */) {
-    extern __shared__ __align__(128) uint4 s_b[];                    // seg_steps x n_sets x 256 bytes
-    __shared__ __align__(8) uint64_t s_full[kAStages], s_free[kAStages], s_dready[2], s_dfree[2];
-    __shared__ uint2 s_steps[kMaxSegSteps];
-    // the segment's runs of steps that belong to one block = its accumulators, in order: (block | starts-here << 31, first step)
-    __shared__ uint2 s_runs[kMaxSegSteps];
-    __shared__ double s_base[kMaxRunBases];          // [run][set]: the block's base where the block starts in this segment, else 0
-    // per step, for the issuer: word & 7 | 8 if the step opens an operand stage (octet) | 16 if it opens an accumulator
-    // (block) | octets to advance << 8 — precomputed so that the single issuing thread does next to nothing per MMA
-    __shared__ uint32_t s_rec[kMaxSegSteps + 1];
-    __shared__ uint32_t s_n_runs;
+        const uint8_t* __restrict__ bstream, const Tc5Range* __restrict__ ranges, uint32_t n_ranges, const Tc5Unit* __restrict__ units,
+        const uint32_t* __restrict__ runs /* block of every run */, uint32_t n_items, uint32_t n_sets, uint32_t n_bstages,
+        const LocalTc5Params P, int* __restrict__ flag,
+        uint32_t dbg /* GSB200_LOCAL_DEBUG bits, measurements only: 1 no operand stores, 2 no mma, 4 no epilogue work, 8 no row loads, 16 no B digits (heads only) */,
+        long long* __restrict__ prof /* GSB200_LOCAL_PROF: CTA 0's cycles per role spent in each kind of wait, or null */) {
+    extern __shared__ __align__(128) uint8_t s_dyn[];               // A lines | output staging | B stages
+    __shared__ __align__(8) uint64_t s_afull[kALines], s_afree[kALines], s_tfull[2], s_udone[kMaxBStages];
+    __shared__ __align__(8) uint64_t s_bfull[kMaxBStages], s_dready[kSlots], s_dfree[kSlots];
+    __shared__ const uint32_t* s_rowptr[128];
     __shared__ uint32_t s_tmem;
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (uint32_t i = 0; i < kAStages; ++i) { mbar_init(&s_full[i], kExpanders / 32); mbar_init(&s_free[i], 1); }
-        for (uint32_t i = 0; i < 2; ++i) { mbar_init(&s_dready[i], 1); mbar_init(&s_dfree[i], kEpilogue / 32); }
+        for (uint32_t i = 0; i < kALines; ++i) { mbar_init(&s_afull[i], 32); mbar_init(&s_afree[i], 4); }
+        for (uint32_t i = 0; i < 2; ++i) mbar_init(&s_tfull[i], 4);
+        for (uint32_t i = 0; i < kMaxBStages; ++i) { mbar_init(&s_bfull[i], 1); mbar_init(&s_udone[i], 1); }
+        for (uint32_t i = 0; i < kSlots; ++i) { mbar_init(&s_dready[i], 1); mbar_init(&s_dfree[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == kWarpIssuer) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -119,229 +197,291 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t bar_full = smem_u32(s_full), bar_free = smem_u32(s_free);
-    const uint32_t bar_dready = smem_u32(s_dready), bar_dfree = smem_u32(s_dfree);
-    const uint32_t b_base = smem_u32(s_b);
+    const uint32_t bar_afull = smem_u32(s_afull), bar_afree = smem_u32(s_afree), bar_tfull = smem_u32(s_tfull), bar_udone = smem_u32(s_udone);
+    const uint32_t bar_bfull = smem_u32(s_bfull), bar_dready = smem_u32(s_dready), bar_dfree = smem_u32(s_dfree);
+    const uint32_t step_bytes = 256 * n_sets, stage_bytes = kUnitHead + kUnitSteps * step_bytes + kStageSlack;
+    const uint32_t a_smem = smem_u32(s_dyn);
+    const uint32_t out_bytes_warp = n_sets * 32 * kOutRow * 8;
+    double* const out_stage0 = reinterpret_cast<double*>(s_dyn + kALines * kALineBytes);
+    const uint32_t b_smem = a_smem + kALines * kALineBytes + 4 * out_bytes_warp;
     // M = 128 wants N % 16 == 0: an odd number of sets contracts 8 more columns against the bytes that follow
-    // (the next step's first set, or the slack behind the last step) into accumulator columns nobody reads
-    const uint32_t n_cols = (8 * n_sets + 15) & ~15u, step_bytes = 256 * n_sets;
+    // (the next step's first set, or whatever the stage held before) into accumulator columns nobody reads
+    const uint32_t n_cols = (8 * n_sets + 15) & ~15u;
     const uint32_t idesc = idesc_i8(n_cols);
+    // the unit barriers form a ring as long as the B ring (>= 2): unit U is committed to barrier U % n_bstages, and
+    // both who wait for it (the expanders for unit U + 2's operand stage, the B loader for unit U + n_bstages' stage)
+    // do so before the issuer can get a full ring further
+    const uint32_t n_ring = n_bstages;
     bool ok = true;
-
-    const uint32_t item_lo = min(blockIdx.x * items_per_cta, n_items), item_hi = min(item_lo + items_per_cta, n_items);
-    // running counts over the CTA's whole life: every role walks the same sequence, so each derives the
-    // barrier phases by itself
-    uint32_t q_oct = 0;          // operand stages (octets of 8 words) produced / consumed so far
-    uint32_t q_flush = 0;        // accumulators finished so far
-
-    for (uint32_t item = item_lo; item < item_hi;) {
-        const uint32_t seg = item / n_tiles, run_end = min(item_hi, (seg + 1) * n_tiles);
-        const uint32_t s_lo = seg_off[seg], s_hi = seg_off[seg + 1], n_seg = s_hi - s_lo;
-        const uint32_t tile_lo = item - seg * n_tiles, n_run = run_end - item;
-
-        // ---- this segment's step list and B digits -> shared memory (the previous segment's mma have all
-        //      completed: the epilogue warps waited for its last accumulator before coming here)
-        tc_fence_before();
-        __syncthreads();
-        for (uint32_t i = tid; i < n_seg; i += kThreads) s_steps[i] = steps[s_lo + i];
-        for (uint32_t i = tid; i < n_seg * n_sets * 16; i += kThreads) {
-            const uint32_t st = i / (n_sets * 16), r = i % (n_sets * 16), q = r >> 4, k = r & 15;
-            s_b[i] = __ldg(P.b[q] + (size_t) (s_lo + st) * 16 + k);
+    // prof[role * 4 + k]: k = 0 the role's whole loop, 1..3 its waits (see local_tc5_launch)
+    const bool profiling = prof != nullptr && blockIdx.x == 0 && lane == 0;
+    long long p_wait[3] = { 0, 0, 0 };
+    const long long p_t0 = clock64();
+    // whole-warp wait: ONE lane polls the barrier, the others park at the warp barrier.  With every lane of nine
+    // waiting warps polling, the shared-memory pipe was so busy with phase checks that the issuer's record
+    // loads took ~200 cycles each (profiles/r2_local_tc5.txt).
+    auto wait_on = [&](uint32_t bar, uint32_t parity, int kind) {
+        if (lane == 0) {
+            if (profiling) { const long long t = clock64(); mbar_wait(bar, parity, ok); p_wait[kind] += clock64() - t; }
+            else mbar_wait(bar, parity, ok);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core's proxy
-        __syncthreads();
-        for (uint32_t st = tid; st <= n_seg; st += kThreads) {
-            uint32_t rec = 24u;                                  // the sentinel behind the last step ends the issuer's fast loop
-            if (st < n_seg) {
-                const uint32_t oct = s_steps[st].x >> 3, blk = s_steps[st].y & 0x7fffffffu;
-                const uint32_t adv = st == 0 ? 1u : oct - (s_steps[st - 1].x >> 3);
-                rec = (s_steps[st].x & 7u) | (adv ? 8u : 0u) | ((st == 0 || blk != (s_steps[st - 1].y & 0x7fffffffu)) ? 16u : 0u) | (adv << 8);
-            }
-            s_rec[st] = rec;
-        }
-        if (warp == 8) {
-            // the runs, by one warp: a step opens a run when its block differs from the previous step's
-            uint32_t n_runs = 0;
-            for (uint32_t s0 = 0; s0 < n_seg; s0 += 32) {
-                const uint32_t st = s0 + lane;
-                const bool opens = st < n_seg && (st == 0 || (s_steps[st].y & 0x7fffffffu) != (s_steps[st - 1].y & 0x7fffffffu));
-                const uint32_t ballot = __ballot_sync(0xffffffffu, opens);
-                if (opens) s_runs[n_runs + __popc(ballot & ((1u << lane) - 1u))] = make_uint2(s_steps[st].y, st);
-                n_runs += __popc(ballot);
-            }
-            if (lane == 0) s_n_runs = n_runs;
-        }
-        __syncthreads();
-        const uint32_t n_runs = s_n_runs;
-        // does the segment's first run start its block, does its last run end it?  (every other run is a whole block)
-        const bool last_run_ends = s_hi == n_steps || (steps[s_hi].y & 0x7fffffffu) != (s_steps[n_seg - 1].y & 0x7fffffffu);
-        const bool bases_in_smem = n_runs * n_sets <= kMaxRunBases;
-        if (bases_in_smem)
-            for (uint32_t i = tid; i < n_runs * n_sets; i += kThreads) {
-                const uint2 run = s_runs[i / n_sets];
-                s_base[i] = (run.x >> 31) ? P.base[i % n_sets][run.x & 0x7fffffffu] : 0.0;
-            }
-        __syncthreads();
-        tc_fence_after();
-        const uint32_t o_first = s_steps[0].x >> 3, o_last = s_steps[n_seg - 1].x >> 3, n_oct = o_last - o_first + 1;
+        __syncwarp();
+    };
+    auto prof_out = [&](uint32_t role) {
+        if (profiling) { prof[role * 4] = clock64() - p_t0; prof[role * 4 + 1] = p_wait[0]; prof[role * 4 + 2] = p_wait[1]; prof[role * 4 + 3] = p_wait[2]; }
+    };
 
-        if (warp < 4) {
-            // ---------------- expanders: thread tid = strand row tid of the tile
-            auto row_ptr = [&](uint32_t tile) -> const uint4* {
-                const uint32_t ind = min(min(tile, n_tiles - 1) * 64 + (tid >> 1), n - 1);
-                return reinterpret_cast<const uint4*>(store + (uint64_t) rows[ind] * row_words + (tid & 1) * plane_words) + 2 * o_first;
+    auto range_of = [&](uint32_t item) {
+        const uint4* p = reinterpret_cast<const uint4*>(ranges + item % n_ranges);
+        const uint4 a = __ldg(p), b = __ldg(p + 1);
+        Tc5Range r;
+        r.unit_lo = a.x; r.n_units = a.y; r.run_lo = a.z; r.run_hi = a.w; r.line_lo = b.x; r.n_lines = b.y; r.blk_lo = b.z; r.blk_hi = b.w;
+        return r;
+    };
+
+    if (warp < 4) {
+        // ---------------- expanders: thread tid = strand row tid of the tile = TMEM lane tid
+        uint32_t q_line = 0, q_unit = 0, ring_i = 0, ring_par = 0;       // ring_i = q_unit % n_ring, ring_par = (q_unit / n_ring) & 1
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const Tc5Range rg = range_of(item);
+            uint32_t lines_taken = 0, as = 0;
+            auto next_line = [&]() {
+                if (lines_taken && lane == 0) mbar_arrive(bar_afree + 8 * as);       // every lane's words of the old line were consumed by its stores
+                as = q_line % kALines;
+                wait_on(bar_afull + 8 * as, (q_line / kALines) & 1, 0);
+                ++q_line; ++lines_taken;
             };
-            const uint32_t total = n_run * n_oct;
-            constexpr uint32_t kDepth = 4;
-            uint4 buf[kDepth][2];
-            uint32_t l_tile = tile_lo, l_oct = 0;
-            const uint4* lptr = row_ptr(l_tile);
-            auto request = [&](uint4 (&b)[2]) {
-                if (!(dbg & 8u)) { b[0] = ldg_stream(lptr + 2 * l_oct); b[1] = ldg_stream(lptr + 2 * l_oct + 1); }
-                else b[0] = b[1] = make_uint4(l_oct, tid, 3u, 4u);
-                if (++l_oct == n_oct) { l_oct = 0; ++l_tile; lptr = row_ptr(l_tile); }
-            };
+#pragma unroll 1
+            for (uint32_t u = 0; u < rg.n_units; ++u, ++q_unit) {
+                const uint32_t desc = __ldg(&units[rg.unit_lo + u].line_adv_half);
+#pragma unroll 1
+                for (uint32_t k = desc >> 1; k; --k) next_line();
+                const uint32_t src = a_smem + as * kALineBytes + tid * kARowBytes + (desc & 1u) * 64;
+                uint4 w[4];
 #pragma unroll
-            for (uint32_t k = 0; k < kDepth; ++k) if (k < total) request(buf[k]);
-            auto produce = [&](const uint4 (&b)[2]) {
-                const uint32_t stage = q_oct % kAStages, use = q_oct / kAStages;
-                const bool tr = trace && blockIdx.x == 0 && tid == 0 && q_oct < kTraceLen;
-                if (tr) trace[0 * kTraceLen + q_oct] = clock64();
-                if (use > 0) {                                 // the mma that read this stage kAStages octets ago
-                    mbar_wait(bar_free + 8 * stage, (use - 1) & 1, ok);
+                for (int k = 0; k < 4; ++k) w[k] = lds128(src + 16 * k);
+                if (q_unit >= 2) {
+                    // the operand stage was read by unit q_unit - 2: its barrier is two behind in the ring
+                    const uint32_t back = ring_i >= 2 ? ring_i - 2 : ring_i + n_ring - 2;
+                    const uint32_t par = ring_i >= 2 ? ring_par : ring_par ^ 1;
+                    wait_on(bar_udone + 8 * back, par, 1);
                     tc_fence_after();
                 }
-                const uint32_t taddr = tmem + ((warp * 32) << 16) + kACol0 + kStageCols * stage;
-                if (tr) trace[1 * kTraceLen + q_oct] = clock64();
-                if (!(dbg & 1u)) store_words(taddr, b[0]);
-                if (tr) trace[2 * kTraceLen + q_oct] = clock64();
-                if (!(dbg & 1u)) store_words(taddr + 32, b[1]);
+                const uint32_t taddr = tmem + ((warp * 32) << 16) + kACol0 + kStageCols * (q_unit & 1);
+                if (!(dbg & 1u)) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) store_words(taddr + 32 * k, w[k]);
+                }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                if (tr) trace[3 * kTraceLen + q_oct] = clock64();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-                ++q_oct;
+                if (lane == 0) mbar_arrive(bar_tfull + 8 * (q_unit & 1));
+                if (++ring_i == n_ring) { ring_i = 0; ring_par ^= 1; }
+            }
+#pragma unroll 1
+            while (lines_taken < rg.n_lines) next_line();            // lines behind the item's last unit
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_afree + 8 * as);
+        }
+        if (warp == 0) prof_out(0);
+    } else if (warp < 8) {
+        // ---------------- epilogue: thread (tid - 128) = TMEM lane = strand row of the tile
+        const uint32_t wq = warp - 4;
+        double* const stage = out_stage0 + (size_t) wq * (out_bytes_warp / 8);
+        uint32_t slot = 0, slot_par = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const Tc5Range rg = range_of(item);
+            const uint32_t tile = item / n_ranges;
+            // four blocks [g0, g0 + 4) staged for the warp's 32 rows -> 32 contiguous bytes per row and set
+            auto flush = [&](uint32_t g_hi) {
+                const uint32_t g0 = (g_hi - 1) & ~3u, g_lo = max(g0, rg.blk_lo);
+                __syncwarp();
+                const uint32_t sl = lane & 3, b = g0 + sl;
+                if (b >= g_lo && b < g_hi) {
+#pragma unroll
+                    for (uint32_t i = 0; i < 4; ++i) {
+                        const uint32_t rl = 8 * i + (lane >> 2), strand_row = wq * 32 + rl;
+                        if (tile * 64 + (strand_row >> 1) < n) {
+                            const size_t o = ((size_t) tile * 128 + strand_row) * n_blocks + b;
+                            for (uint32_t q = 0; q < n_sets; ++q) P.out[q][o] = stage[(q * 32 + rl) * kOutRow + sl];
+                        }
+                    }
+                }
+                __syncwarp();
             };
-            for (uint32_t c0 = 0; c0 < total; c0 += kDepth) {
+            uint32_t blk_next = rg.blk_lo;
+            auto empty_until = [&](uint32_t blk) {                // blocks without markers sum to 0
+                while (blk_next < blk) {
+                    for (uint32_t q = 0; q < n_sets; ++q) stage[(q * 32 + lane) * kOutRow + (blk_next & 3)] = 0.0;
+                    ++blk_next;
+                    if ((blk_next & 3) == 0 || blk_next == rg.blk_hi) flush(blk_next);
+                }
+            };
+#pragma unroll 1
+            for (uint32_t run = rg.run_lo; run < rg.run_hi; ++run) {
+                const uint32_t blk = __ldg(runs + run);
+                empty_until(blk);
+                wait_on(bar_dready + 8 * slot, slot_par, 0);
+                tc_fence_after();
+                const uint32_t taddr = tmem + ((wq * 32) << 16) + kSlotCols * slot;
+#pragma unroll 1
+                for (uint32_t q0 = 0; q0 < ((dbg & 4u) ? 0u : n_sets); q0 += 4) {
+                    // four sets at a time: the loads first, then four independent recombinations
+                    uint32_t d[4][8];
 #pragma unroll
-                for (uint32_t k = 0; k < kDepth; ++k) {
-                    if (c0 + k < total) {
-                        produce(buf[k]);
-                        if (c0 + k + kDepth < total) request(buf[k]);
+                    for (int j = 0; j < 4; ++j)
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(d[j][0]), "=r"(d[j][1]), "=r"(d[j][2]), "=r"(d[j][3]), "=r"(d[j][4]), "=r"(d[j][5]), "=r"(d[j][6]), "=r"(d[j][7])
+                                     : "r"(taddr + 8 * min(q0 + j, n_sets - 1)) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (q0 + 4 >= n_sets) {                            // the accumulator can take another block
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_dfree + 8 * slot);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t q = q0 + j;
+                        // sum_k d_k 256^k: the two halves are exact in int64 (|d_k| < 2^31), one fp64 fma joins them
+                        const long long lo = (long long) (int) d[j][0] + ((long long) (int) d[j][1] << 8) + ((long long) (int) d[j][2] << 16) + ((long long) (int) d[j][3] << 24);
+                        const long long hi = (long long) (int) d[j][4] + ((long long) (int) d[j][5] << 8) + ((long long) (int) d[j][6] << 16) + ((long long) (int) d[j][7] << 24);
+                        if (q < n_sets)
+                            stage[(q * 32 + lane) * kOutRow + (blk & 3)] = fma((double) hi, 4294967296.0, (double) lo) * P.scale[q] + __ldg(P.base[q] + blk);
                     }
                 }
+                if (dbg & 4u) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_dfree + 8 * slot); }
+                if (++slot == kSlots) { slot = 0; slot_par ^= 1; }
+                blk_next = blk + 1;
+                if ((blk_next & 3) == 0 || blk_next == rg.blk_hi) flush(blk_next);
             }
-        } else if (warp < 8) {
-            // ---------------- epilogue: thread (tid - 128) = TMEM lane = strand row of the tile
-            const uint32_t t = tid - kExpanders, wq = warp - 4;
-            for (uint32_t it = 0; it < n_run; ++it) {
-                const uint32_t tile = tile_lo + it;
-                const uint64_t out_row = (uint64_t) tile * 128 + t;          // = 2 * individual + strand
-                const bool live = (tile * 64 + (t >> 1)) < n;
-                for (uint32_t run = 0; run < n_runs; ++run) {
-                    const uint32_t blk = s_runs[run].x & 0x7fffffffu, starts = s_runs[run].x >> 31;
-                    const bool whole = starts && (run + 1 < n_runs || last_run_ends);      // complete sums: plain stores, no atomics
-                    const uint32_t dbuf = q_flush & 1;
-                    const bool tr = trace && blockIdx.x == 0 && t == 0 && q_flush < kTraceLen;
-                    if (tr) trace[6 * kTraceLen + q_flush] = clock64();
-                    mbar_wait(bar_dready + 8 * dbuf, (q_flush >> 1) & 1, ok);
-                    tc_fence_after();
-                    if (tr) trace[7 * kTraceLen + q_flush] = clock64();
-                    const uint32_t taddr = tmem + ((wq * 32) << 16) + (dbuf ? kDCol1 : 0u);
-                    double* out = P.out[0] + out_row * n_blocks + blk;
-                    for (uint32_t q0 = 0; q0 < ((dbg & 4u) ? 0u : n_sets); q0 += 4) {
-                        // four sets at a time: the loads first, then four independent recombinations
-                        uint32_t d[4][8];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                         : "=r"(d[j][0]), "=r"(d[j][1]), "=r"(d[j][2]), "=r"(d[j][3]), "=r"(d[j][4]), "=r"(d[j][5]), "=r"(d[j][6]), "=r"(d[j][7])
-                                         : "r"(taddr + 8 * min(q0 + j, n_sets - 1)) : "memory");
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t q = q0 + j;
-                            // sum_k d_k 256^k: the two halves are exact in int64 (|d_k| < 2^31), one fp64 fma joins them
-                            const long long lo = (long long) (int) d[j][0] + ((long long) (int) d[j][1] << 8) + ((long long) (int) d[j][2] << 16) + ((long long) (int) d[j][3] << 24);
-                            const long long hi = (long long) (int) d[j][4] + ((long long) (int) d[j][5] << 8) + ((long long) (int) d[j][6] << 16) + ((long long) (int) d[j][7] << 24);
-                            if (q < n_sets) {
-                                double v = fma((double) hi, 4294967296.0, (double) lo) * P.scale[q];
-                                if (starts) v += bases_in_smem ? s_base[run * n_sets + q] : P.base[q][blk];
-                                if (live) { if (whole) P.out[q][out - P.out[0]] = v; else atomicAdd(P.out[q] + (out - P.out[0]), v); }
-                            }
+            empty_until(rg.blk_hi);
+        }
+        if (warp == 4) prof_out(1);
+    } else if (warp == kWarpIssuer) {
+        // ---------------- issuer: the whole warp walks the records CONVERGED and one elected lane issues.  From a
+        // lone thread inside `if (lane == 0)` every tcgen05.mma / commit is wrapped in a waterfall loop (ELECT,
+        // R2UR.BROADCAST, BRA.U.ANY): 47 cycles per MMA and ~300 per commit whatever N; converged + elect.sync the
+        // MMA issues in 17 cycles and N = 80 runs at its 40-cycle floor (profiles/r2_umma_i8_probe2.txt).
+        uint32_t q_unit = 0, ring_i = 0, b_stage = 0, b_par = 0;
+        uint32_t q_blk = 0, slot = 0, slot_par = 0;       // slot = q_blk % kSlots, slot_par = (q_blk / kSlots) & 1
+        uint32_t d_addr = tmem;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const Tc5Range rg = range_of(item);
+#pragma unroll 1
+            for (uint32_t u = 0; u < rg.n_units; ++u, ++q_unit) {
+                wait_on(bar_bfull + 8 * b_stage, b_par, 0);
+                const uint32_t b_addr = b_smem + b_stage * stage_bytes;
+                const uint32_t n_seg = lds32(b_addr);
+                uint64_t desc = b_descriptor(b_addr + kUnitHead);
+                uint32_t seg = lds32(b_addr + 4);
+                wait_on(bar_tfull + 8 * (q_unit & 1), (q_unit >> 1) & 1, 1);
+                tc_fence_after();
+                const uint32_t a_base = tmem + kACol0 + kStageCols * (q_unit & 1);
+                const long long tl = clock64();
+                // a segment = consecutive words of one block: its MMAs are issued four at a time from one elected lane
+                // with nothing but uniform adds between them — a lone warp pays ~15 cycles per branch, so per-STEP
+                // control flow (the first version of this loop) cost 200 cycles per step
+#pragma unroll 1
+                for (uint32_t sg = 0; sg < n_seg; ++sg) {
+                    const uint32_t seg_next = lds32(b_addr + 8 + 4 * sg);
+                    const uint32_t cnt = (seg >> 4) & 31u;
+                    uint32_t acc = 1;
+                    if (seg & kSegFirst) {
+                        if (q_blk >= kSlots) {                       // the epilogue has read this accumulator's previous sums
+                            wait_on(bar_dfree + 8 * slot, slot_par ^ 1, 2);
+                            tc_fence_after();
                         }
+                        d_addr = tmem + kSlotCols * slot;
+                        acc = 0;
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_dfree + 8 * dbuf);
-                    if (tr) trace[8 * kTraceLen + q_flush] = clock64();
-                    ++q_flush;
+                    uint32_t a_addr = a_base + 8 * (seg & 15u);
+#pragma unroll 1
+                    for (uint32_t c = 0; c < cnt; c += 4) {
+                        if (!(dbg & 2u) && elect_one()) {
+                            umma_i8_ts_if(d_addr, a_addr, desc, idesc, acc, 1u);
+                            umma_i8_ts_if(d_addr, a_addr + 8, desc + (step_bytes >> 4), idesc, 1u, c + 1 < cnt);
+                            umma_i8_ts_if(d_addr, a_addr + 16, desc + 2 * (step_bytes >> 4), idesc, 1u, c + 2 < cnt);
+                            umma_i8_ts_if(d_addr, a_addr + 24, desc + 3 * (step_bytes >> 4), idesc, 1u, c + 3 < cnt);
+                        }
+                        __syncwarp();
+                        acc = 1;
+                        a_addr += 32;
+                        desc += 4 * (step_bytes >> 4);          // the start-address field counts 16-byte units
+                    }
+                    desc -= (uint64_t) ((0u - cnt) & 3u) * (step_bytes >> 4);      // the last trip's unused steps
+                    if (seg & kSegLast) {
+                        if (elect_one()) tc_commit(bar_dready + 8 * slot);
+                        __syncwarp();
+                        ++q_blk;
+                        if (++slot == kSlots) { slot = 0; slot_par ^= 1; }
+                    }
+                    seg = seg_next;
                 }
+                if (profiling && (dbg & 32u)) p_wait[1] += clock64() - tl;
+                { const long long tq = clock64();
+                if (elect_one()) tc_commit(bar_udone + 8 * ring_i);
+                __syncwarp();
+                if (profiling && (dbg & 32u)) p_wait[2] += clock64() - tq; }
+                if (++ring_i == n_ring) ring_i = 0;
+                if (++b_stage == n_bstages) { b_stage = 0; b_par ^= 1; }
             }
-        } else {
-            // ---------------- issuer: one thread.  A lone thread retires an instruction every ~4 cycles, so the
-            // step loop is kept to a dozen instructions (record prefetch, operand column, descriptor bump, mma) —
-            // a first version with the stage / accumulator bookkeeping inline spent ~300 cycles per step, three
-            // times what the mma itself takes (profiles/r2_local_tc5.txt).  Octet and block changes, flagged in
-            // the precomputed records, leave the fast loop.
-            if (lane == 0) {
-                const uint64_t desc0 = b_descriptor(b_base);
-                const uint32_t desc_step = step_bytes >> 4;          // the start-address field counts 16-byte units; all of shared memory fits its 14 bits
-                for (uint32_t it = 0; it < n_run; ++it) {
-                    uint32_t stage = 0, dbuf = 0, a_base = 0, d_addr = 0, s = 0;
-                    bool have_oct = false, have_blk = false;
-                    uint64_t desc = desc0;
-                    uint32_t rec = s_rec[0];
-                    while (s < n_seg) {
-                        uint32_t acc = 1;
-                        if (rec & 8u) {
-                            // (a gap between two blocks may skip whole octets; the expanders deliver every octet of the segment)
-                            for (uint32_t adv = rec >> 8; adv; --adv) {
-                                if (have_oct) tc_commit(bar_free + 8 * stage);
-                                have_oct = true;
-                                stage = q_oct % kAStages;
-                                if (trace && blockIdx.x == 0 && q_oct < kTraceLen) trace[4 * kTraceLen + q_oct] = clock64();
-                                mbar_wait(bar_full + 8 * stage, (q_oct / kAStages) & 1, ok);
-                                tc_fence_after();
-                                if (trace && blockIdx.x == 0 && q_oct < kTraceLen) trace[5 * kTraceLen + q_oct] = clock64();
-                                ++q_oct;
-                            }
-                            a_base = tmem + kACol0 + kStageCols * stage;
-                        }
-                        if (rec & 16u) {
-                            if (have_blk) { tc_commit(bar_dready + 8 * dbuf); ++q_flush; }
-                            have_blk = true;
-                            dbuf = q_flush & 1;
-                            if (q_flush >= 2) {                      // the epilogue has read this accumulator's previous sums
-                                mbar_wait(bar_dfree + 8 * dbuf, ((q_flush >> 1) - 1) & 1, ok);
-                                tc_fence_after();
-                            }
-                            d_addr = tmem + (dbuf ? kDCol1 : 0u);
-                            acc = 0;
-                        }
-                        // the steps up to the next octet or block change (the record behind the last step has both flags set)
-                        do {
-                            if (!(dbg & 2u)) umma_i8_ts(d_addr, a_base + 8 * (rec & 7u), desc, idesc, acc);
-                            acc = 1;
-                            desc += desc_step;
-                            rec = s_rec[++s];
-                        } while (!(rec & 24u));
-                    }
-                    tc_commit(bar_free + 8 * stage);
-                    tc_commit(bar_dready + 8 * dbuf);
-                    ++q_flush;
-                }
+        }
+        prof_out(2);
+    } else if (warp == kWarpALoader) {
+        // ---------------- A loader: lanes 8k .. 8k + 7 copy one 128-byte line of one strand row
+        uint32_t q_line = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const Tc5Range rg = range_of(item);
+            const uint32_t tile = item / n_ranges;
+            __syncwarp();
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                const uint32_t r = 4 * lane + k, ind = min(tile * 64 + (r >> 1), n - 1);
+                s_rowptr[r] = store + (uint64_t) __ldg(rows + ind) * row_words + (r & 1) * plane_words;
             }
             __syncwarp();
+#pragma unroll 1
+            for (uint32_t line = 0; line < rg.n_lines; ++line, ++q_line) {
+                const uint32_t as = q_line % kALines;
+                if (q_line >= kALines) wait_on(bar_afree + 8 * as, ((q_line / kALines) - 1) & 1, 0);
+                const uint32_t word0 = (rg.line_lo + line) * 32 + (lane & 7) * 4;
+                const uint32_t dst0 = a_smem + as * kALineBytes + (lane >> 3) * kARowBytes + (lane & 7) * 16;
+#pragma unroll 8
+                for (uint32_t j = 0; j < ((dbg & 8u) ? 0u : 32u); ++j) cp_async16_s(dst0 + j * 4 * kARowBytes, s_rowptr[4 * j + (lane >> 3)] + word0);
+                cp_async_arrive_noinc(bar_afull + 8 * as);
+            }
         }
-        item = run_end;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        prof_out(3);
+    } else {
+        // ---------------- B loader: one thread, one bulk copy per unit
+        if (lane == 0) {
+            uint32_t b_stage = 0, b_par = 0, filled = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const Tc5Range rg = range_of(item);
+#pragma unroll 1
+                for (uint32_t u = 0; u < rg.n_units; ++u) {
+                    const uint2 ub = __ldg(reinterpret_cast<const uint2*>(units + rg.unit_lo + u));
+                    // stage b_stage was last read by the unit n_bstages back, committed to ring barrier b_stage
+                    if (filled >= n_bstages) {
+                        const long long t = profiling ? clock64() : 0;
+                        mbar_wait(bar_udone + 8 * b_stage, b_par ^ 1, ok);
+                        if (profiling) p_wait[0] += clock64() - t;
+                    }
+                    bulk_g2s(b_smem + b_stage * stage_bytes, bstream + (size_t) ub.x * 16, (dbg & 16u) ? kUnitHead : ub.y, bar_bfull + 8 * b_stage);
+                    ++filled;
+                    if (++b_stage == n_bstages) { b_stage = 0; b_par ^= 1; }
+                }
+            }
+            prof_out(4);
+        }
+        __syncwarp();
     }
     if (!ok) atomicExch(flag, 2);
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
+    if (warp == kWarpIssuer) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
 }
 
 }  // namespace
@@ -370,79 +510,138 @@ void build_local_tc5_fragments(const std::vector<double>& delta /* [M] */, const
     }
 }
 
-// One pass over the genotypes for n_sets (<= kLocalTc5MaxSets) effect sets.  d_steps: the schedule with the
-// first-step-of-block flag in bit 31 of .y; d_b / d_base / d_out / scale per set.  Asynchronous.
-// Marker segments for a pass of n_sets effect sets: consecutive step ranges of at most `cap` steps (their B
-// digits must fit shared memory) that end where a 128-byte line of the strand rows ends (32 marker words),
-// so that every line of the genotypes is fetched from DRAM by one segment only; when not even 32 words'
-// steps fit (blocks of a few markers each) a segment is cut at `cap` steps.  A block that a segment boundary
-// cuts is summed in two parts (fp64 atomics on the output); whole blocks are stored plainly.  Cutting at block
-// boundaries instead was measured and is slower: segments then start inside a line, which two segments fetch.
-void local_tc5_segments(const std::vector<uint2>& steps, uint32_t n_sets, std::vector<uint32_t>& seg_off) {
-    const uint32_t cap = std::min<uint32_t>(kMaxSegSteps, kBBytes / (256 * n_sets));
-    const uint32_t n_steps = (uint32_t) steps.size();
-    seg_off.assign(1, 0u);
-    uint32_t pos = 0;
-    while (pos < n_steps) {
-        uint32_t best = 0, end = pos;
-        for (uint32_t end_word = (steps[pos].x / 32 + 1) * 32;; end_word += 32) {
-            while (end < n_steps && steps[end].x < end_word) ++end;
-            if (end - pos > cap) break;
-            best = end;
-            if (end == n_steps) break;
-        }
-        if (best == 0) best = std::min(n_steps, pos + cap);
-        seg_off.push_back(best);
-        pos = best;
-    }
-}
-
-int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t n_blocks, const uint2* d_steps,
-                     const std::vector<uint32_t>& seg_off, const uint32_t* d_seg_off,
+// One pass over the genotypes for n_sets (<= kLocalTc5MaxSets) effect sets: d_b / d_base / d_out / scale per
+// set; `steps` (marker word, block) in block order and `block_first` (first step of every non-empty block,
+// then the number of steps) are the schedule of evaluate.cu.  Every element of the outputs is written.
+// Asynchronous.
+int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t n_blocks,
+                     const std::vector<uint2>& steps, const std::vector<uint32_t>& block_first,
                      uint32_t n_sets, const uint32_t* const* d_b, const double* const* d_base, double* const* d_out, const double* scale) {
     GSB_REQUIRE(n_sets >= 1 && n_sets <= kLocalTc5MaxSets, GSB200_ERR_ARG, "local GEBV (tcgen05 path): %u effect sets in one pass", n_sets);
     LocalTc5Params P;
     memset(&P, 0, sizeof P);
     for (uint32_t q = 0; q < n_sets; ++q) { P.b[q] = (const uint4*) d_b[q]; P.base[q] = d_base[q]; P.out[q] = d_out[q]; P.scale[q] = scale[q]; }
-    const uint32_t cap = std::min<uint32_t>(kMaxSegSteps, kBBytes / (256 * n_sets));
-    const uint32_t n_seg = (uint32_t) seg_off.size() - 1;
+    const uint32_t n_steps = (uint32_t) steps.size(), n_runs = (uint32_t) block_first.size() - 1;
     const uint32_t n_tiles = (n + 63) / 64;
-    const uint64_t n_items64 = (uint64_t) n_seg * n_tiles;
-    GSB_REQUIRE(n_items64 < (1ull << 31), GSB200_ERR_ARG, "local GEBV: too many work items");
-    const uint32_t n_items = (uint32_t) n_items64;
-    const uint32_t ctas = std::min<uint32_t>((uint32_t) ctx->sm_count, n_items);
-    const uint32_t items_per_cta = (n_items + ctas - 1) / ctas;
-    const uint32_t grid = (n_items + items_per_cta - 1) / items_per_cta;
-    uint32_t seg_steps = 0;
-    for (uint32_t k = 0; k < n_seg; ++k) seg_steps = std::max(seg_steps, seg_off[k + 1] - seg_off[k]);
-    GSB_REQUIRE(seg_steps <= cap, GSB200_ERR_ARG, "local GEBV (tcgen05 path): internal: a segment of %u steps exceeds %u", seg_steps, cap);
-    const uint32_t smem = seg_steps * 256 * n_sets + 256;
-    GSB_CUDA_TRY(cudaFuncSetAttribute(local_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kBBytes + 256));
-    // GSB200_LOCAL_TRACE=<file>: clock64 stamps of CTA 0's first stages (profiles/scripts/local_trace.py reads them)
-    static const char* trace_path = getenv("GSB200_LOCAL_TRACE");
-    static const uint32_t dbg = getenv("GSB200_LOCAL_DEBUG") ? (uint32_t) atoi(getenv("GSB200_LOCAL_DEBUG")) : 0u;
-    long long* d_trace = nullptr;
-    if (trace_path) {
-        GSB_CUDA_TRY(cudaMalloc((void**) &d_trace, 9 * kTraceLen * sizeof(long long)));
-        GSB_CUDA_TRY(cudaMemsetAsync(d_trace, 0, 9 * kTraceLen * sizeof(long long), ctx->stream));
+    const uint32_t step_bytes = 256 * n_sets;
+
+    // ranges of whole blocks: enough items for ~8 per SM (few tiles) but at least 64 steps each
+    uint32_t want = (uint32_t) std::max<uint64_t>(1, ((uint64_t) ctx->sm_count * 8 + n_tiles - 1) / n_tiles);
+    want = std::min(want, std::min(n_runs, std::max(1u, n_steps / 64)));
+    std::vector<uint32_t> cut(1, 0u);                       // first run of every range
+    for (uint32_t r = 1; r < want; ++r) {
+        const uint32_t target = (uint32_t) ((uint64_t) n_steps * r / want);
+        const uint32_t run = (uint32_t) (std::lower_bound(block_first.begin(), block_first.end(), target) - block_first.begin());
+        if (run > cut.back() && run < n_runs) cut.push_back(run);
     }
-    local_tc5_kernel<<<grid, kThreads, smem, ctx->stream>>>(ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, n_blocks, d_steps,
-                                                           (uint32_t) seg_off.back(), d_seg_off, n_tiles, n_items, items_per_cta, n_sets, P, ctx->d_flag + 2, dbg, d_trace);
+    cut.push_back(n_runs);
+    const uint32_t n_ranges = (uint32_t) cut.size() - 1;
+    std::vector<Tc5Range> ranges(n_ranges);
+    std::vector<Tc5Unit> units;
+    std::vector<uint32_t> runs(n_runs), unit_step, heads;
+    for (uint32_t r = 0; r < n_runs; ++r) runs[r] = steps[block_first[r]].y & 0x7fffffffu;
+    uint64_t b_off16 = 0;
+    for (uint32_t k = 0; k < n_ranges; ++k) {
+        const uint32_t s_lo = block_first[cut[k]], s_hi = block_first[cut[k + 1]];
+        Tc5Range& g = ranges[k];
+        g.unit_lo = (uint32_t) units.size();
+        g.run_lo = cut[k]; g.run_hi = cut[k + 1];
+        g.line_lo = steps[s_lo].x >> 5; g.n_lines = (steps[s_hi - 1].x >> 5) - g.line_lo + 1;
+        g.blk_lo = k == 0 ? 0u : runs[cut[k]];
+        g.blk_hi = k + 1 == n_ranges ? n_blocks : runs[cut[k + 1]];
+        uint32_t line_at = g.line_lo - 1;                   // the line the expanders hold (none yet: one before the first)
+        for (uint32_t s = s_lo; s < s_hi;) {
+            // a unit: the steps of one 16-word half line, at most kUnitSteps of them
+            const uint32_t half = steps[s].x / kUnitWords;
+            uint32_t e = s;
+            while (e < s_hi && e - s < kUnitSteps && steps[e].x / kUnitWords == half) ++e;
+            Tc5Unit u;
+            u.b_off16 = (uint32_t) b_off16;
+            u.b_bytes = kUnitHead + (e - s) * step_bytes;
+            u.line_adv_half = (((half >> 1) - line_at) << 1) | (half & 1u);
+            u.pad = 0;
+            line_at = half >> 1;
+            b_off16 += u.b_bytes / 16;
+            GSB_REQUIRE(b_off16 < (1ull << 32), GSB200_ERR_ARG, "local GEBV (tcgen05 path): B stream too long");
+            units.push_back(u);
+            unit_step.push_back(s);
+            const size_t h0 = heads.size();
+            heads.resize(h0 + kUnitHead / 4, 0u);
+            uint32_t n_seg = 0;
+            for (uint32_t p = s; p < e;) {
+                const uint32_t blk = steps[p].y & 0x7fffffffu;
+                uint32_t r = p + 1;
+                while (r < e && (steps[r].y & 0x7fffffffu) == blk) ++r;
+                const bool first = p == s_lo || (steps[p - 1].y & 0x7fffffffu) != blk;
+                const bool last = r == s_hi || (steps[r].y & 0x7fffffffu) != blk;
+                heads[h0 + 1 + n_seg++] = (steps[p].x % kUnitWords) | ((r - p) << 4) | (first ? kSegFirst : 0u) | (last ? kSegLast : 0u);
+                p = r;
+            }
+            heads[h0] = n_seg;
+            s = e;
+        }
+        g.n_units = (uint32_t) units.size() - g.unit_lo;
+    }
+    unit_step.push_back(n_steps);
+    const uint32_t n_units = (uint32_t) units.size();
+
+    // plan -> device: ranges | units | runs | first step of every unit | heads, then the B stream
+    LocalSchedule& sc = ctx->local_sched;
+    auto pad16 = [](size_t x) { return (x + 15) & ~(size_t) 15; };
+    const size_t off_units = ranges.size() * sizeof(Tc5Range), off_runs = off_units + units.size() * sizeof(Tc5Unit);
+    const size_t off_us = pad16(off_runs + runs.size() * 4), off_heads = pad16(off_us + unit_step.size() * 4);
+    const size_t plan_bytes = off_heads + heads.size() * 4;
+    std::vector<uint8_t> plan(plan_bytes);
+    memcpy(plan.data(), ranges.data(), off_units);
+    memcpy(plan.data() + off_units, units.data(), units.size() * sizeof(Tc5Unit));
+    memcpy(plan.data() + off_runs, runs.data(), runs.size() * 4);
+    memcpy(plan.data() + off_us, unit_step.data(), unit_step.size() * 4);
+    memcpy(plan.data() + off_heads, heads.data(), heads.size() * 4);
+    GSB_TRY(sc.d_plan.ensure(plan_bytes));
+    GSB_TRY(sc.d_bstream.ensure((size_t) b_off16 * 16));
+    GSB_CUDA_TRY(cudaMemcpyAsync(sc.d_plan.ptr, plan.data(), plan_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));          // `plan` is pageable host memory about to go out of scope
+    const char* dp = (const char*) sc.d_plan.ptr;
+    const Tc5Unit* d_units = (const Tc5Unit*) (dp + off_units);
+    local_tc5_pack_kernel<<<n_units, 256, 0, ctx->stream>>>((uint4*) sc.d_bstream.ptr, d_units, n_sets,
+                                                             (const uint32_t*) (dp + off_us), (const uint32_t*) (dp + off_heads), P);
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
-    if (d_trace) {
-        std::vector<long long> h(9 * kTraceLen);
-        GSB_CUDA_TRY(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+
+    const uint64_t n_items64 = (uint64_t) n_tiles * n_ranges;
+    GSB_REQUIRE(n_items64 < (1ull << 31), GSB200_ERR_ARG, "local GEBV: too many work items");
+    const uint32_t n_items = (uint32_t) n_items64;
+    const uint32_t fixed = kALines * kALineBytes + 4 * n_sets * 32 * kOutRow * 8;
+    const uint32_t stage_bytes = kUnitHead + kUnitSteps * step_bytes + kStageSlack;
+    const uint32_t n_bstages = std::min<uint32_t>(kMaxBStages, (kSmemBudget - fixed) / stage_bytes);
+    GSB_REQUIRE(n_bstages >= 2, GSB200_ERR_ARG, "local GEBV (tcgen05 path): internal: shared memory does not hold two B stages");
+    const uint32_t smem = fixed + n_bstages * stage_bytes;
+    GSB_CUDA_TRY(cudaFuncSetAttribute(local_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBudget));
+    static const uint32_t dbg = getenv("GSB200_LOCAL_DEBUG") ? (uint32_t) atoi(getenv("GSB200_LOCAL_DEBUG")) : 0u;
+    const uint32_t grid = std::min<uint32_t>((uint32_t) ctx->sm_count, n_items);
+    // GSB200_LOCAL_PROF=<file>: where CTA 0's roles spent their cycles (one line per launch)
+    static const char* prof_path = getenv("GSB200_LOCAL_PROF");
+    long long* d_prof = nullptr;
+    if (prof_path) {
+        GSB_CUDA_TRY(cudaMalloc((void**) &d_prof, 20 * sizeof(long long)));
+        GSB_CUDA_TRY(cudaMemsetAsync(d_prof, 0, 20 * sizeof(long long), ctx->stream));
+    }
+    local_tc5_kernel<<<grid, kThreads, smem, ctx->stream>>>(ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, n_blocks,
+                                                           (const uint8_t*) sc.d_bstream.ptr, (const Tc5Range*) dp, n_ranges, d_units, (const uint32_t*) (dp + off_runs),
+                                                           n_items, n_sets, n_bstages, P, ctx->d_flag + 2, dbg, d_prof);
+    ++ctx->launches;
+    GSB_CUDA_TRY(cudaGetLastError());
+    if (d_prof) {
+        long long h[20];
+        GSB_CUDA_TRY(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
         GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_trace);
-        if (FILE* f = fopen(trace_path, "w")) {
-            fprintf(f, "# stage/flush: expander warp 0 (enter, stage free, first store issued, stores done) | issuer (wants stage, has stage) | epilogue warp 0 (wants sums, has sums, done); cycles since the first stamp\n");
-            long long t0 = h[0];
-            for (uint32_t k = 0; k < kTraceLen; ++k) {
-                fprintf(f, "%3u", k);
-                for (uint32_t r = 0; r < 9; ++r) fprintf(f, " %9lld", h[r * kTraceLen + k] ? h[r * kTraceLen + k] - t0 : -1ll);
-                fprintf(f, "\n");
-            }
+        cudaFree(d_prof);
+        if (FILE* f = fopen(prof_path, "a")) {
+            fprintf(f, "items %u (tiles %u x ranges %u) steps %u units %u sets %u B stages %u | cycles of CTA 0: "
+                       "expander total %lld wait(line) %lld wait(stage free) %lld | epilogue total %lld wait(sums) %lld | "
+                       "issuer total %lld wait(B) %lld wait(operand) %lld wait(accumulator free) %lld | A loader total %lld wait(line free) %lld | "
+                       "B loader total %lld wait(stage free) %lld\n", n_items, n_tiles, n_ranges, n_steps, n_units, n_sets, n_bstages,
+                    h[0], h[1], h[2], h[4], h[5], h[8], h[9], h[10], h[11], h[12], h[13], h[16], h[17]);
             fclose(f);
         }
     }
