@@ -50,8 +50,9 @@ namespace gsb {
 
 namespace {
 
-constexpr uint32_t kWarpIssuer = 8, kWarpALoader = 9, kWarpBLoader = 10;
-constexpr uint32_t kThreads = 11 * 32;           // 4 expander + 4 epilogue warps, issuer, A loader, B loader
+constexpr uint32_t kEpiWarps = 8;                // two per TMEM lane quarter: even / odd effect sets
+constexpr uint32_t kWarpIssuer = 4 + kEpiWarps, kWarpALoader = kWarpIssuer + 1, kWarpBLoader = kWarpIssuer + 2;
+constexpr uint32_t kThreads = (kWarpBLoader + 1) * 32;           // 4 expander + 8 epilogue warps, issuer, A loader, B loader
 constexpr uint32_t kALines = 3;                  // ring of 128-byte lines (32 marker words x 128 strand rows) in shared memory
 constexpr uint32_t kARowBytes = 144;             // 128 + 16: the expanders' 16-byte reads of 8 different rows hit different banks
 constexpr uint32_t kALineBytes = 128 * kARowBytes;
@@ -97,16 +98,19 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     return leader != 0;
 }
-// the kind::i8 MMA of tc5_common.cuh under a predicate of its own
-__device__ __forceinline__ void umma_i8_ts_if(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+// the kind::i8 MMA of tc5_common.cuh under a predicate of its own, without the optional lane mask; the B descriptor in
+// halves (only the low one, which holds the start address, changes from step to step)
+__device__ __forceinline__ void umma_i8_ts_if(uint32_t tmem_d, uint32_t tmem_a, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate, uint32_t issue) {
     asm volatile(
         "{\n\t"
         ".reg .pred p, q;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
+        ".reg .b64 d;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
         "setp.ne.b32 q, %6, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], d, %4, p;\n\t"
         "}\n"
-        :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(issue) : "memory");
+        :: "r"(tmem_d), "r"(tmem_a), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
 }
 __device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const uint32_t* gmem_src) {
     asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" :: "r"(smem_dst), "l"(gmem_src) : "memory");
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         for (uint32_t i = 0; i < kALines; ++i) { mbar_init(&s_afull[i], 32); mbar_init(&s_afree[i], 4); }
         for (uint32_t i = 0; i < 2; ++i) mbar_init(&s_tfull[i], 4);
         for (uint32_t i = 0; i < kMaxBStages; ++i) { mbar_init(&s_bfull[i], 1); mbar_init(&s_udone[i], 1); }
-        for (uint32_t i = 0; i < kSlots; ++i) { mbar_init(&s_dready[i], 1); mbar_init(&s_dfree[i], 4); }
+        for (uint32_t i = 0; i < kSlots; ++i) { mbar_init(&s_dready[i], 1); mbar_init(&s_dfree[i], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWarpIssuer) {
@@ -201,9 +205,10 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
     const uint32_t bar_bfull = smem_u32(s_bfull), bar_dready = smem_u32(s_dready), bar_dfree = smem_u32(s_dfree);
     const uint32_t step_bytes = 256 * n_sets, stage_bytes = kUnitHead + kUnitSteps * step_bytes + kStageSlack;
     const uint32_t a_smem = smem_u32(s_dyn);
-    const uint32_t out_bytes_warp = n_sets * 32 * kOutRow * 8;
+    const uint32_t sets_warp = (n_sets + 1) / 2;                    // effect sets per epilogue warp
+    const uint32_t out_bytes_warp = sets_warp * 32 * kOutRow * 8;
     double* const out_stage0 = reinterpret_cast<double*>(s_dyn + kALines * kALineBytes);
-    const uint32_t b_smem = a_smem + kALines * kALineBytes + 4 * out_bytes_warp;
+    const uint32_t b_smem = a_smem + kALines * kALineBytes + kEpiWarps * out_bytes_warp;
     // M = 128 wants N % 16 == 0: an odd number of sets contracts 8 more columns against the bytes that follow
     // (the next step's first set, or whatever the stage held before) into accumulator columns nobody reads
     const uint32_t n_cols = (8 * n_sets + 15) & ~15u;
@@ -251,9 +256,11 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                 wait_on(bar_afull + 8 * as, (q_line / kALines) & 1, 0);
                 ++q_line; ++lines_taken;
             };
+            uint32_t desc_next = __ldg(&units[rg.unit_lo].line_adv_half);
 #pragma unroll 1
             for (uint32_t u = 0; u < rg.n_units; ++u, ++q_unit) {
-                const uint32_t desc = __ldg(&units[rg.unit_lo + u].line_adv_half);
+                const uint32_t desc = desc_next;
+                if (u + 1 < rg.n_units) desc_next = __ldg(&units[rg.unit_lo + u + 1].line_adv_half);      // an L2 round trip: asked for a unit ahead
 #pragma unroll 1
                 for (uint32_t k = desc >> 1; k; --k) next_line();
                 const uint32_t src = a_smem + as * kALineBytes + tid * kARowBytes + (desc & 1u) * 64;
@@ -284,26 +291,29 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
             if (lane == 0) mbar_arrive(bar_afree + 8 * as);
         }
         if (warp == 0) prof_out(0);
-    } else if (warp < 8) {
-        // ---------------- epilogue: thread (tid - 128) = TMEM lane = strand row of the tile
-        const uint32_t wq = warp - 4;
-        double* const stage = out_stage0 + (size_t) wq * (out_bytes_warp / 8);
+    } else if (warp < 4 + kEpiWarps) {
+        // ---------------- epilogue: lane = TMEM lane within the quarter wq = strand row of the tile; the two warps of a
+        // quarter take the even and the odd effect sets (a lone warp per quarter recombining ten sets took ~3 300
+        // cycles per block, four times what the MMAs of a 270-marker block take)
+        const uint32_t wq = warp & 3, half = (warp - 4) >> 2;
+        const uint32_t my_sets = (n_sets + 1 - half) / 2;               // sets half, half + 2, ...
+        double* const stage = out_stage0 + (size_t) (warp - 4) * (out_bytes_warp / 8);
         uint32_t slot = 0, slot_par = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const Tc5Range rg = range_of(item);
             const uint32_t tile = item / n_ranges;
-            // four blocks [g0, g0 + 4) staged for the warp's 32 rows -> 32 contiguous bytes per row and set
+            // four blocks [g0, g0 + 4) staged for the quarter's 32 rows -> 32 contiguous bytes per row and set
             auto flush = [&](uint32_t g_hi) {
                 const uint32_t g0 = (g_hi - 1) & ~3u, g_lo = max(g0, rg.blk_lo);
                 __syncwarp();
                 const uint32_t sl = lane & 3, b = g0 + sl;
-                if (b >= g_lo && b < g_hi) {
+                if (b >= g_lo && b < g_hi && !(dbg & 64u)) {
 #pragma unroll
                     for (uint32_t i = 0; i < 4; ++i) {
                         const uint32_t rl = 8 * i + (lane >> 2), strand_row = wq * 32 + rl;
                         if (tile * 64 + (strand_row >> 1) < n) {
                             const size_t o = ((size_t) tile * 128 + strand_row) * n_blocks + b;
-                            for (uint32_t q = 0; q < n_sets; ++q) P.out[q][o] = stage[(q * 32 + rl) * kOutRow + sl];
+                            for (uint32_t j = 0; j < my_sets; ++j) P.out[2 * j + half][o] = stage[(j * 32 + rl) * kOutRow + sl];
                         }
                     }
                 }
@@ -312,44 +322,66 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
             uint32_t blk_next = rg.blk_lo;
             auto empty_until = [&](uint32_t blk) {                // blocks without markers sum to 0
                 while (blk_next < blk) {
-                    for (uint32_t q = 0; q < n_sets; ++q) stage[(q * 32 + lane) * kOutRow + (blk_next & 3)] = 0.0;
+                    for (uint32_t j = 0; j < my_sets; ++j) stage[(j * 32 + lane) * kOutRow + (blk_next & 3)] = 0.0;
                     ++blk_next;
                     if ((blk_next & 3) == 0 || blk_next == rg.blk_hi) flush(blk_next);
                 }
             };
+            // the block numbers two runs ahead and the bases one run ahead: global loads, an L2 round trip each, that a lone
+            // warp cannot hide otherwise (they were ~1 400 of the ~3 000 cycles a block's flush took)
+            constexpr uint32_t kMySets = (kLocalTc5MaxSets + 1) / 2;
+            uint32_t blk_n1 = __ldg(runs + rg.run_lo), blk_n2 = rg.run_lo + 1 < rg.run_hi ? __ldg(runs + rg.run_lo + 1) : 0u;
+            double base_n1[kMySets];
+#pragma unroll
+            for (uint32_t j = 0; j < kMySets; ++j) base_n1[j] = j < my_sets ? __ldg(P.base[2 * j + half] + blk_n1) : 0.0;
 #pragma unroll 1
             for (uint32_t run = rg.run_lo; run < rg.run_hi; ++run) {
-                const uint32_t blk = __ldg(runs + run);
+                const uint32_t blk = blk_n1;
+                double base[kMySets];
+#pragma unroll
+                for (uint32_t j = 0; j < kMySets; ++j) base[j] = base_n1[j];
+                blk_n1 = blk_n2;
+                if (run + 1 < rg.run_hi) {
+#pragma unroll
+                    for (uint32_t j = 0; j < kMySets; ++j) if (j < my_sets) base_n1[j] = __ldg(P.base[2 * j + half] + blk_n1);
+                }
+                if (run + 2 < rg.run_hi) blk_n2 = __ldg(runs + run + 2);
                 empty_until(blk);
                 wait_on(bar_dready + 8 * slot, slot_par, 0);
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((wq * 32) << 16) + kSlotCols * slot;
-#pragma unroll 1
-                for (uint32_t q0 = 0; q0 < ((dbg & 4u) ? 0u : n_sets); q0 += 4) {
-                    // four sets at a time: the loads first, then four independent recombinations
-                    uint32_t d[4][8];
+                const uint32_t todo = (dbg & 4u) ? 0u : my_sets;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                     : "=r"(d[j][0]), "=r"(d[j][1]), "=r"(d[j][2]), "=r"(d[j][3]), "=r"(d[j][4]), "=r"(d[j][5]), "=r"(d[j][6]), "=r"(d[j][7])
-                                     : "r"(taddr + 8 * min(q0 + j, n_sets - 1)) : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (q0 + 4 >= n_sets) {                            // the accumulator can take another block
+                for (uint32_t j0 = 0; j0 < kMySets + 1; j0 += 3) {
+                    // three sets at a time: the loads first, then three independent recombinations
+                    uint32_t d[3][8];
+                    if (j0 < todo) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=r"(d[j][0]), "=r"(d[j][1]), "=r"(d[j][2]), "=r"(d[j][3]), "=r"(d[j][4]), "=r"(d[j][5]), "=r"(d[j][6]), "=r"(d[j][7])
+                                         : "r"(taddr + 8 * (2 * min(j0 + j, my_sets - 1) + half)) : "memory");
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    }
+                    if (j0 + 3 >= todo && (j0 < todo || j0 == 0)) {     // the accumulator can take another block
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_dfree + 8 * slot);
                     }
+                    if (j0 < todo) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t q = q0 + j;
-                        // sum_k d_k 256^k: the two halves are exact in int64 (|d_k| < 2^31), one fp64 fma joins them
-                        const long long lo = (long long) (int) d[j][0] + ((long long) (int) d[j][1] << 8) + ((long long) (int) d[j][2] << 16) + ((long long) (int) d[j][3] << 24);
-                        const long long hi = (long long) (int) d[j][4] + ((long long) (int) d[j][5] << 8) + ((long long) (int) d[j][6] << 16) + ((long long) (int) d[j][7] << 24);
-                        if (q < n_sets)
-                            stage[(q * 32 + lane) * kOutRow + (blk & 3)] = fma((double) hi, 4294967296.0, (double) lo) * P.scale[q] + __ldg(P.base[q] + blk);
+                        for (int j = 0; j < 3; ++j) {
+                            if (j0 + j < kMySets) {
+                                // sum_k d_k 256^k by Horner in fp64: |d_k| < 2^31, so every step is exact or rounds at 2^-53 relative
+                                double v = (double) (int) d[j][7];
+#pragma unroll
+                                for (int k = 6; k >= 0; --k) v = fma(v, 256.0, (double) (int) d[j][k]);
+                                if (j0 + j < my_sets)
+                                    stage[((j0 + j) * 32 + lane) * kOutRow + (blk & 3)] = fma(v, P.scale[2 * (j0 + j) + half], base[j0 + j]);
+                            }
+                        }
                     }
                 }
-                if (dbg & 4u) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_dfree + 8 * slot); }
                 if (++slot == kSlots) { slot = 0; slot_par ^= 1; }
                 blk_next = blk + 1;
                 if ((blk_next & 3) == 0 || blk_next == rg.blk_hi) flush(blk_next);
@@ -364,26 +396,31 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         // MMA issues in 17 cycles and N = 80 runs at its 40-cycle floor (profiles/r2_umma_i8_probe2.txt).
         uint32_t q_unit = 0, ring_i = 0, b_stage = 0, b_par = 0;
         uint32_t q_blk = 0, slot = 0, slot_par = 0;       // slot = q_blk % kSlots, slot_par = (q_blk / kSlots) & 1
-        uint32_t d_addr = tmem;
+        // (addresses that came out of shared memory or a cvta, re-declared warp-uniform for the compiler)
+        const uint32_t u_tmem = __shfl_sync(0xffffffffu, tmem, 0), u_b_smem = __shfl_sync(0xffffffffu, b_smem, 0);
+        uint32_t d_addr = u_tmem;
+        const uint32_t d_hi = (uint32_t) (b_descriptor(0) >> 32);
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const Tc5Range rg = range_of(item);
 #pragma unroll 1
             for (uint32_t u = 0; u < rg.n_units; ++u, ++q_unit) {
                 wait_on(bar_bfull + 8 * b_stage, b_par, 0);
-                const uint32_t b_addr = b_smem + b_stage * stage_bytes;
-                const uint32_t n_seg = lds32(b_addr);
-                uint64_t desc = b_descriptor(b_addr + kUnitHead);
-                uint32_t seg = lds32(b_addr + 4);
+                const uint32_t b_addr = u_b_smem + b_stage * stage_bytes;
+                // (records go through a shuffle from lane 0: it tells the compiler they are warp-uniform, and the MMA operands
+                // derived from them then live in uniform registers instead of being moved there one by one)
+                const uint32_t n_seg = __shfl_sync(0xffffffffu, lds32(b_addr), 0);
+                uint32_t d_lo = (uint32_t) b_descriptor(b_addr + kUnitHead);      // the half with the start address
+                uint32_t seg = __shfl_sync(0xffffffffu, lds32(b_addr + 4), 0);
                 wait_on(bar_tfull + 8 * (q_unit & 1), (q_unit >> 1) & 1, 1);
                 tc_fence_after();
-                const uint32_t a_base = tmem + kACol0 + kStageCols * (q_unit & 1);
+                const uint32_t a_base = u_tmem + kACol0 + kStageCols * (q_unit & 1);
                 const long long tl = clock64();
                 // a segment = consecutive words of one block: its MMAs are issued four at a time from one elected lane
                 // with nothing but uniform adds between them — a lone warp pays ~15 cycles per branch, so per-STEP
                 // control flow (the first version of this loop) cost 200 cycles per step
 #pragma unroll 1
                 for (uint32_t sg = 0; sg < n_seg; ++sg) {
-                    const uint32_t seg_next = lds32(b_addr + 8 + 4 * sg);
+                    const uint32_t seg_next = __shfl_sync(0xffffffffu, lds32(b_addr + 8 + 4 * sg), 0);
                     const uint32_t cnt = (seg >> 4) & 31u;
                     uint32_t acc = 1;
                     if (seg & kSegFirst) {
@@ -391,24 +428,20 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
                             wait_on(bar_dfree + 8 * slot, slot_par ^ 1, 2);
                             tc_fence_after();
                         }
-                        d_addr = tmem + kSlotCols * slot;
+                        d_addr = u_tmem + kSlotCols * slot;
                         acc = 0;
                     }
-                    uint32_t a_addr = a_base + 8 * (seg & 15u);
-#pragma unroll 1
-                    for (uint32_t c = 0; c < cnt; c += 4) {
-                        if (!(dbg & 2u) && elect_one()) {
-                            umma_i8_ts_if(d_addr, a_addr, desc, idesc, acc, 1u);
-                            umma_i8_ts_if(d_addr, a_addr + 8, desc + (step_bytes >> 4), idesc, 1u, c + 1 < cnt);
-                            umma_i8_ts_if(d_addr, a_addr + 16, desc + 2 * (step_bytes >> 4), idesc, 1u, c + 2 < cnt);
-                            umma_i8_ts_if(d_addr, a_addr + 24, desc + 3 * (step_bytes >> 4), idesc, 1u, c + 3 < cnt);
-                        }
-                        __syncwarp();
-                        acc = 1;
-                        a_addr += 32;
-                        desc += 4 * (step_bytes >> 4);          // the start-address field counts 16-byte units
+                    const uint32_t a_addr = a_base + 8 * (seg & 15u);
+                    if (!(dbg & 2u) && elect_one()) {
+                        // straight-line: up to kUnitSteps predicated MMAs.  The tensor pipe takes the next MMA only when it has little
+                        // else queued, so what the issuing warp executes between two MMAs is added to the 40 cycles the MMA takes
+                        const uint32_t sd = step_bytes >> 4;          // the descriptor's start-address field counts 16-byte units
+#pragma unroll
+                        for (uint32_t k = 0; k < kUnitSteps; ++k)
+                            umma_i8_ts_if(d_addr, a_addr + 8 * k, d_lo + k * sd, d_hi, idesc, k == 0 ? acc : 1u, k < cnt);
                     }
-                    desc -= (uint64_t) ((0u - cnt) & 3u) * (step_bytes >> 4);      // the last trip's unused steps
+                    __syncwarp();
+                    d_lo += cnt * (step_bytes >> 4);
                     if (seg & kSegLast) {
                         if (elect_one()) tc_commit(bar_dready + 8 * slot);
                         __syncwarp();
@@ -611,7 +644,7 @@ int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32
     const uint64_t n_items64 = (uint64_t) n_tiles * n_ranges;
     GSB_REQUIRE(n_items64 < (1ull << 31), GSB200_ERR_ARG, "local GEBV: too many work items");
     const uint32_t n_items = (uint32_t) n_items64;
-    const uint32_t fixed = kALines * kALineBytes + 4 * n_sets * 32 * kOutRow * 8;
+    const uint32_t fixed = kALines * kALineBytes + kEpiWarps * ((n_sets + 1) / 2) * 32 * kOutRow * 8;
     const uint32_t stage_bytes = kUnitHead + kUnitSteps * step_bytes + kStageSlack;
     const uint32_t n_bstages = std::min<uint32_t>(kMaxBStages, (kSmemBudget - fixed) / stage_bytes);
     GSB_REQUIRE(n_bstages >= 2, GSB200_ERR_ARG, "local GEBV (tcgen05 path): internal: shared memory does not hold two B stages");
