@@ -498,7 +498,9 @@ def engine_arm(a):
             "regime": "parent pool of %d rows = %.1f MB %s the 126 MB L2: parents are re-read from %s" %
                       (top, pool_mb, "fits" if pool_mb < 100 else "does not fit", "L2" if pool_mb < 100 else "DRAM")}
     roof["frac"] = roof["achieved"] / peak
-    roof_g = {"bound": "hbm", "kernel": "gebv_counts_kernel (+ memset + gebv_finish_kernel)", "achieved": alg_gebv / (gebv_ms * 1e-3) / 1e9,
+    # the GEBV kernel is bound by instruction issue, not by HBM (alu + imma pipes busy 99.9 % of the active
+    # cycles in the committed ncu capture); achieved / peak / frac stay the HBM figures the north star asks for
+    roof_g = {"bound": "issue", "kernel": "gebv_counts_kernel (+ memset + gebv_finish_kernel)", "achieved": alg_gebv / (gebv_ms * 1e-3) / 1e9,
               "peak": peak, "unit": "GB/s", "traffic": None, "ms_per_launch": gebv_ms, "algorithmic_bytes_per_launch": alg_gebv}
     roof_g["frac"] = roof_g["achieved"] / peak
     try:        # per-launch DRAM traffic from the committed ncu capture of this same command (profiles/)
@@ -507,6 +509,10 @@ def engine_arm(a):
         roof["traffic"] = tr.get("splice_flat_kernel")
         roof_g["traffic"] = tr.get("gebv_counts_kernel")
         roof["traffic_source"] = roof_g["traffic_source"] = tr.get("source")
+        if tr.get("gebv_issue"):
+            gi = dict(tr["gebv_issue"])
+            gi["frac"] = gi["alu_pipe_active_frac"] + gi["imma_pipe_active_frac"]
+            roof_g["issue"] = gi
     except Exception:
         pass
 

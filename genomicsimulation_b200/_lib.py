@@ -154,6 +154,15 @@ HOST_SYMBOLS = {
     "gsb_make_group_from": (UINT, [VP, UINT, VP]),
     "gsb_delete_group": (None, [VP, UINT]),
     "gsb_combine_groups": (UINT, [VP, UINT, VP]),
+    "gsb_split_into_families": (UINT, [VP, UINT, UINT, VP]),
+    "gsb_split_into_halfsib_families": (UINT, [VP, UINT, C.c_int, UINT, VP]),
+    "gsb_split_into_individuals": (UINT, [VP, UINT, UINT, VP]),
+    "gsb_split_evenly_into_two": (UINT, [VP, UINT]),
+    "gsb_split_evenly_into_n": (UINT, [VP, UINT, UINT, VP]),
+    "gsb_split_into_buckets": (UINT, [VP, UINT, UINT, VP, VP]),
+    "gsb_split_randomly_into_two": (UINT, [VP, UINT]),
+    "gsb_split_randomly_into_n": (UINT, [VP, UINT, UINT, VP]),
+    "gsb_split_by_probabilities": (UINT, [VP, UINT, UINT, VP, VP]),
     "gsb_make_random_crosses": (UINT, [VP, UINT, UINT, UINT, UINT, GenOptions]),
     "gsb_make_random_crosses_between": (UINT, [VP, UINT, UINT, UINT, UINT, UINT, UINT, UINT, GenOptions]),
     "gsb_make_targeted_crosses": (UINT, [VP, UINT, VP, VP, UINT, UINT, GenOptions]),

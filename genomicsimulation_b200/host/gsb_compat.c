@@ -93,6 +93,32 @@ gsc_GroupNum gsc_split_by_bv(gsc_SimData* d, const gsc_GroupNum group, const gsc
     return (gsc_GroupNum){ .num = gsb_split_by_bv(d->engine, group.num, e.id, top_n, low) };
 }
 
+/* gsc_GroupNum is a struct of one unsigned (core.h:561-563): an array of them is an array of unsigned */
+_Static_assert(sizeof(gsc_GroupNum) == sizeof(unsigned), "gsc_GroupNum arrays are passed through as unsigned arrays");
+unsigned int gsc_split_into_families(gsc_SimData* d, const gsc_GroupNum g, unsigned int cap, gsc_GroupNum* results) {
+    return gsb_split_into_families(d->engine, g.num, cap, (unsigned*) results);
+}
+unsigned int gsc_split_into_halfsib_families(gsc_SimData* d, const gsc_GroupNum g, const int parent, unsigned int cap, gsc_GroupNum* results) {
+    return gsb_split_into_halfsib_families(d->engine, g.num, parent, cap, (unsigned*) results);
+}
+unsigned int gsc_split_into_individuals(gsc_SimData* d, const gsc_GroupNum g, unsigned int cap, gsc_GroupNum* results) {
+    return gsb_split_into_individuals(d->engine, g.num, cap, (unsigned*) results);
+}
+gsc_GroupNum gsc_split_evenly_into_two(gsc_SimData* d, const gsc_GroupNum g) { return (gsc_GroupNum){ .num = gsb_split_evenly_into_two(d->engine, g.num) }; }
+unsigned int gsc_split_evenly_into_n(gsc_SimData* d, const gsc_GroupNum g, const unsigned int n, gsc_GroupNum* results) {
+    return gsb_split_evenly_into_n(d->engine, g.num, n, (unsigned*) results);
+}
+unsigned int gsc_split_into_buckets(gsc_SimData* d, const gsc_GroupNum g, const unsigned int n, const GSC_GLOBALX_T* counts, gsc_GroupNum* results) {
+    return gsb_split_into_buckets(d->engine, g.num, n, counts, (unsigned*) results);
+}
+gsc_GroupNum gsc_split_randomly_into_two(gsc_SimData* d, const gsc_GroupNum g) { return (gsc_GroupNum){ .num = gsb_split_randomly_into_two(d->engine, g.num) }; }
+unsigned int gsc_split_randomly_into_n(gsc_SimData* d, const gsc_GroupNum g, const unsigned int n, gsc_GroupNum* results) {
+    return gsb_split_randomly_into_n(d->engine, g.num, n, (unsigned*) results);
+}
+unsigned int gsc_split_by_probabilities(gsc_SimData* d, const gsc_GroupNum g, const unsigned int n, const double* probs, gsc_GroupNum* results) {
+    return gsb_split_by_probabilities(d->engine, g.num, n, probs, (unsigned*) results);
+}
+
 /* flat row-major -> one allocation per row, as the reference hands matrices out (core.c:419-429) */
 static gsc_DecimalMatrix rows_of(gsb_DecimalMatrix f) {
     gsc_DecimalMatrix m = { NULL, 0, 0 };

@@ -365,3 +365,45 @@ class SimData:
 
     def delete_group(self, group):
         self.L.gsb_delete_group(self.d, group)
+
+    def combine_groups(self, groups):
+        a = np.ascontiguousarray(groups, dtype=np.uint32)
+        return self.L.gsb_combine_groups(self.d, len(a), _p(a))
+
+    # ---- group-split utilities (gsb_split_*, core.c:2980-3784): each returns the list of new group numbers
+    def _split(self, fn, group, cap, *args):
+        out = np.zeros(max(cap, 1), dtype=np.uint32)
+        n = fn(self.d, group, *args, _p(out))
+        return [int(x) for x in out[:min(n, cap)]]
+
+    def split_into_families(self, group):
+        cap = self.group_size(group)
+        return self._split(self.L.gsb_split_into_families, group, cap, cap)
+
+    def split_into_halfsib_families(self, group, parent):
+        cap = self.group_size(group)
+        return self._split(self.L.gsb_split_into_halfsib_families, group, cap, parent, cap)
+
+    def split_into_individuals(self, group):
+        cap = self.group_size(group)
+        return self._split(self.L.gsb_split_into_individuals, group, cap, cap)
+
+    def split_evenly_into_two(self, group):
+        return self.L.gsb_split_evenly_into_two(self.d, group)
+
+    def split_evenly_into_n(self, group, n):
+        return self._split(self.L.gsb_split_evenly_into_n, group, n, n)
+
+    def split_into_buckets(self, group, counts):
+        c = np.ascontiguousarray(counts, dtype=np.uint32)
+        return self._split(self.L.gsb_split_into_buckets, group, len(c) + 1, len(c) + 1, _p(c))
+
+    def split_randomly_into_two(self, group):
+        return self.L.gsb_split_randomly_into_two(self.d, group)
+
+    def split_randomly_into_n(self, group, n):
+        return self._split(self.L.gsb_split_randomly_into_n, group, n, n)
+
+    def split_by_probabilities(self, group, probs):
+        pr = np.ascontiguousarray(probs, dtype=np.float64)
+        return self._split(self.L.gsb_split_by_probabilities, group, len(pr) + 1, len(pr) + 1, _p(pr))

@@ -124,6 +124,16 @@ gsc_GroupNum gsc_make_clones(gsc_SimData* d, const gsc_GroupNum group, const _Bo
 gsc_GroupNum gsc_make_all_unidirectional_crosses(gsc_SimData* d, const gsc_GroupNum from_group, const gsc_MapID mapID, const gsc_GenOptions g);
 
 gsc_GroupNum gsc_split_by_bv(gsc_SimData* d, const gsc_GroupNum group, const gsc_EffectID effID, const GSC_GLOBALX_T top_n, const _Bool lowIsBest);
+/* group-split utilities, core.h:1469-1520 */
+unsigned int gsc_split_into_families(gsc_SimData* d, const gsc_GroupNum group_id, unsigned int maxentries_results, gsc_GroupNum* results);
+unsigned int gsc_split_into_halfsib_families(gsc_SimData* d, const gsc_GroupNum group_id, const int parent, unsigned int maxentries_results, gsc_GroupNum* results);
+unsigned int gsc_split_into_individuals(gsc_SimData* d, const gsc_GroupNum group_id, unsigned int maxentries_results, gsc_GroupNum* results);
+gsc_GroupNum gsc_split_evenly_into_two(gsc_SimData* d, const gsc_GroupNum group_id);
+unsigned int gsc_split_evenly_into_n(gsc_SimData* d, const gsc_GroupNum group_id, const unsigned int n, gsc_GroupNum* results);
+unsigned int gsc_split_into_buckets(gsc_SimData* d, const gsc_GroupNum group_id, const unsigned int n, const GSC_GLOBALX_T* counts, gsc_GroupNum* results);
+gsc_GroupNum gsc_split_randomly_into_two(gsc_SimData* d, const gsc_GroupNum group_id);
+unsigned int gsc_split_randomly_into_n(gsc_SimData* d, const gsc_GroupNum group_id, const unsigned int n, gsc_GroupNum* results);
+unsigned int gsc_split_by_probabilities(gsc_SimData* d, const gsc_GroupNum group_id, const unsigned int n, const double* probs, gsc_GroupNum* results);
 gsc_DecimalMatrix gsc_calculate_bvs(const gsc_SimData* d, const gsc_GroupNum group, const gsc_EffectID effID);
 gsc_DecimalMatrix gsc_calculate_allele_counts(const gsc_SimData* d, const gsc_GroupNum group, const char allele);
 gsc_DecimalMatrix gsc_calculate_local_bvs(const gsc_SimData* d, const gsc_GroupNum group, const gsc_MarkerBlocks b, const gsc_EffectID effID);
@@ -166,6 +176,15 @@ typedef gsc_MapID MapID;
 #define make_clones gsc_make_clones
 #define make_all_unidirectional_crosses gsc_make_all_unidirectional_crosses
 #define split_by_bv gsc_split_by_bv
+#define split_into_families gsc_split_into_families
+#define split_into_halfsib_families gsc_split_into_halfsib_families
+#define split_into_individuals gsc_split_into_individuals
+#define split_evenly_into_two gsc_split_evenly_into_two
+#define split_evenly_into_n gsc_split_evenly_into_n
+#define split_into_buckets gsc_split_into_buckets
+#define split_randomly_into_two gsc_split_randomly_into_two
+#define split_randomly_into_n gsc_split_randomly_into_n
+#define split_by_probabilities gsc_split_by_probabilities
 #define calculate_bvs gsc_calculate_bvs
 #define calculate_allele_counts gsc_calculate_allele_counts
 #define calculate_local_bvs gsc_calculate_local_bvs

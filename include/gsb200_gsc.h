@@ -126,6 +126,19 @@ gsb_GroupNum gsb_make_group_from(gsb_SimData* d, unsigned int n, const unsigned 
 void gsb_delete_group(gsb_SimData* d, gsb_GroupNum group);            /* core.c:4658-4692 */
 gsb_GroupNum gsb_combine_groups(gsb_SimData* d, unsigned int n, const gsb_GroupNum* groups);   /* core.c:2705-2742 */
 
+/* ---- group-split utilities (core.c:2980-3784): metadata only.  `results` receives the new group
+ * numbers (the smallest free ones, in order of first appearance), the return value is how many groups were made.
+ * Families come out of a hash table, one probe per genotype (the reference searches the families found so far). */
+unsigned int gsb_split_into_families(gsb_SimData* d, gsb_GroupNum group, unsigned int maxentries_results, gsb_GroupNum* results);               /* core.c:3207-3230 */
+unsigned int gsb_split_into_halfsib_families(gsb_SimData* d, gsb_GroupNum group, int parent, unsigned int maxentries_results, gsb_GroupNum* results); /* core.c:3125-3153 */
+unsigned int gsb_split_into_individuals(gsb_SimData* d, gsb_GroupNum group, unsigned int maxentries_results, gsb_GroupNum* results);            /* core.c:3264-3271 */
+gsb_GroupNum gsb_split_evenly_into_two(gsb_SimData* d, gsb_GroupNum group);                                                                      /* core.c:3298-3334 */
+unsigned int gsb_split_evenly_into_n(gsb_SimData* d, gsb_GroupNum group, unsigned int n, gsb_GroupNum* results);                                 /* core.c:3444-3484 */
+unsigned int gsb_split_into_buckets(gsb_SimData* d, gsb_GroupNum group, unsigned int n, const unsigned int* counts, gsb_GroupNum* results);      /* core.c:3521-3560 */
+gsb_GroupNum gsb_split_randomly_into_two(gsb_SimData* d, gsb_GroupNum group);                                                                    /* core.c:3580-3602 */
+unsigned int gsb_split_randomly_into_n(gsb_SimData* d, gsb_GroupNum group, unsigned int n, gsb_GroupNum* results);                               /* core.c:3645-3667 */
+unsigned int gsb_split_by_probabilities(gsb_SimData* d, gsb_GroupNum group, unsigned int n, const double* probs, gsb_GroupNum* results);         /* core.c:3720-3763 */
+
 /* ---- crossing (core.c:8483-9212); same argument order as the reference */
 gsb_GroupNum gsb_make_random_crosses(gsb_SimData* d, gsb_GroupNum from_group, unsigned int n_crosses,
                                      unsigned int cap, gsb_MapID which_map, gsb_GenOptions g);

@@ -355,6 +355,15 @@ class RefSim:
     def split_by_bv(self, group, eff_id, top_n, low_is_best=False):
         return self.L.refb_split_by_bv(self.d, group, eff_id, top_n, int(low_is_best))
 
+    def split(self, kind, group, n=0, counts=None, probs=None):
+        """the reference's group-split utilities (refb_split in ref_bridge.c lists the kinds); returns the new group numbers"""
+        cap = max(self.group_size(group), n, 1)
+        out = np.zeros(cap, dtype=np.uint32)
+        c = _u32(counts if counts is not None else [0])
+        pr = np.ascontiguousarray(probs if probs is not None else [0.0], dtype=np.float64)
+        made = self.L.refb_split(self.d, kind, group, n, _ptr(c, U), pr.ctypes.data_as(C.POINTER(C.c_double)), cap, _ptr(out, U))
+        return [int(x) for x in out[:min(made, cap)]]
+
     def make_group_from(self, indexes):
         a = _u32(indexes)
         return self.L.refb_make_group_from(self.d, len(a), _ptr(a, U))

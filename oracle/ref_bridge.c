@@ -297,6 +297,29 @@ EXPORT unsigned refb_split_by_bv(void* d, unsigned group, unsigned eff_id, unsig
     return gsc_split_by_bv((gsc_SimData*) d, (gsc_GroupNum){.num = group}, (gsc_EffectID){.id = eff_id},
                            top_n, low_is_best != 0).num;
 }
+/* group-split utilities of the reference (core.c:2980-3784); kind: 0 families, 1 / 2 half-sibs on parent 1 / 2, 3 individuals,
+ * 4 evenly into two, 5 evenly into n, 6 buckets (counts), 7 randomly into two, 8 randomly into n, 9 by probabilities */
+EXPORT unsigned refb_split(void* dv, int kind, unsigned group, unsigned n, const unsigned* counts, const double* probs, unsigned cap, unsigned* out) {
+    gsc_SimData* d = (gsc_SimData*) dv;
+    const gsc_GroupNum g = { .num = group };
+    gsc_GroupNum res[cap ? cap : 1];
+    unsigned made = 0;
+    for (unsigned i = 0; i < cap; ++i) res[i].num = 0;
+    switch (kind) {
+        case 0: made = gsc_split_into_families(d, g, cap, res); break;
+        case 1: case 2: made = gsc_split_into_halfsib_families(d, g, kind, cap, res); break;
+        case 3: made = gsc_split_into_individuals(d, g, cap, res); break;
+        case 4: res[0] = gsc_split_evenly_into_two(d, g); made = res[0].num != 0; break;
+        case 5: made = gsc_split_evenly_into_n(d, g, n, res); break;
+        case 6: made = gsc_split_into_buckets(d, g, n, counts, res); break;
+        case 7: res[0] = gsc_split_randomly_into_two(d, g); made = res[0].num != 0; break;
+        case 8: made = gsc_split_randomly_into_n(d, g, n, res); break;
+        case 9: made = gsc_split_by_probabilities(d, g, n, probs, res); break;
+        default: break;
+    }
+    for (unsigned i = 0; i < cap; ++i) out[i] = res[i].num;
+    return made;
+}
 EXPORT unsigned refb_make_group_from(void* d, unsigned n, const unsigned* indexes) {
     return gsc_make_group_from((gsc_SimData*) d, n, indexes).num;
 }

@@ -31,7 +31,8 @@ def W():
     for name in ("shim_int_vector", "shim_real_vector", "shim_logical", "shim_string", "shim_nil", "shim_extptr", "shim_data",
                  "gsc_compat_attach", "SXP_make_random_crosses", "SXP_self_n_times", "SXP_make_doubled_haploids", "SXP_make_clones",
                  "SXP_break_group_by_GEBV_num", "SXP_break_group_by_GEBV_percent", "SXP_create_markerblocks_nperchr",
-                 "SXP_see_local_gebvs", "SXP_save_genotypes", "SXP_save_GEBVs", "SXP_save_local_GEBVs", "SXP_make_targeted_crosses"):
+                 "SXP_see_local_gebvs", "SXP_save_genotypes", "SXP_save_GEBVs", "SXP_save_local_GEBVs", "SXP_make_targeted_crosses",
+                 "SXP_break_group_into_families", "SXP_break_group_into_halfsib_families", "SXP_break_group_evenly"):
         getattr(L, name).restype = VP
     L.shim_int_vector.argtypes = [C.c_ssize_t, VP]
     L.shim_real_vector.argtypes = [C.c_ssize_t, VP]
@@ -136,4 +137,21 @@ def test_unmodified_r_wrappers_drive_the_engine(W, tmp_path):
     tc = int(r.int_result(VP(W.SXP_make_targeted_crosses(exd, VP(n1), r.chr("k30"), r.ints(0), r.ints(0), *r.genoptions(family=3))))[0])
     y = sim.export_group(tc, genotypes=False)
     assert sim.group_size(tc) == 3 and set(y["ped1"]) == {21} and set(y["ped2"]) == {30}
+
+    # break.group.into.families / .halfsib.families / .evenly: the group-split utilities behind their unmodified wrappers
+    # (r-wrappers.c:1383-1517): what is left of f1 are full-sib pairs -> one group per pair of parents still together
+    left = sim.export_group(f1, genotypes=False)
+    pairs = {(a, b) for a, b in zip(left["ped1"].tolist(), left["ped2"].tolist())}
+    fams = r.int_result(VP(W.SXP_break_group_into_families(exd, r.ints(f1))))
+    assert len(fams) == len(pairs) and sim.group_size(f1) == 0
+    assert sum(sim.group_size(int(g)) for g in fams) == len(left["ids"])
+    for g in fams[:5]:
+        z = sim.export_group(int(g), genotypes=False)
+        assert len(set(zip(z["ped1"].tolist(), z["ped2"].tolist()))) == 1
+    firsts = set(sim.export_group(s3, genotypes=False)["ped1"].tolist())
+    hs = r.int_result(VP(W.SXP_break_group_into_halfsib_families(exd, r.ints(s3), r.ints(1))))
+    assert len(hs) == len(firsts)
+    assert all(len(set(sim.export_group(int(g), genotypes=False)["ped1"].tolist())) == 1 for g in hs)
+    ev = r.int_result(VP(W.SXP_break_group_evenly(exd, r.ints(int(dh[0])), r.ints(4))))
+    assert sorted(sim.group_size(int(g)) for g in ev) == [15, 15, 15, 15]
     sim.close()
