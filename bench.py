@@ -212,37 +212,23 @@ def _timed(ext, fn, reps):
 
 
 def extra_config3(a, peak):
-    """configs[2] on ONE GPU: 1 M offspring from 10 000 parents (the pool, 125 MB, no longer fits L2) + GEBV"""
-    import torch
+    """configs[2] on ONE GPU: generations of 1 M offspring, top 1 % = 10 000 parents selected (the pool, 125 MB, no longer
+    fits L2 beside the offspring stream) — the same sharded step as the headline, world size 1"""
     from genomicsimulation_b200 import SimData, synthetic
-    from genomicsimulation_b200._lib import Draws
-    M, P, N = a.markers, 10000, 1000000
-    sim = SimData.from_dataset(synthetic.founders(200, M, a.chr, 150.0, seed=2))
-    E, ctx = sim.E, sim.ctx
-    chk = lambda st: (_ for _ in ()).throw(RuntimeError(E.gsb200_last_error().decode())) if st != 0 else None
-    chk(E.gsb200_store_reserve(ctx, 200 + P + N))
-    ext = torch.cuda.ExternalStream(E.gsb200_stream(ctx))
-    founders = np.arange(200, dtype=np.uint32)
-    dr = Draws(mode=0, seed=3, stream=0, first_unit=0)
-    chk(E.gsb200_cross_random_pairs(ctx, P, 1, founders.ctypes.data, 200, None, 0, 0, 0, None, 200, C.byref(dr), None, None))
-    g = torch.Generator(device="cuda").manual_seed(5)
-    p1 = torch.randint(0, P, (N,), device="cuda", generator=g, dtype=torch.int32)
-    p2 = (p1 + torch.randint(1, P, (N,), device="cuda", generator=g, dtype=torch.int32)) % P
-    p1 += 200; p2 += 200
-    out = torch.arange(200 + P, 200 + P + N, dtype=torch.int32, device="cuda")
-    bv = torch.empty(N, dtype=torch.float64, device="cuda")
-    torch.cuda.synchronize()
-    dr2 = Draws(mode=0, seed=3, stream=1, first_unit=0)
-    cross_ms = _timed(ext, lambda: chk(E.gsb200_cross_dev(ctx, N, p1.data_ptr(), p2.data_ptr(), 0, 0, out.data_ptr(), C.byref(dr2))), 3)
-    gebv_ms = _timed(ext, lambda: chk(E.gsb200_gebv_dev(ctx, N, out.data_ptr(), 0, bv.data_ptr())), 3)
-    chk(E.gsb200_cross_dev_status(ctx))
+    M, N, F = a.markers, 1000000, a.founders
+    sim = SimData.from_dataset(synthetic.founders(F, M, a.chr, 150.0, seed=2))
+    sim.use_native_draws(seed=77)
+    r = sharded_loop(sim, 0, 1, 0, N, F, 6, 3, 77, False)
     sim.close()
+    ph = r["phases"]
     row = 12544 * (M / 50000.0)
-    return {"workload": "1 000 000 random-cross offspring from 10 000 parents x %d SNPs on one GPU + GEBV (BASELINE.json configs[2], one GPU)" % M,
-            "regime": "pool > L2 (%.0f MB of parents against 126 MB)" % (P * row / 1e6),
-            "splice_ms": cross_ms, "splice_frac_of_hbm": N * (M / 2.0) / (cross_ms * 1e-3) / 1e9 / peak,
-            "gebv_ms": gebv_ms, "gebv_frac_of_hbm": N * (M / 4.0 + 8) / (gebv_ms * 1e-3) / 1e9 / peak,
-            "offspring_per_s": N / ((cross_ms + gebv_ms) * 1e-3)}
+    return {"workload": "1 000 000-offspring generations of recurrent selection on one GPU: GEBV of 1 M individuals x %d SNPs, top 1 %% = %d "
+                        "parents selected, 1 M random-cross offspring (BASELINE.json configs[2], one GPU)" % (M, r["top"]),
+            "regime": "pool > L2 (%.0f MB of parents against 126 MB; part of L2 set aside for it during the splice)" % (r["top"] * row / 1e6),
+            "ms_per_generation": r["ms_step"], "offspring_per_s": N / (r["ms_step"] * 1e-3), "phases_ms": ph,
+            "splice_ms": ph["pairs_and_splice_ms"], "splice_frac_of_hbm": N * (M / 2.0) / (ph["pairs_and_splice_ms"] * 1e-3) / 1e9 / peak,
+            "gebv_ms": ph["gebv_ms"], "gebv_frac_of_hbm": N * (M / 4.0 + 8) / (ph["gebv_ms"] * 1e-3) / 1e9 / peak,
+            "select_ms": ph["select_ms"]}
 
 
 def extra_config4(a, peak):

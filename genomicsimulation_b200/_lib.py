@@ -154,6 +154,8 @@ HOST_SYMBOLS = {
     "gsb_make_group_from": (UINT, [VP, UINT, VP]),
     "gsb_delete_group": (None, [VP, UINT]),
     "gsb_combine_groups": (UINT, [VP, UINT, VP]),
+    "gsb_calculate_min_recombinations": (C.c_int, [VP, UINT, UINT, UINT, UINT, UINT, UINT, C.c_int, C.c_int, VP]),
+    "gsb_calculate_recombinations_from_file": (C.c_int, [VP, C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
     "gsb_split_into_families": (UINT, [VP, UINT, UINT, VP]),
     "gsb_split_into_halfsib_families": (UINT, [VP, UINT, C.c_int, UINT, VP]),
     "gsb_split_into_individuals": (UINT, [VP, UINT, UINT, VP]),

@@ -113,7 +113,11 @@ int gsb200_create(gsb200_ctx** out, int device_ordinal, uint32_t n_markers) {
     ctx->dict_sym.assign((size_t) n_markers << ctx->planes, 0);
     ctx->dict_n.assign(n_markers, 0);
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) {
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->l2_persist_max = (size_t) prop.persistingL2CacheMaxSize;
+        ctx->l2_window_max = (size_t) prop.accessPolicyMaxWindowSize;
+    }
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));

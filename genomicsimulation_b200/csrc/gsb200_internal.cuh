@@ -167,6 +167,9 @@ struct gsb200_ctx {
         gsb200_draws draws;
     } pending_cross;
     int sm_count = gsb::kNumSMsB200;
+    size_t l2_persist_max = 0;      // cudaDeviceProp::persistingL2CacheMaxSize
+    size_t l2_window_max = 0;       // cudaDeviceProp::accessPolicyMaxWindowSize
+    size_t l2_persist_set = 0;      // what cudaLimitPersistingL2CacheSize was last set to by this context
     int* d_flag = nullptr;          // kernel-side error flag (capacity overflow in a splice plan)
 
     // symbol dictionary: code -> char, per marker. host master copy + device mirror.

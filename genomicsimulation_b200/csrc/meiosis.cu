@@ -1075,7 +1075,39 @@ int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_poo
         GSB_CUDA_TRY(cudaMemcpyAsync(h_picks, d_picks, (size_t) 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (picks_ready) GSB_CUDA_TRY(cudaEventRecord(picks_ready, ctx->stream));
     }
-    return cross_impl(ctx, n, d_p1, d_p2, map, map, d_out_rows ? d_out_rows : d_run, draws, false, what, nullptr, pool_base);
+    // A pool that no longer fits L2 beside the offspring stream (configs[2]: 10 000 parents = 125 MB) is re-read ~200 times
+    // per generation; left to LRU it is flushed by the 12.5 GB the same kernel writes.  Part of L2 is therefore set aside
+    // for the pool's lines for the duration of the splice (access-policy window on the stream: hits persist, everything
+    // else streams).  GSB200_L2_PERSIST=0 switches it off (measurements).
+    static const int persist_mode = [] { const char* v = getenv("GSB200_L2_PERSIST"); return v ? atoi(v) : 1; }();
+    const bool persist_on = persist_mode != 0;
+    const size_t pool_bytes = (size_t) n_pool * ctx->row_words() * sizeof(uint32_t);
+    bool window = false;
+    if (persist_on && pool_bytes > ((size_t) 48 << 20) && ctx->l2_persist_max > 0 && pool_bytes <= ctx->l2_window_max) {
+        const size_t want = persist_mode == 4 ? ctx->l2_persist_max / 2 : ctx->l2_persist_max;
+        if (ctx->l2_persist_set != want) {
+            GSB_CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+            ctx->l2_persist_set = want;
+            fprintf(stderr, "gsb200: persisting L2 set-aside %zu MB of max %zu MB, window max %zu MB\n", want >> 20, ctx->l2_persist_max >> 20, ctx->l2_window_max >> 20);
+        }
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof attr);
+        attr.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(pool_base);
+        attr.accessPolicyWindow.num_bytes = pool_bytes;
+        attr.accessPolicyWindow.hitRatio = (float) std::min(1.0, (persist_mode == 3 ? 0.45 : 0.9) * (double) ctx->l2_persist_max / (double) pool_bytes);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = persist_mode == 1 ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+        GSB_CUDA_TRY(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        window = true;
+    }
+    const int st = cross_impl(ctx, n, d_p1, d_p2, map, map, d_out_rows ? d_out_rows : d_run, draws, false, what, nullptr, pool_base);
+    if (window) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof attr);
+        attr.accessPolicyWindow.num_bytes = 0;
+        GSB_CUDA_TRY(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
+    return st;
 }
 
 }  // namespace gsb

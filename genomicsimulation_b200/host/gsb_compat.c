@@ -93,6 +93,10 @@ gsc_GroupNum gsc_split_by_bv(gsc_SimData* d, const gsc_GroupNum group, const gsc
     return (gsc_GroupNum){ .num = gsb_split_by_bv(d->engine, group.num, e.id, top_n, low) };
 }
 
+int gsc_calculate_recombinations_from_file(gsc_SimData* d, const char* input_file, const char* output_file, int window_len, int certain) {
+    return gsb_calculate_recombinations_from_file(d->engine, input_file, output_file, window_len, certain);
+}
+
 /* gsc_GroupNum is a struct of one unsigned (core.h:561-563): an array of them is an array of unsigned */
 _Static_assert(sizeof(gsc_GroupNum) == sizeof(unsigned), "gsc_GroupNum arrays are passed through as unsigned arrays");
 unsigned int gsc_split_into_families(gsc_SimData* d, const gsc_GroupNum g, unsigned int cap, gsc_GroupNum* results) {

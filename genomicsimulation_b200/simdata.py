@@ -370,6 +370,18 @@ class SimData:
         a = np.ascontiguousarray(groups, dtype=np.uint32)
         return self.L.gsb_combine_groups(self.d, len(a), _p(a))
 
+    # ---- find.crossovers (gsb_calculate_recombinations_from_file, core.c:7760-7818)
+    def find_crossovers(self, input_file, output_file, window=1, certain=True):
+        st = self.L.gsb_calculate_recombinations_from_file(self.d, str(input_file).encode(), str(output_file).encode(), int(window), int(bool(certain)))
+        self._check()
+        return st
+
+    def min_recombinations(self, parent1, p1num, parent2, p2num, offspring, window=1, certain=True, map_id=0):
+        out = np.zeros(self.M, dtype=np.int32)
+        self.L.gsb_calculate_min_recombinations(self.d, map_id, parent1, p1num, parent2, p2num, offspring, int(window), int(bool(certain)), _p(out))
+        self._check()
+        return out
+
     # ---- group-split utilities (gsb_split_*, core.c:2980-3784): each returns the list of new group numbers
     def _split(self, fn, group, cap, *args):
         out = np.zeros(max(cap, 1), dtype=np.uint32)

@@ -124,6 +124,7 @@ gsc_GroupNum gsc_make_clones(gsc_SimData* d, const gsc_GroupNum group, const _Bo
 gsc_GroupNum gsc_make_all_unidirectional_crosses(gsc_SimData* d, const gsc_GroupNum from_group, const gsc_MapID mapID, const gsc_GenOptions g);
 
 gsc_GroupNum gsc_split_by_bv(gsc_SimData* d, const gsc_GroupNum group, const gsc_EffectID effID, const GSC_GLOBALX_T top_n, const _Bool lowIsBest);
+int gsc_calculate_recombinations_from_file(gsc_SimData* d, const char* input_file, const char* output_file, int window_len, int certain);   /* core.h:1889 */
 /* group-split utilities, core.h:1469-1520 */
 unsigned int gsc_split_into_families(gsc_SimData* d, const gsc_GroupNum group_id, unsigned int maxentries_results, gsc_GroupNum* results);
 unsigned int gsc_split_into_halfsib_families(gsc_SimData* d, const gsc_GroupNum group_id, const int parent, unsigned int maxentries_results, gsc_GroupNum* results);
@@ -176,6 +177,7 @@ typedef gsc_MapID MapID;
 #define make_clones gsc_make_clones
 #define make_all_unidirectional_crosses gsc_make_all_unidirectional_crosses
 #define split_by_bv gsc_split_by_bv
+#define calculate_recombinations_from_file gsc_calculate_recombinations_from_file
 #define split_into_families gsc_split_into_families
 #define split_into_halfsib_families gsc_split_into_halfsib_families
 #define split_into_individuals gsc_split_into_individuals

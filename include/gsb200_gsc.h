@@ -139,6 +139,15 @@ gsb_GroupNum gsb_split_randomly_into_two(gsb_SimData* d, gsb_GroupNum group);   
 unsigned int gsb_split_randomly_into_n(gsb_SimData* d, gsb_GroupNum group, unsigned int n, gsb_GroupNum* results);                               /* core.c:3645-3667 */
 unsigned int gsb_split_by_probabilities(gsb_SimData* d, gsb_GroupNum group, unsigned int n, const double* probs, gsb_GroupNum* results);         /* core.c:3720-3763 */
 
+/* ---- find.crossovers (core.c:7534-7818, experimental upstream): which parent every marker of an
+ * offspring came from, judged marker by marker (window 1) or over a window; `origins` holds gsb_get_n_markers ints.
+ * The from-file form reads "offspring parent1 parent2" names per line and writes the reference's table. 0 = done. */
+int gsb_calculate_min_recombinations(gsb_SimData* d, gsb_MapID mapid, unsigned int parent1_index, unsigned int p1num,
+                                     unsigned int parent2_index, unsigned int p2num, unsigned int offspring_index,
+                                     int window_size, int certain, int* origins);                         /* core.c:7534, 7643 */
+int gsb_calculate_recombinations_from_file(gsb_SimData* d, const char* input_file, const char* output_file,
+                                           int window_len, int certain);                                   /* core.c:7760-7818 */
+
 /* ---- crossing (core.c:8483-9212); same argument order as the reference */
 gsb_GroupNum gsb_make_random_crosses(gsb_SimData* d, gsb_GroupNum from_group, unsigned int n_crosses,
                                      unsigned int cap, gsb_MapID which_map, gsb_GenOptions g);

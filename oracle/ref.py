@@ -355,6 +355,9 @@ class RefSim:
     def split_by_bv(self, group, eff_id, top_n, low_is_best=False):
         return self.L.refb_split_by_bv(self.d, group, eff_id, top_n, int(low_is_best))
 
+    def find_crossovers(self, input_file, output_file, window=1, certain=True):
+        return self.L.refb_recombinations_from_file(self.d, str(input_file).encode(), str(output_file).encode(), int(window), int(bool(certain)))
+
     def split(self, kind, group, n=0, counts=None, probs=None):
         """the reference's group-split utilities (refb_split in ref_bridge.c lists the kinds); returns the new group numbers"""
         cap = max(self.group_size(group), n, 1)

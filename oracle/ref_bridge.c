@@ -297,6 +297,9 @@ EXPORT unsigned refb_split_by_bv(void* d, unsigned group, unsigned eff_id, unsig
     return gsc_split_by_bv((gsc_SimData*) d, (gsc_GroupNum){.num = group}, (gsc_EffectID){.id = eff_id},
                            top_n, low_is_best != 0).num;
 }
+EXPORT int refb_recombinations_from_file(void* d, const char* input_file, const char* output_file, int window_len, int certain) {
+    return gsc_calculate_recombinations_from_file((gsc_SimData*) d, input_file, output_file, window_len, certain);
+}
 /* group-split utilities of the reference (core.c:2980-3784); kind: 0 families, 1 / 2 half-sibs on parent 1 / 2, 3 individuals,
  * 4 evenly into two, 5 evenly into n, 6 buckets (counts), 7 randomly into two, 8 randomly into n, 9 by probabilities */
 EXPORT unsigned refb_split(void* dv, int kind, unsigned group, unsigned n, const unsigned* counts, const double* probs, unsigned cap, unsigned* out) {

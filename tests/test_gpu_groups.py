@@ -87,3 +87,41 @@ def test_allocation_splits_match_the_reference(tmp_path):
     run_both(r, s, 9, 1, lambda: s.split_by_probabilities(1, [0.3]), n=2, probs=[0.3])
     assert s.split_evenly_into_n(1, 1) == [] and s.split_evenly_into_two(999) == 0
     r.close(); s.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("window,certain", [(1, True), (1, False), (3, True), (5, False)])
+def test_find_crossovers_file_matches_the_reference(tmp_path, window, certain):
+    """gsc_calculate_recombinations_from_file (core.c:7760-7818; find.crossovers): the table the
+    reference writes for named (offspring, parent 1, parent 2) triples, byte for byte — its chromosome-local indexing
+    and the `previous` that carries over between chromosomes included."""
+    ds = datasets.synthetic(8, 240, 3, 100.0, seed=5, spacing="random")
+    gf, mf, ef = datasets.write_files(ds, str(tmp_path))
+    r = ref.RefSim()
+    ref.set_print_mode(0)
+    g, m, e = r.load(gf, mf, ef)
+    p1 = np.array([0, 2, 4, 1], dtype=np.uint32)
+    p2 = np.array([1, 3, 5, 6], dtype=np.uint32)
+    ref.seed(3)
+    ref.record_start()
+    f1 = r.make_targeted_crosses(p1, p2, m, m, family_size=2, name_offspring=True, name_prefix="x")
+    tape = ref.record_stop().draws_only()
+    s = engine_from(datasets.from_ref(r, g))
+    with port.Replay(tape) as rp:
+        h1 = s.make_targeted_crosses(p1, p2, 1, 1, family_size=2, name_offspring=True, name_prefix="x")
+    assert not rp.error and rp.consumed == len(tape) and f1 == h1
+    kids, founders = r.group_names(f1), r.group_names(g)
+    assert kids == s.group_names(h1) and len(kids) == 8
+    plan = tmp_path / "triples.txt"
+    lines = ["%s\t%s\t%s" % (kids[k], founders[int(p1[k // 2])], founders[int(p2[k // 2])]) for k in range(8)]
+    lines.insert(3, "nobody\t%s\t%s" % (founders[0], founders[1]))            # a name that does not exist: skipped with a NOTE
+    plan.write_text("\n".join(lines) + "\n")
+    want, got = tmp_path / "want.txt", tmp_path / "got.txt"
+    assert r.find_crossovers(plan, want, window, certain) == 0
+    assert s.find_crossovers(plan, got, window, certain) == 0
+    a, b = want.read_bytes(), got.read_bytes()
+    assert a == b and a.count(b"\n") == 10 and len(a) > 3000
+    # the array form, for one triple
+    o = s.min_recombinations(int(p1[0]), 101, int(p2[0]), 202, s.group_indexes(h1)[0], window, certain)
+    assert set(np.unique(o).tolist()) <= {0, 101, 202} and (o != 0).any()
+    r.close(); s.close()
