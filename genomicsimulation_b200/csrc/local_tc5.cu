@@ -51,12 +51,12 @@ namespace gsb {
 namespace {
 
 constexpr uint32_t kEpiWarps = 8;                // two per TMEM lane quarter: even / odd effect sets
-constexpr uint32_t kWarpIssuer = 4 + kEpiWarps, kWarpALoader = kWarpIssuer + 1, kWarpBLoader = kWarpIssuer + 2;
-constexpr uint32_t kThreads = (kWarpBLoader + 1) * 32;           // 4 expander + 8 epilogue warps, issuer, A loader, B loader
-constexpr uint32_t kALines = 3;                  // ring of 128-byte lines (32 marker words x 128 strand rows) in shared memory
+constexpr uint32_t kWarpIssuer = 4 + kEpiWarps, kWarpALoader = kWarpIssuer + 2, kWarpBLoader = kWarpIssuer + 3;      // two issuer warps, alternating units
+constexpr uint32_t kThreads = (kWarpBLoader + 1) * 32;           // 4 expander + 8 epilogue warps, 2 issuers, A loader, B loader
+constexpr uint32_t kALines = 2;                  // ring of 128-byte lines (32 marker words x 128 strand rows) in shared memory
 constexpr uint32_t kARowBytes = 144;             // 128 + 16: the expanders' 16-byte reads of 8 different rows hit different banks
 constexpr uint32_t kALineBytes = 128 * kARowBytes;
-constexpr uint32_t kUnitWords = 16, kUnitSteps = 20;
+constexpr uint32_t kUnitWords = 16, kUnitSteps = 17;      // 17: three B stages of ten effect sets fit beside the rest
 constexpr uint32_t kStageCols = 8 * kUnitWords;  // an operand stage in TMEM: 16 words x 8 columns
 constexpr uint32_t kACol0 = 256;                 // two operand stages: columns 256..511
 constexpr uint32_t kSlots = 3, kSlotCols = 80;   // three accumulators: columns 0..239
@@ -69,6 +69,7 @@ constexpr uint32_t kSmemBudget = 227 * 1024 - 2048;
 // segment record (consecutive words of one block within a unit): first word within the half line (4 bits) | steps << 4 |
 // 512 the block starts here | 1024 the block ends here
 constexpr uint32_t kSegFirst = 512u, kSegLast = 1024u;
+static_assert(kUnitSteps <= 20, "the MMA chain of the issuer is written out for up to 20 steps");
 static_assert(kLocalTc5MaxSets * 8 <= kSlotCols, "an accumulator holds 8 columns per effect set");
 
 struct Tc5Range {          // the whole blocks [blk_lo, blk_hi) = runs [run_lo, run_hi) of non-empty blocks
@@ -80,7 +81,7 @@ struct Tc5Range {          // the whole blocks [blk_lo, blk_hi) = runs [run_lo, 
 struct Tc5Unit {
     uint32_t b_off16, b_bytes;  // the unit in the B stream (offset in 16-byte units): head + n_steps x 256 x sets
     uint32_t line_adv_half;     // lines to advance before the unit << 1 | which half of the line
-    uint32_t pad;
+    uint32_t n_ends;            // blocks that end inside the unit
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -98,19 +99,18 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     return leader != 0;
 }
-// the kind::i8 MMA of tc5_common.cuh under a predicate of its own, without the optional lane mask; the B descriptor in
-// halves (only the low one, which holds the start address, changes from step to step)
-__device__ __forceinline__ void umma_i8_ts_if(uint32_t tmem_d, uint32_t tmem_a, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+// the kind::i8 MMA of tc5_common.cuh without the optional lane mask and with the B descriptor in halves (only the low
+// one, which holds the start address, changes from step to step)
+__device__ __forceinline__ void umma_i8_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p, q;\n\t"
+        ".reg .pred p;\n\t"
         ".reg .b64 d;\n\t"
         "setp.ne.b32 p, %5, 0;\n\t"
-        "setp.ne.b32 q, %6, 0;\n\t"
         "mov.b64 d, {%2, %3};\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], d, %4, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], d, %4, p;\n\t"
         "}\n"
-        :: "r"(tmem_d), "r"(tmem_a), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+        :: "r"(tmem_d), "r"(tmem_a), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const uint32_t* gmem_src) {
     asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" :: "r"(smem_dst), "l"(gmem_src) : "memory");
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
         uint32_t dbg /* GSB200_LOCAL_DEBUG bits, measurements only: 1 no operand stores, 2 no mma, 4 no epilogue work, 8 no row loads, 16 no B digits (heads only) */,
         long long* __restrict__ prof /* GSB200_LOCAL_PROF: CTA 0's cycles per role spent in each kind of wait, or null */) {
     extern __shared__ __align__(128) uint8_t s_dyn[];               // A lines | output staging | B stages
-    __shared__ __align__(8) uint64_t s_afull[kALines], s_afree[kALines], s_tfull[2], s_udone[kMaxBStages];
+    __shared__ __align__(8) uint64_t s_afull[kALines], s_afree[kALines], s_tfull[2], s_issued[2], s_udone[kMaxBStages];
     __shared__ __align__(8) uint64_t s_bfull[kMaxBStages], s_dready[kSlots], s_dfree[kSlots];
     __shared__ const uint32_t* s_rowptr[128];
     __shared__ uint32_t s_tmem;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (uint32_t i = 0; i < kALines; ++i) { mbar_init(&s_afull[i], 32); mbar_init(&s_afree[i], 4); }
-        for (uint32_t i = 0; i < 2; ++i) mbar_init(&s_tfull[i], 4);
+        for (uint32_t i = 0; i < 2; ++i) { mbar_init(&s_tfull[i], 4); mbar_init(&s_issued[i], 1); }
         for (uint32_t i = 0; i < kMaxBStages; ++i) { mbar_init(&s_bfull[i], 1); mbar_init(&s_udone[i], 1); }
         for (uint32_t i = 0; i < kSlots; ++i) { mbar_init(&s_dready[i], 1); mbar_init(&s_dfree[i], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t bar_afull = smem_u32(s_afull), bar_afree = smem_u32(s_afree), bar_tfull = smem_u32(s_tfull), bar_udone = smem_u32(s_udone);
+    const uint32_t bar_afull = smem_u32(s_afull), bar_afree = smem_u32(s_afree), bar_tfull = smem_u32(s_tfull), bar_udone = smem_u32(s_udone), bar_issued = smem_u32(s_issued);
     const uint32_t bar_bfull = smem_u32(s_bfull), bar_dready = smem_u32(s_dready), bar_dfree = smem_u32(s_dfree);
     const uint32_t step_bytes = 256 * n_sets, stage_bytes = kUnitHead + kUnitSteps * step_bytes + kStageSlack;
     const uint32_t a_smem = smem_u32(s_dyn);
@@ -389,77 +389,101 @@ __global__ void __launch_bounds__(kThreads, 1) local_tc5_kernel(
             empty_until(rg.blk_hi);
         }
         if (warp == 4) prof_out(1);
-    } else if (warp == kWarpIssuer) {
-        // ---------------- issuer: the whole warp walks the records CONVERGED and one elected lane issues.  From a
-        // lone thread inside `if (lane == 0)` every tcgen05.mma / commit is wrapped in a waterfall loop (ELECT,
-        // R2UR.BROADCAST, BRA.U.ANY): 47 cycles per MMA and ~300 per commit whatever N; converged + elect.sync the
-        // MMA issues in 17 cycles and N = 80 runs at its 40-cycle floor (profiles/r2_umma_i8_probe2.txt).
+    } else if (warp == kWarpIssuer || warp == kWarpIssuer + 1) {
+        // ---------------- issuers: TWO warps take the units in turn.  Each walks its unit's records CONVERGED and one elected
+        // lane issues: from a lone thread inside `if (lane == 0)` every tcgen05.mma / commit is wrapped in a waterfall loop
+        // (ELECT, R2UR.BROADCAST, BRA.U.ANY) — 47 cycles per MMA and ~300 per commit whatever N; converged + elect.sync the MMA
+        // issues in 17 cycles and N = 80 runs at its 40-cycle floor (profiles/r2_umma_i8_probe2.txt).  Why two: the pipe
+        // accepts the next MMA only when the one before is nearly done, so a unit's MMAs hold their warp ~50 cycles each, and
+        // what that warp does per unit besides (waits for B and the operand stage, records, commits: ~1 100 cycles) left the
+        // pipe idle for longer than the MMAs ran.  Now one warp prepares unit u + 1 while the other issues unit u; a
+        // barrier hands the pipe over so that the units' MMAs are issued in order (a block's first MMA, which overwrites the
+        // accumulator, must precede the rest; completion is in issue order, so a block's commit by one warp covers the
+        // other's earlier MMAs too).
+        const uint32_t me = warp - kWarpIssuer;
         uint32_t q_unit = 0, ring_i = 0, b_stage = 0, b_par = 0;
-        uint32_t q_blk = 0, slot = 0, slot_par = 0;       // slot = q_blk % kSlots, slot_par = (q_blk / kSlots) & 1
+        uint32_t q_blk = 0, slot = 0, slot_par = 0;       // blocks ended so far; slot = q_blk % kSlots, slot_par = (q_blk / kSlots) & 1
         // (addresses that came out of shared memory or a cvta, re-declared warp-uniform for the compiler)
         const uint32_t u_tmem = __shfl_sync(0xffffffffu, tmem, 0), u_b_smem = __shfl_sync(0xffffffffu, b_smem, 0);
-        uint32_t d_addr = u_tmem;
         const uint32_t d_hi = (uint32_t) (b_descriptor(0) >> 32);
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const Tc5Range rg = range_of(item);
+            // how many blocks end in a unit this warp skips: from the head of its own unit before (the last word); for an item
+            // that starts with the other warp's unit, from the unit table (one exposed L2 round trip per item)
+            uint32_t n_ends = ((q_unit & 1u) != me) ? __ldg(&units[rg.unit_lo].n_ends) : 0u;
 #pragma unroll 1
             for (uint32_t u = 0; u < rg.n_units; ++u, ++q_unit) {
-                wait_on(bar_bfull + 8 * b_stage, b_par, 0);
-                const uint32_t b_addr = u_b_smem + b_stage * stage_bytes;
-                // (records go through a shuffle from lane 0: it tells the compiler they are warp-uniform, and the MMA operands
-                // derived from them then live in uniform registers instead of being moved there one by one)
-                const uint32_t n_seg = __shfl_sync(0xffffffffu, lds32(b_addr), 0);
-                uint32_t d_lo = (uint32_t) b_descriptor(b_addr + kUnitHead);      // the half with the start address
-                uint32_t seg = __shfl_sync(0xffffffffu, lds32(b_addr + 4), 0);
-                wait_on(bar_tfull + 8 * (q_unit & 1), (q_unit >> 1) & 1, 1);
-                tc_fence_after();
-                const uint32_t a_base = u_tmem + kACol0 + kStageCols * (q_unit & 1);
-                const long long tl = clock64();
-                // a segment = consecutive words of one block: its MMAs are issued four at a time from one elected lane
-                // with nothing but uniform adds between them — a lone warp pays ~15 cycles per branch, so per-STEP
-                // control flow (the first version of this loop) cost 200 cycles per step
+                if ((q_unit & 1u) != me) {
+                    // the other warp's unit: only the accumulator rotation moves on
+                    q_blk += n_ends;
+                    slot += n_ends % kSlots;
+                    slot_par ^= (n_ends / kSlots) & 1u;
+                    if (slot >= kSlots) { slot -= kSlots; slot_par ^= 1; }
+                } else {
+                    wait_on(bar_bfull + 8 * b_stage, b_par, 0);
+                    const uint32_t b_addr = u_b_smem + b_stage * stage_bytes;
+                    // (records go through a shuffle from lane 0: it tells the compiler they are warp-uniform, and the MMA operands
+                    // derived from them then live in uniform registers instead of being moved there one by one)
+                    const uint32_t n_seg = __shfl_sync(0xffffffffu, lds32(b_addr), 0);
+                    uint32_t d_lo = (uint32_t) b_descriptor(b_addr + kUnitHead);      // the half with the start address
+                    uint32_t seg = __shfl_sync(0xffffffffu, lds32(b_addr + 4), 0);
+                    n_ends = __shfl_sync(0xffffffffu, lds32(b_addr + kUnitHead - 4), 0);       // of the NEXT unit, which this warp skips
+                    wait_on(bar_tfull + 8 * (q_unit & 1), (q_unit >> 1) & 1, 1);
+                    tc_fence_after();
+                    const uint32_t a_base = u_tmem + kACol0 + kStageCols * (q_unit & 1);
+                    uint32_t d_addr = u_tmem + kSlotCols * slot;       // a block that continues from the unit before
+                    // the pipe is mine once the other warp has issued the unit before
+                    if (q_unit > 0) wait_on(bar_issued + 8 * ((q_unit - 1) & 1), ((q_unit - 1) >> 1) & 1, 2);
+                    // a segment = consecutive words of one block, issued as one straight-line burst: a lone warp pays ~15 cycles
+                    // per branch, so per-STEP control flow (the first version of this loop) cost 200 cycles per step
 #pragma unroll 1
-                for (uint32_t sg = 0; sg < n_seg; ++sg) {
-                    const uint32_t seg_next = __shfl_sync(0xffffffffu, lds32(b_addr + 8 + 4 * sg), 0);
-                    const uint32_t cnt = (seg >> 4) & 31u;
-                    uint32_t acc = 1;
-                    if (seg & kSegFirst) {
-                        if (q_blk >= kSlots) {                       // the epilogue has read this accumulator's previous sums
-                            wait_on(bar_dfree + 8 * slot, slot_par ^ 1, 2);
-                            tc_fence_after();
+                    for (uint32_t sg = 0; sg < n_seg; ++sg) {
+                        const uint32_t seg_next = __shfl_sync(0xffffffffu, lds32(b_addr + 8 + 4 * sg), 0);
+                        const uint32_t cnt = (seg >> 4) & 31u;
+                        uint32_t acc = 1;
+                        if (seg & kSegFirst) {
+                            if (q_blk >= kSlots) {                       // the epilogue has read this accumulator's previous sums
+                                wait_on(bar_dfree + 8 * slot, slot_par ^ 1, 2);
+                                tc_fence_after();
+                            }
+                            d_addr = u_tmem + kSlotCols * slot;
+                            acc = 0;
                         }
-                        d_addr = u_tmem + kSlotCols * slot;
-                        acc = 0;
-                    }
-                    const uint32_t a_addr = a_base + 8 * (seg & 15u);
-                    if (!(dbg & 2u) && elect_one()) {
-                        // straight-line: up to kUnitSteps predicated MMAs.  The tensor pipe takes the next MMA only when it has little
-                        // else queued, so what the issuing warp executes between two MMAs is added to the 40 cycles the MMA takes
-                        const uint32_t sd = step_bytes >> 4;          // the descriptor's start-address field counts 16-byte units
-#pragma unroll
-                        for (uint32_t k = 0; k < kUnitSteps; ++k)
-                            umma_i8_ts_if(d_addr, a_addr + 8 * k, d_lo + k * sd, d_hi, idesc, k == 0 ? acc : 1u, k < cnt);
-                    }
-                    __syncwarp();
-                    d_lo += cnt * (step_bytes >> 4);
-                    if (seg & kSegLast) {
-                        if (elect_one()) tc_commit(bar_dready + 8 * slot);
+                        const uint32_t a_addr = a_base + 8 * (seg & 15u);
+                        if (!(dbg & 2u) && elect_one()) {
+                            // Straight-line, no predicates: the first MMA of the segment, then a jump into a descending chain of
+                            // the remaining cnt - 1 (their order does not matter: they all accumulate)
+                            const uint32_t sd = step_bytes >> 4;          // the descriptor's start-address field counts 16-byte units
+                            umma_i8_ts_lohi(d_addr, a_addr, d_lo, d_hi, idesc, acc);
+                            uint32_t a = a_addr + 8 * (cnt - 1), dl = d_lo + (cnt - 1) * sd;
+#define GSB_TC5_STEP(K) case K: umma_i8_ts_lohi(d_addr, a, dl, d_hi, idesc, 1u); a -= 8; dl -= sd;
+                            switch (cnt - 1) {
+                                GSB_TC5_STEP(19) GSB_TC5_STEP(18) GSB_TC5_STEP(17) GSB_TC5_STEP(16) GSB_TC5_STEP(15) GSB_TC5_STEP(14) GSB_TC5_STEP(13)
+                                GSB_TC5_STEP(12) GSB_TC5_STEP(11) GSB_TC5_STEP(10) GSB_TC5_STEP(9) GSB_TC5_STEP(8) GSB_TC5_STEP(7) GSB_TC5_STEP(6)
+                                GSB_TC5_STEP(5) GSB_TC5_STEP(4) GSB_TC5_STEP(3) GSB_TC5_STEP(2) GSB_TC5_STEP(1)
+                                default: break;
+                            }
+#undef GSB_TC5_STEP
+                        }
                         __syncwarp();
-                        ++q_blk;
-                        if (++slot == kSlots) { slot = 0; slot_par ^= 1; }
+                        d_lo += cnt * (step_bytes >> 4);
+                        if (seg & kSegLast) {
+                            if (elect_one()) tc_commit(bar_dready + 8 * slot);
+                            __syncwarp();
+                            ++q_blk;
+                            if (++slot == kSlots) { slot = 0; slot_par ^= 1; }
+                        }
+                        seg = seg_next;
                     }
-                    seg = seg_next;
+                    if (lane == 0) mbar_arrive(bar_issued + 8 * (q_unit & 1));       // the pipe is the other warp's
+                    if (elect_one()) tc_commit(bar_udone + 8 * ring_i);
+                    __syncwarp();
                 }
-                if (profiling && (dbg & 32u)) p_wait[1] += clock64() - tl;
-                { const long long tq = clock64();
-                if (elect_one()) tc_commit(bar_udone + 8 * ring_i);
-                __syncwarp();
-                if (profiling && (dbg & 32u)) p_wait[2] += clock64() - tq; }
                 if (++ring_i == n_ring) ring_i = 0;
                 if (++b_stage == n_bstages) { b_stage = 0; b_par ^= 1; }
             }
         }
-        prof_out(2);
+        if (me == 0) prof_out(2);
     } else if (warp == kWarpALoader) {
         // ---------------- A loader: lanes 8k .. 8k + 7 copy one 128-byte line of one strand row
         uint32_t q_line = 0;
@@ -592,7 +616,7 @@ int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32
             u.b_off16 = (uint32_t) b_off16;
             u.b_bytes = kUnitHead + (e - s) * step_bytes;
             u.line_adv_half = (((half >> 1) - line_at) << 1) | (half & 1u);
-            u.pad = 0;
+            u.n_ends = 0;
             line_at = half >> 1;
             b_off16 += u.b_bytes / 16;
             GSB_REQUIRE(b_off16 < (1ull << 32), GSB200_ERR_ARG, "local GEBV (tcgen05 path): B stream too long");
@@ -608,12 +632,14 @@ int local_tc5_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32
                 const bool first = p == s_lo || (steps[p - 1].y & 0x7fffffffu) != blk;
                 const bool last = r == s_hi || (steps[r].y & 0x7fffffffu) != blk;
                 heads[h0 + 1 + n_seg++] = (steps[p].x % kUnitWords) | ((r - p) << 4) | (first ? kSegFirst : 0u) | (last ? kSegLast : 0u);
+                units.back().n_ends += last;
                 p = r;
             }
             heads[h0] = n_seg;
             s = e;
         }
         g.n_units = (uint32_t) units.size() - g.unit_lo;
+        for (uint32_t q = g.unit_lo; q + 1 < (uint32_t) units.size(); ++q) heads[(size_t) q * (kUnitHead / 4) + kUnitHead / 4 - 1] = units[q + 1].n_ends;
     }
     unit_step.push_back(n_steps);
     const uint32_t n_units = (uint32_t) units.size();

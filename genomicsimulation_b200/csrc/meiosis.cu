@@ -1078,8 +1078,10 @@ int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_poo
     // A pool that no longer fits L2 beside the offspring stream (configs[2]: 10 000 parents = 125 MB) is re-read ~200 times
     // per generation; left to LRU it is flushed by the 12.5 GB the same kernel writes.  Part of L2 is therefore set aside
     // for the pool's lines for the duration of the splice (access-policy window on the stream: hits persist, everything
-    // else streams).  GSB200_L2_PERSIST=0 switches it off (measurements).
-    static const int persist_mode = [] { const char* v = getenv("GSB200_L2_PERSIST"); return v ? atoi(v) : 1; }();
+    // else streams).  MEASURED AND LEFT OFF: with the 79 MB set-aside the splice of 1 M offspring from 10 000 parents takes 12.4 ms
+    // instead of 4.65 (misses streaming), 10.2 ms (misses normal), 4.66 ms with half the set-aside — the 12.5 GB write stream needs
+    // the L2 more than the pool does.  GSB200_L2_PERSIST=1..4 switches the variants on again (profiles/scripts/config3_ab.py).
+    static const int persist_mode = [] { const char* v = getenv("GSB200_L2_PERSIST"); return v ? atoi(v) : 0; }();
     const bool persist_on = persist_mode != 0;
     const size_t pool_bytes = (size_t) n_pool * ctx->row_words() * sizeof(uint32_t);
     bool window = false;

@@ -120,7 +120,7 @@ def test_find_crossovers_file_matches_the_reference(tmp_path, window, certain):
     assert r.find_crossovers(plan, want, window, certain) == 0
     assert s.find_crossovers(plan, got, window, certain) == 0
     a, b = want.read_bytes(), got.read_bytes()
-    assert a == b and a.count(b"\n") == 10 and len(a) > 3000
+    assert a == b and a.count(b"\n") == 9 and len(a) > 3000
     # the array form, for one triple
     o = s.min_recombinations(int(p1[0]), 101, int(p2[0]), 202, s.group_indexes(h1)[0], window, certain)
     assert set(np.unique(o).tolist()) <= {0, 101, 202} and (o != 0).any()
