@@ -224,7 +224,7 @@ def extra_config3(a, peak):
     row = 12544 * (M / 50000.0)
     return {"workload": "1 000 000-offspring generations of recurrent selection on one GPU: GEBV of 1 M individuals x %d SNPs, top 1 %% = %d "
                         "parents selected, 1 M random-cross offspring (BASELINE.json configs[2], one GPU)" % (M, r["top"]),
-            "regime": "pool > L2 (%.0f MB of parents against 126 MB; part of L2 set aside for it during the splice)" % (r["top"] * row / 1e6),
+            "regime": "pool > L2 (%.0f MB of parents against 126 MB: they are re-read from DRAM)" % (r["top"] * row / 1e6),
             "ms_per_generation": r["ms_step"], "offspring_per_s": N / (r["ms_step"] * 1e-3), "phases_ms": ph,
             "splice_ms": ph["pairs_and_splice_ms"], "splice_frac_of_hbm": N * (M / 2.0) / (ph["pairs_and_splice_ms"] * 1e-3) / 1e9 / peak,
             "gebv_ms": ph["gebv_ms"], "gebv_frac_of_hbm": N * (M / 4.0 + 8) / (ph["gebv_ms"] * 1e-3) / 1e9 / peak,
