@@ -91,6 +91,7 @@ struct MeiosisArgs {
     const uint32_t* bv_slot;   // row -> slot
     const long long* bv_q;     // [plane_words * 32]: fixed-point delta per marker
     unsigned long long* bv_acc;// per unit: sum over its gametes, two's complement
+    const uint32_t* order;     // fast kernel: the gametes in processing order (null: as numbered); see pool_random_cross
 };
 
 // ------------------------------------------------------------------ native draw stream
@@ -247,7 +248,8 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
     uint32_t* piece_multi = piece_seen + a.parity_words;
 
     const uint32_t n_gametes = a.n_units * a.gametes_per_unit;      // host keeps this below 2^32
-    for (uint32_t g = blockIdx.x * warps + warp; g < n_gametes; g += gridDim.x * warps) {
+    for (uint32_t gi = blockIdx.x * warps + warp; gi < n_gametes; gi += gridDim.x * warps) {
+        const uint32_t g = a.order ? a.order[gi] : gi;           // gametes sorted by parent: neighbouring warps share their source rows
         const uint32_t unit_local = a.gametes_per_unit == 2 ? g >> 1 : g;
         const uint32_t gam = a.gametes_per_unit == 2 ? g & 1u : 0u;
         const uint64_t unit = a.draws.first_unit + unit_local;
@@ -816,6 +818,7 @@ struct Batch {
     const long long* bv_tab = nullptr; const uint32_t* bv_slot = nullptr; const long long* bv_q = nullptr;
     unsigned long long* bv_acc = nullptr;
     uint32_t bv_shift = 5;
+    const uint32_t* d_order = nullptr;   // gametes in processing order, or null
 };
 
 // Philox draws materialised in tape layout on the device (s_plan[4..7]).
@@ -897,6 +900,7 @@ int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
     a.draws = b.draws;
     a.flag = ctx->d_flag;
     a.bv_tab = b.bv_tab; a.bv_slot = b.bv_slot; a.bv_q = b.bv_q; a.bv_acc = b.bv_acc; a.bv_shift = b.bv_shift;
+    a.order = b.d_order;
 
     const DeviceMap* maps[2] = { b.map0, b.gametes_per_unit > 1 ? b.map1 : b.map0 };
     if (b.draws.mode == GSB200_DRAWS_PHILOX) {
@@ -1021,9 +1025,19 @@ int make_draw_view(const gsb200_draws* d, DrawView* v, const char* what) {
 
 struct FusedBv { const long long* tab; const uint32_t* slot; const long long* q; unsigned long long* acc; uint32_t shift; };
 
+// key = the row a gamete is made from, value = the gamete (2 * offspring + which parent)
+__global__ void gamete_keys_kernel(uint32_t n_gametes, const uint32_t* __restrict__ p1, const uint32_t* __restrict__ p2,
+                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_gametes) return;
+    keys[g] = (g & 1u) ? p2[g >> 1] : p1[g >> 1];
+    vals[g] = g;
+}
+
 int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t* d_p2, uint32_t map1, uint32_t map2,
                const uint32_t* d_out, const gsb200_draws* draws, bool may_sync, const char* what, const FusedBv* bv = nullptr,
-               const uint32_t* src_base = nullptr /* rows the parents are read from; null: the store */) {
+               const uint32_t* src_base = nullptr /* rows the parents are read from; null: the store */,
+               const uint32_t* d_order = nullptr /* gametes (2 * offspring + which) in processing order; null: as numbered */) {
     const DeviceMap *m1, *m2;
     GSB_TRY(get_map(ctx, map1, &m1, what));
     GSB_TRY(get_map(ctx, map2, &m2, what));
@@ -1034,6 +1048,7 @@ int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t
     b.src_base = src_base ? src_base : ctx->d_store; b.d_src0 = d_p1; b.d_src1 = d_p2; b.dst_base = ctx->d_store; b.d_dst = d_out;
     b.map0 = m1; b.map1 = m2; b.gametes_per_unit = 2; b.doubled = 0; b.tape_xcap = 0;
     if (bv) { b.bv_tab = bv->tab; b.bv_slot = bv->slot; b.bv_q = bv->q; b.bv_acc = bv->acc; b.bv_shift = bv->shift; }
+    b.d_order = d_order;
     GSB_TRY(make_draw_view(draws, &b.draws, what));
     if (draws->mode == GSB200_DRAWS_TAPE) {
         GSB_REQUIRE(may_sync, GSB200_ERR_ARG, "%s: device-pointer entry points take PHILOX draws only", what);
@@ -1102,7 +1117,36 @@ int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_poo
         GSB_CUDA_TRY(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
         window = true;
     }
-    const int st = cross_impl(ctx, n, d_p1, d_p2, map, map, d_out_rows ? d_out_rows : d_run, draws, false, what, nullptr, pool_base);
+    // A pool that does not stay in L2 beside the offspring stream: the gametes are processed sorted by parent, so that the
+    // ~2n / n_pool gametes of a parent are spliced by neighbouring warps at the same time and its row comes from DRAM once
+    // instead of once per gamete (configs[2]: 10 000 parents = 125 MB, 200 gametes each: read traffic 12.5 GB -> 0.13 GB per
+    // million offspring).  The draws are keyed by the global offspring number, so the order changes nothing in the result
+    // (tests/test_gpu_sharding.py).  Measured, 50 k SNPs (profiles/r2_sorted_gametes.txt): 100 MB pool 3.69 -> 3.00 ms per 800 k
+    // offspring (0.83 -> 1.02 of the HBM peak on the algorithmic bytes), 50 MB 1.64 -> 1.51 ms per 400 k, 25 MB 0.80 -> 0.78 ms
+    // per 200 k; the 12.5 MB pool of the headline step sits in L2 anyway and would only pay the sort's ~27 us: threshold 24 MB.
+    const uint32_t* d_order = nullptr;
+    // GSB200_SORT_GAMETES_MIN_MB (read at every call: tests switch it): pools from this many MB on are sorted, default 24
+    const char* min_mb_env = getenv("GSB200_SORT_GAMETES_MIN_MB");
+    const size_t min_mb = min_mb_env ? (size_t) atol(min_mb_env) : 24;
+    if (pool_bytes >= (min_mb << 20) && n >= 4 * (size_t) n_pool) {
+        const uint32_t n_g = 2 * n;
+        int bits = 1;
+        while ((1u << bits) < n_pool) ++bits;
+        size_t temp_bytes = 0;
+        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*) nullptr, (uint32_t*) nullptr,
+                                                     (const uint32_t*) nullptr, (uint32_t*) nullptr, (int) n_g, 0, bits, ctx->stream));
+        const size_t arr = ((size_t) n_g * sizeof(uint32_t) + 255) & ~(size_t) 255;
+        GSB_TRY(ctx->s_plan[0].ensure(4 * arr + temp_bytes));
+        uint32_t* k_in = (uint32_t*) ctx->s_plan[0].ptr;
+        uint32_t* k_out = (uint32_t*) ((char*) k_in + arr);
+        uint32_t* v_in = (uint32_t*) ((char*) k_in + 2 * arr);
+        uint32_t* v_out = (uint32_t*) ((char*) k_in + 3 * arr);
+        gamete_keys_kernel<<<grid_for(n_g, 256), 256, 0, ctx->stream>>>(n_g, d_p1, d_p2, k_in, v_in);
+        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs((char*) k_in + 4 * arr, temp_bytes, k_in, k_out, v_in, v_out, (int) n_g, 0, bits, ctx->stream));
+        ctx->launches += 3;
+        d_order = v_out;
+    }
+    const int st = cross_impl(ctx, n, d_p1, d_p2, map, map, d_out_rows ? d_out_rows : d_run, draws, false, what, nullptr, pool_base, d_order);
     if (window) {
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof attr);

@@ -127,6 +127,29 @@ def test_shards_in_one_process_reproduce_one_shard():
     same_history(engine_level(3), single)
 
 
+@pytest.mark.timeout(300)
+def test_gametes_sorted_by_parent_change_nothing():
+    """Pools that do not stay in L2 are spliced with the gametes sorted by parent (pool_random_cross, csrc/meiosis.cu);
+    the draws are keyed by the global offspring number, so the offspring must be the same bit for bit.  The size
+    threshold is lowered to 0 MB to take that path on this small case."""
+    old = os.environ.get("GSB200_SORT_GAMETES_MIN_MB")
+    try:
+        # one shard first: a kernel's first launch loads its module, which waits for the device — with two shards driven from
+        # one host thread that would be waiting for a kernel of shard 0 that spins until shard 1 has been enqueued
+        os.environ["GSB200_SORT_GAMETES_MIN_MB"] = "0"
+        sorted_one = engine_level(1)
+        os.environ["GSB200_SORT_GAMETES_MIN_MB"] = "1000000"
+        plain = engine_level(2)
+        same_history(sorted_one, plain)
+        os.environ["GSB200_SORT_GAMETES_MIN_MB"] = "0"
+        same_history(engine_level(2), plain)
+    finally:
+        if old is None:
+            os.environ.pop("GSB200_SORT_GAMETES_MIN_MB", None)
+        else:
+            os.environ["GSB200_SORT_GAMETES_MIN_MB"] = old
+
+
 def host_level(rank, world, handles_io, device=0):
     """the host mirror's gsb_shard_* (synchronous per rank: each rank needs its own thread or process)"""
     from genomicsimulation_b200 import SimData, sharding
