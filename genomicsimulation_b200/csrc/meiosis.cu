@@ -1026,12 +1026,49 @@ int make_draw_view(const gsb200_draws* d, DrawView* v, const char* what) {
 struct FusedBv { const long long* tab; const uint32_t* slot; const long long* q; unsigned long long* acc; uint32_t shift; };
 
 // key = the row a gamete is made from, value = the gamete (2 * offspring + which parent)
-__global__ void gamete_keys_kernel(uint32_t n_gametes, const uint32_t* __restrict__ p1, const uint32_t* __restrict__ p2,
+__global__ void gamete_keys_kernel(uint32_t n_gametes, const uint32_t* __restrict__ p1, const uint32_t* __restrict__ p2, uint32_t p2_offset,
                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_gametes) return;
-    keys[g] = (g & 1u) ? p2[g >> 1] : p1[g >> 1];
+    keys[g] = (g & 1u) ? p2[g >> 1] + p2_offset : p1[g >> 1];
     vals[g] = g;
+}
+
+// A parent pool that does not stay in L2 beside the offspring stream: the gametes are processed sorted by parent, so that
+// the ~2n / n_pool gametes of a parent are spliced by neighbouring warps at the same time and its row comes from DRAM once
+// instead of once per gamete (configs[2]: 10 000 parents = 125 MB, 200 gametes each: read traffic 12.5 GB -> 0.13 GB per
+// million offspring).  The draws are keyed by the global offspring number, so the order changes nothing in the result
+// (tests/test_gpu_sharding.py).  Measured, 50 k SNPs (profiles/r2_sorted_gametes.txt): 100 MB pool 3.69 -> 3.00 ms per 800 k
+// offspring (0.83 -> 1.02 of the HBM peak on the algorithmic bytes), 50 MB 1.64 -> 1.51 ms per 400 k, 25 MB 0.80 -> 0.78 ms
+// per 200 k; the 12.5 MB pool of the headline step sits in L2 anyway and would only pay the sort's ~27 us: threshold 24 MB.
+// keys1 / keys2: per offspring, which of the n_keys candidate parents made gamete 0 / 1 (keys2 counted from key2_offset on).
+// *d_order stays null when sorting is not worth it.
+int gamete_order(gsb200_ctx* ctx, uint32_t n, const uint32_t* keys1, const uint32_t* keys2, uint32_t key2_offset, uint32_t n_keys,
+                 const uint32_t** d_order) {
+    *d_order = nullptr;
+    // GSB200_SORT_GAMETES_MIN_MB (read at every call: tests switch it): pools from this many MB on are sorted, default 24
+    const char* min_mb_env = getenv("GSB200_SORT_GAMETES_MIN_MB");
+    const size_t min_mb = min_mb_env ? (size_t) atol(min_mb_env) : 24;
+    const size_t pool_bytes = (size_t) n_keys * ctx->row_words() * sizeof(uint32_t);
+    if (pool_bytes < (min_mb << 20) || n < 4 * (size_t) n_keys || n >= (1u << 30)) return GSB200_OK;
+    const uint32_t n_g = 2 * n;
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < n_keys) ++bits;
+    size_t temp_bytes = 0;
+    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*) nullptr, (uint32_t*) nullptr,
+                                                 (const uint32_t*) nullptr, (uint32_t*) nullptr, (int) n_g, 0, bits, ctx->stream));
+    const size_t arr = ((size_t) n_g * sizeof(uint32_t) + 255) & ~(size_t) 255;
+    GSB_TRY(ctx->s_plan[0].ensure(4 * arr + temp_bytes));
+    uint32_t* k_in = (uint32_t*) ctx->s_plan[0].ptr;
+    uint32_t* k_out = (uint32_t*) ((char*) k_in + arr);
+    uint32_t* v_in = (uint32_t*) ((char*) k_in + 2 * arr);
+    uint32_t* v_out = (uint32_t*) ((char*) k_in + 3 * arr);
+    gamete_keys_kernel<<<grid_for(n_g, 256), 256, 0, ctx->stream>>>(n_g, keys1, keys2, key2_offset, k_in, v_in);
+    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs((char*) k_in + 4 * arr, temp_bytes, k_in, k_out, v_in, v_out, (int) n_g, 0, bits, ctx->stream));
+    ctx->launches += 3;
+    GSB_CUDA_TRY(cudaGetLastError());
+    *d_order = v_out;
+    return GSB200_OK;
 }
 
 int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t* d_p2, uint32_t map1, uint32_t map2,
@@ -1117,35 +1154,8 @@ int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_poo
         GSB_CUDA_TRY(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
         window = true;
     }
-    // A pool that does not stay in L2 beside the offspring stream: the gametes are processed sorted by parent, so that the
-    // ~2n / n_pool gametes of a parent are spliced by neighbouring warps at the same time and its row comes from DRAM once
-    // instead of once per gamete (configs[2]: 10 000 parents = 125 MB, 200 gametes each: read traffic 12.5 GB -> 0.13 GB per
-    // million offspring).  The draws are keyed by the global offspring number, so the order changes nothing in the result
-    // (tests/test_gpu_sharding.py).  Measured, 50 k SNPs (profiles/r2_sorted_gametes.txt): 100 MB pool 3.69 -> 3.00 ms per 800 k
-    // offspring (0.83 -> 1.02 of the HBM peak on the algorithmic bytes), 50 MB 1.64 -> 1.51 ms per 400 k, 25 MB 0.80 -> 0.78 ms
-    // per 200 k; the 12.5 MB pool of the headline step sits in L2 anyway and would only pay the sort's ~27 us: threshold 24 MB.
     const uint32_t* d_order = nullptr;
-    // GSB200_SORT_GAMETES_MIN_MB (read at every call: tests switch it): pools from this many MB on are sorted, default 24
-    const char* min_mb_env = getenv("GSB200_SORT_GAMETES_MIN_MB");
-    const size_t min_mb = min_mb_env ? (size_t) atol(min_mb_env) : 24;
-    if (pool_bytes >= (min_mb << 20) && n >= 4 * (size_t) n_pool) {
-        const uint32_t n_g = 2 * n;
-        int bits = 1;
-        while ((1u << bits) < n_pool) ++bits;
-        size_t temp_bytes = 0;
-        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*) nullptr, (uint32_t*) nullptr,
-                                                     (const uint32_t*) nullptr, (uint32_t*) nullptr, (int) n_g, 0, bits, ctx->stream));
-        const size_t arr = ((size_t) n_g * sizeof(uint32_t) + 255) & ~(size_t) 255;
-        GSB_TRY(ctx->s_plan[0].ensure(4 * arr + temp_bytes));
-        uint32_t* k_in = (uint32_t*) ctx->s_plan[0].ptr;
-        uint32_t* k_out = (uint32_t*) ((char*) k_in + arr);
-        uint32_t* v_in = (uint32_t*) ((char*) k_in + 2 * arr);
-        uint32_t* v_out = (uint32_t*) ((char*) k_in + 3 * arr);
-        gamete_keys_kernel<<<grid_for(n_g, 256), 256, 0, ctx->stream>>>(n_g, d_p1, d_p2, k_in, v_in);
-        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs((char*) k_in + 4 * arr, temp_bytes, k_in, k_out, v_in, v_out, (int) n_g, 0, bits, ctx->stream));
-        ctx->launches += 3;
-        d_order = v_out;
-    }
+    GSB_TRY(gamete_order(ctx, n, d_p1, d_p2, 0, n_pool, &d_order));
     const int st = cross_impl(ctx, n, d_p1, d_p2, map, map, d_out_rows ? d_out_rows : d_run, draws, false, what, nullptr, pool_base, d_order);
     if (window) {
         cudaStreamAttrValue attr;
@@ -1293,7 +1303,11 @@ int gsb200_cross_random_pairs_begin(gsb200_ctx* ctx, uint32_t n_crosses, uint32_
     if (picked1) GSB_CUDA_TRY(cudaMemcpyAsync(picked1, d_k1, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (picked2) GSB_CUDA_TRY(cudaMemcpyAsync(picked2, d_k2, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (picked1 || picked2) GSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    GSB_TRY(cross_impl(ctx, n, d_p1, d_p2, map1, map2, d_out, &per_offspring, false, what));
+    // many offspring of a parent group that does not stay in L2: gametes sorted by parent (gamete_order above); d_k1 / d_k2
+    // are the picks' positions in the candidate lists
+    const uint32_t* d_order = nullptr;
+    GSB_TRY(gamete_order(ctx, n, d_k1, d_k2, same ? 0u : n1, same ? n1 : n1 + n2, &d_order));
+    GSB_TRY(cross_impl(ctx, n, d_p1, d_p2, map1, map2, d_out, &per_offspring, false, what, nullptr, nullptr, d_order));
     gsb200_ctx::PendingCross& pc = ctx->pending_cross;
     pc.active = true; pc.n = n; pc.map1 = map1; pc.map2 = map2;
     pc.d_p1 = d_p1; pc.d_p2 = d_p2; pc.d_out = d_out; pc.draws = per_offspring;

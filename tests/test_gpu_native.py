@@ -219,6 +219,26 @@ def test_device_side_parent_choice():
     sim.close()
 
 
+def test_gametes_sorted_by_parent_give_the_same_offspring(monkeypatch):
+    """Large parent groups are spliced with the gametes sorted by parent (gamete_order, csrc/meiosis.cu: each parent's row
+    then comes from DRAM once).  The draws are keyed by the offspring number, so the result must not depend on it —
+    within one group and between two groups, with the size threshold lowered to 0 MB and raised out of reach."""
+    ds = datasets.synthetic(24, 1500, 5, 110.0, seed=31)
+    out = []
+    for min_mb in ("1000000", "0"):
+        monkeypatch.setenv("GSB200_SORT_GAMETES_MIN_MB", min_mb)
+        sim = make_sim(ds)
+        sim.use_native_draws(9)
+        g = sim.make_random_crosses(1, 3000, family_size=2)
+        h = sim.make_group_from(np.arange(8, 24))
+        b = sim.make_random_crosses_between(1, h, 2500)
+        out.append((sim.export_group(g), sim.export_group(b)))
+        sim.close()
+    for (x, y) in zip(out[0], out[1]):
+        for key in ("genotypes", "ids", "ped1", "ped2"):
+            assert np.array_equal(x[key], y[key]), key
+
+
 def test_kernels_stay_inside_their_rows_and_keep_padding_zero():
     """Guard rows: offspring written to every other row must leave the rows in between untouched,
     and the bits of a plane beyond the last marker must stay 0 (they feed the GEBV contraction)."""
