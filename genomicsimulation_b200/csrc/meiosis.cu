@@ -1040,17 +1040,26 @@ __global__ void gamete_keys_kernel(uint32_t n_gametes, const uint32_t* __restric
 // million offspring).  The draws are keyed by the global offspring number, so the order changes nothing in the result
 // (tests/test_gpu_sharding.py).  Measured, 50 k SNPs (profiles/r2_sorted_gametes.txt): 100 MB pool 3.69 -> 3.00 ms per 800 k
 // offspring (0.83 -> 1.02 of the HBM peak on the algorithmic bytes), 50 MB 1.64 -> 1.51 ms per 400 k, 25 MB 0.80 -> 0.78 ms
-// per 200 k; the 12.5 MB pool of the headline step sits in L2 anyway and would only pay the sort's ~27 us: threshold 24 MB.
+// per 200 k; the 12.5 MB pool of the headline step sits in L2 anyway and would only pay the sort's ~27 us.
 // keys1 / keys2: per offspring, which of the n_keys candidate parents made gamete 0 / 1 (keys2 counted from key2_offset on).
 // *d_order stays null when sorting is not worth it.
 int gamete_order(gsb200_ctx* ctx, uint32_t n, const uint32_t* keys1, const uint32_t* keys2, uint32_t key2_offset, uint32_t n_keys,
                  const uint32_t** d_order) {
     *d_order = nullptr;
-    // GSB200_SORT_GAMETES_MIN_MB (read at every call: tests switch it): pools from this many MB on are sorted, default 24
-    const char* min_mb_env = getenv("GSB200_SORT_GAMETES_MIN_MB");
-    const size_t min_mb = min_mb_env ? (size_t) atol(min_mb_env) : 24;
+    // Worth it when the DRAM reads it saves outweigh the sort (~30 us, mostly launches): the saving is the parents' half of
+    // the algorithmic bytes times the share of them that misses L2 in numbered order — ~0 for a 12 MB pool, ~1 from 110 MB
+    // on (measured: 0.2 at 25 MB, 0.4 at 50 MB, 0.9 at 100 MB).  GSB200_SORT_GAMETES_MIN_MB, read at every call so that
+    // tests can switch it, replaces the estimate by a plain size threshold (0: always, huge: never).
     const size_t pool_bytes = (size_t) n_keys * ctx->row_words() * sizeof(uint32_t);
-    if (pool_bytes < (min_mb << 20) || n < 4 * (size_t) n_keys || n >= (1u << 30)) return GSB200_OK;
+    if (n < 4 * (size_t) n_keys || n >= (1u << 30)) return GSB200_OK;
+    if (const char* min_mb_env = getenv("GSB200_SORT_GAMETES_MIN_MB")) {
+        if (pool_bytes < ((size_t) atol(min_mb_env) << 20)) return GSB200_OK;
+    } else {
+        const double pool_mb = (double) pool_bytes / (1 << 20);
+        const double miss = std::min(1.0, std::max(0.0, (pool_mb - 12.0) / 100.0));
+        const double saved_us = (double) n * (double) (ctx->row_words() * sizeof(uint32_t) / 2) * miss / 6.5e6;      // at ~6.5 TB/s
+        if (saved_us < 45.0) return GSB200_OK;
+    }
     const uint32_t n_g = 2 * n;
     int bits = 1;
     while (bits < 32 && (1ull << bits) < n_keys) ++bits;
