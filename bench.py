@@ -67,17 +67,21 @@ def workload(a, world=1, top=None):
 # ---------------------------------------------------------------------------- clocks
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md).  The sampler is started before
+    the warm-up steps (nvidia-smi needs a few hundred ms to deliver its first line, more on an 8-GPU box) and every line
+    is stamped on arrival; summary() keeps the lines that arrived inside the timed window, or — a timed region shorter
+    than the sampling period — the ones nearest to it (the warm-up steps right before run the same load)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t_lo = self.t_hi = None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -87,17 +91,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
+
+    def wait_for_first_sample(self, seconds=3.0):
+        t = time.monotonic()
+        while self.proc and not self.rows and time.monotonic() - t < seconds:
+            time.sleep(0.01)
+
+    def window(self, t_lo, t_hi):
+        self.t_lo, self.t_hi = t_lo, t_hi
 
     def __exit__(self, *exc):
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.05)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self):
+        rows = [r for t, r in self.rows if self.t_lo is None or self.t_lo <= t <= self.t_hi + 0.03]
+        where = "inside the timed region"
+        if not rows and self.rows:
+            mid = 0.5 * (self.t_lo + self.t_hi)
+            nearest = sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]
+            rows = [r for t, r in nearest]
+            where = "nearest to the timed region (%.0f ms away; the warm-up steps run the same load)" % (1e3 * min(abs(t - mid) for t, r in nearest))
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -107,7 +126,7 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm), "sampled": where}
 
 
 # ---------------------------------------------------------------------------- CPU baselines
@@ -350,6 +369,10 @@ def sharded_loop(sim, rank, world, local, n, F, steps, warmup, seed, sample_cloc
         check(E.gsb200_shard_cross_dev(shard.h, n, 0, None, F + (1 - cur) * n, C.byref(d), None))
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(local) if sample_clocks else None
+    if clocks:
+        clocks.__enter__()
+        clocks.wait_for_first_sample()
     for i in range(warmup):
         step(i)
     check(E.gsb200_cross_dev_status(ctx))
@@ -360,9 +383,7 @@ def sharded_loop(sim, rank, world, local, n, F, steps, warmup, seed, sample_cloc
     launches0 = E.gsb200_kernel_launches(ctx)
     epoch0 = E.gsb200_shard_epoch(shard.h)
     t0, t1 = ev(), ev()
-    clocks = ClockSampler(local) if sample_clocks else None
-    if clocks:
-        clocks.__enter__()
+    w0 = time.monotonic()
     t0.record(ext)
     for i in range(steps):
         step(warmup + i)
@@ -370,6 +391,7 @@ def sharded_loop(sim, rank, world, local, n, F, steps, warmup, seed, sample_cloc
     ext.synchronize()
     torch.cuda.synchronize()
     if clocks:
+        clocks.window(w0, time.monotonic())
         clocks.__exit__()
     if world > 1:
         dist.barrier()
@@ -439,11 +461,18 @@ def engine_arm(a):
     sim.shard_connect(sharding.exchange_handles(sim.shard_handle()))
     bv_host = np.empty(n, dtype=np.float64)
     E = sim.E
-    e2e_t = []
-    e2e_steps = 2 + min(a.steps, 20)
-    for i in range(e2e_steps):
-        if world > 1:
-            dist.barrier()
+    # the timed steps are bracketed ONCE by a barrier + synchronize on both sides; inside, the ranks meet only through the
+    # generation's own exchange (two barriers per step cost more than the step at N = 8)
+    e2e_warm, e2e_steps = 2, min(a.steps, 20)
+    t_start = 0.0
+    for i in range(e2e_warm + e2e_steps):
+        if i == e2e_warm:
+            sim.shard_finish()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t_start = time.perf_counter()
         t = time.perf_counter()
         new = sim.shard_select_and_cross(g, n_total, 1, top, n_total)      # pedigrees tracked, ids allocated
         ta = time.perf_counter()
@@ -451,14 +480,16 @@ def engine_arm(a):
         tb = time.perf_counter()
         sim.delete_group(g)
         g = new
-        if world > 1:
-            dist.barrier()
-        e2e_t.append(time.perf_counter() - t)
         if os.environ.get("GSB200_BENCH_VERBOSE") and rank == 0:
             print("e2e step %d: select_and_cross %.3f ms, local_bvs %.3f ms, delete_group %.3f ms" %
                   (i, (ta - t) * 1e3, (tb - ta) * 1e3, (time.perf_counter() - tb) * 1e3), file=sys.stderr)
         assert bv.shape[0] == n
-    te = torch.tensor([float(np.mean(e2e_t[2:]))], dtype=torch.float64, device="cuda")
+    sim.shard_finish()                                                      # the last generation's offspring are in place
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    te = torch.tensor([(time.perf_counter() - t_start) / e2e_steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_sec = float(te.item())

@@ -324,6 +324,11 @@ class SimData:
         self._check()
         return g
 
+    def shard_finish(self):
+        """waits for the generation in flight and reports its verdict (gsb_shard_finish)"""
+        if self.L.gsb_shard_finish(self.d) != 0:
+            self._check()
+
     def shard_local_bvs(self, out):
         got = self.L.gsb_shard_get_local_bvs(self.d, len(out), _p(out))
         self._check()
