@@ -219,7 +219,16 @@ int select_top_n(gsb200_ctx* ctx, const double* d_values, uint32_t n, uint32_t t
 // meiosis.cu: n random crosses among the n_pool rows of `pool_base` (packed rows in store layout, e.g. a
 // shard's exchanged parent pool), pairs drawn on the device from the stream position draws->first_unit on;
 // d_picks (device, 2n, may be null) receives the pool positions of both parents.  Asynchronous.
+// A pool that is still arriving from the peers of a sharded generation (shard.cu): which rank owns which slots and where
+// its "rows are here" flags live.  The splice then waits per parent, for the owner of that parent only.
+struct PoolWait {
+    const volatile uint32_t* flags;    // [world]: the epoch of rank r's rows present in this pool
+    const uint32_t* bounds;            // device, [world + 1]: slots bounds[r] .. bounds[r + 1] - 1 are rank r's
+    uint32_t epoch, world, rank;
+    int* err;                          // raised when a peer does not show up in time
+};
 int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_pool, uint32_t n, uint32_t map,
                       const uint32_t* d_out_rows, uint32_t first_out_row, const gsb200_draws* draws, uint32_t* d_picks,
-                      const char* what, uint32_t* h_picks = nullptr /* pinned, 2n: copy of d_picks */, cudaEvent_t picks_ready = nullptr);
+                      const char* what, uint32_t* h_picks = nullptr /* pinned, 2n: copy of d_picks */, cudaEvent_t picks_ready = nullptr,
+                      const PoolWait* pw = nullptr);
 }  // namespace gsb

@@ -65,6 +65,8 @@ struct DrawView {
     uint64_t base_offset;      // entries before this generation's gametes within a unit
 };
 
+constexpr long long kPoolWaitCycles = 40000000000ll;        // ~20 s: a peer that never delivers (shard.cu has the same)
+
 struct MeiosisArgs {
     const uint32_t* src_base;  // rows the gametes are made from
     const uint32_t* src_rows0; // per unit: row of the parent of gamete 0 (null: unit index)
@@ -92,6 +94,7 @@ struct MeiosisArgs {
     const long long* bv_q;     // [plane_words * 32]: fixed-point delta per marker
     unsigned long long* bv_acc;// per unit: sum over its gametes, two's complement
     const uint32_t* order;     // fast kernel: the gametes in processing order (null: as numbered); see pool_random_cross
+    PoolWait pw;               // fast kernel: flags null unless the source rows are a pool that is still arriving
 };
 
 // ------------------------------------------------------------------ native draw stream
@@ -248,6 +251,7 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
     uint32_t* piece_multi = piece_seen + a.parity_words;
 
     const uint32_t n_gametes = a.n_units * a.gametes_per_unit;      // host keeps this below 2^32
+    uint32_t owners_seen = 0;                                        // pool still arriving: the ranks whose rows this warp has seen
     for (uint32_t gi = blockIdx.x * warps + warp; gi < n_gametes; gi += gridDim.x * warps) {
         const uint32_t g = a.order ? a.order[gi] : gi;           // gametes sorted by parent: neighbouring warps share their source rows
         const uint32_t unit_local = a.gametes_per_unit == 2 ? g >> 1 : g;
@@ -369,6 +373,29 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
         const uint32_t* src = a.src_base + (uint64_t) src_row * a.row_words;
         uint32_t* dst = a.dst_base + (uint64_t) dst_row * a.row_words;
         const uint32_t hap_stride = a.planes * a.plane_words;
+
+        // The pool may still be arriving from the peers of a sharded generation: wait for the OWNER of this parent's slot
+        // only (everything above — draws, crossover plan — needed no parent data).  The flag is read with acquire semantics
+        // by lane 0; the other lanes pass the warp barrier after it, so no row load below is issued before the flag was seen.
+        // (A __threadfence() here instead cost 15 % of the kernel: it also waits for the warp's own stores of the gamete before.)
+        if (a.pw.flags) {
+            uint32_t owner = 0;
+            while (owner + 1 < a.pw.world && src_row >= a.pw.bounds[owner + 1]) ++owner;
+            if (!((owners_seen >> owner) & 1u)) {                  // (warp-uniform: a rank's rows, once here, stay)
+                if (lane == 0 && owner != a.pw.rank) {
+                    const long long t0 = clock64();
+                    for (;;) {
+                        uint32_t have;
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(a.pw.flags + owner) : "memory");
+                        if (have >= a.pw.epoch) break;
+                        if (clock64() - t0 > kPoolWaitCycles) { atomicExch(a.pw.err, 1); break; }
+                        __nanosleep(200);
+                    }
+                }
+                __syncwarp();
+                owners_seen |= 1u << owner;
+            }
+        }
 
         // E1. every piece, whole, from the strand it starts on: plain 128-bit copies.  Full groups of
         //     32 * kUnroll pieces run without bounds checks; 32-bit piece offsets from two bases.
@@ -805,6 +832,17 @@ int prepare_uncovered(gsb200_ctx* ctx, const DeviceMap& m) {
     return GSB200_OK;
 }
 
+__global__ void pool_wait_all_kernel(const PoolWait pw) {
+    if (threadIdx.x < pw.world) {
+        const long long t0 = clock64();
+        while (pw.flags[threadIdx.x] < pw.epoch) {
+            if (clock64() - t0 > kPoolWaitCycles) { atomicExch(pw.err, 1); break; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
 struct Batch {
     const char* what;
     uint32_t n_units;
@@ -819,6 +857,7 @@ struct Batch {
     unsigned long long* bv_acc = nullptr;
     uint32_t bv_shift = 5;
     const uint32_t* d_order = nullptr;   // gametes in processing order, or null
+    const PoolWait* pw = nullptr;        // the source rows are a pool that is still arriving, or null
 };
 
 // Philox draws materialised in tape layout on the device (s_plan[4..7]).
@@ -901,6 +940,8 @@ int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
     a.flag = ctx->d_flag;
     a.bv_tab = b.bv_tab; a.bv_slot = b.bv_slot; a.bv_q = b.bv_q; a.bv_acc = b.bv_acc; a.bv_shift = b.bv_shift;
     a.order = b.d_order;
+    memset(&a.pw, 0, sizeof a.pw);
+    if (b.pw) a.pw = *b.pw;
 
     const DeviceMap* maps[2] = { b.map0, b.gametes_per_unit > 1 ? b.map1 : b.map0 };
     if (b.draws.mode == GSB200_DRAWS_PHILOX) {
@@ -954,6 +995,10 @@ int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
         // plan capacity exceeded somewhere in the batch: same draws, general kernel
     }
     GSB_REQUIRE(may_sync || !fast, GSB200_ERR_UNSUPPORTED, "%s: internal: unreachable", b.what);
+    if (a.pw.flags) {                   // the general kernels do not wait per parent: everybody's rows first
+        pool_wait_all_kernel<<<1, 32, 0, ctx->stream>>>(a.pw);
+        ++ctx->launches;
+    }
     return run_general(ctx, a, maps);
 }
 
@@ -1026,11 +1071,19 @@ int make_draw_view(const gsb200_draws* d, DrawView* v, const char* what) {
 struct FusedBv { const long long* tab; const uint32_t* slot; const long long* q; unsigned long long* acc; uint32_t shift; };
 
 // key = the row a gamete is made from, value = the gamete (2 * offspring + which parent)
+// (with a pool that is still arriving: the rank's own slots first, then its neighbours' in the order their rows arrive —
+// rank - 1 pushes to this rank first, then rank - 2, ...; `slot_bits` bits of slot below the owner's turn)
 __global__ void gamete_keys_kernel(uint32_t n_gametes, const uint32_t* __restrict__ p1, const uint32_t* __restrict__ p2, uint32_t p2_offset,
-                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, const PoolWait pw, uint32_t slot_bits) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_gametes) return;
-    keys[g] = (g & 1u) ? p2[g >> 1] + p2_offset : p1[g >> 1];
+    uint32_t k = (g & 1u) ? p2[g >> 1] + p2_offset : p1[g >> 1];
+    if (pw.bounds) {
+        uint32_t owner = 0;
+        while (owner + 1 < pw.world && k >= pw.bounds[owner + 1]) ++owner;
+        k |= ((pw.rank + pw.world - owner) % pw.world) << slot_bits;
+    }
+    keys[g] = k;
     vals[g] = g;
 }
 
@@ -1044,7 +1097,7 @@ __global__ void gamete_keys_kernel(uint32_t n_gametes, const uint32_t* __restric
 // keys1 / keys2: per offspring, which of the n_keys candidate parents made gamete 0 / 1 (keys2 counted from key2_offset on).
 // *d_order stays null when sorting is not worth it.
 int gamete_order(gsb200_ctx* ctx, uint32_t n, const uint32_t* keys1, const uint32_t* keys2, uint32_t key2_offset, uint32_t n_keys,
-                 const uint32_t** d_order) {
+                 const uint32_t** d_order, const PoolWait* pw = nullptr) {
     *d_order = nullptr;
     // Worth it when the DRAM reads it saves outweigh the sort (~30 us, mostly launches): the saving is the parents' half of
     // the algorithmic bytes times the share of them that misses L2 in numbered order — ~0 for a 12 MB pool, ~1 from 110 MB
@@ -1057,12 +1110,23 @@ int gamete_order(gsb200_ctx* ctx, uint32_t n, const uint32_t* keys1, const uint3
     } else {
         const double pool_mb = (double) pool_bytes / (1 << 20);
         const double miss = std::min(1.0, std::max(0.0, (pool_mb - 12.0) / 100.0));
-        const double saved_us = (double) n * (double) (ctx->row_words() * sizeof(uint32_t) / 2) * miss / 6.5e6;      // at ~6.5 TB/s
-        if (saved_us < 45.0) return GSB200_OK;
+        double saved_us = (double) n * (double) (ctx->row_words() * sizeof(uint32_t) / 2) * miss / 6.5e6;      // at ~6.5 TB/s
+        // a pool that is still arriving: sorted, the splice starts on the rank's own parents while the others' rows come in
+        // over NVLink (~0.6 TB/s) instead of waiting for all of them
+        if (pw && pw->world > 1) saved_us += (double) pool_bytes * (pw->world - 1) / pw->world / 0.6e6;
+        if (saved_us < 45.0 && !(pw && pw->world > 1)) return GSB200_OK;          // (shard.cu splits the push only when it is worth this)
     }
     const uint32_t n_g = 2 * n;
     int bits = 1;
     while (bits < 32 && (1ull << bits) < n_keys) ++bits;
+    const uint32_t slot_bits = (uint32_t) bits;
+    PoolWait rot;
+    memset(&rot, 0, sizeof rot);
+    if (pw && pw->world > 1) {
+        rot = *pw;
+        while ((1u << (bits - (int) slot_bits)) < pw->world) ++bits;
+        GSB_REQUIRE(bits <= 32, GSB200_ERR_ARG, "gamete order: too many parents for the sort key");
+    }
     size_t temp_bytes = 0;
     GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*) nullptr, (uint32_t*) nullptr,
                                                  (const uint32_t*) nullptr, (uint32_t*) nullptr, (int) n_g, 0, bits, ctx->stream));
@@ -1072,7 +1136,7 @@ int gamete_order(gsb200_ctx* ctx, uint32_t n, const uint32_t* keys1, const uint3
     uint32_t* k_out = (uint32_t*) ((char*) k_in + arr);
     uint32_t* v_in = (uint32_t*) ((char*) k_in + 2 * arr);
     uint32_t* v_out = (uint32_t*) ((char*) k_in + 3 * arr);
-    gamete_keys_kernel<<<grid_for(n_g, 256), 256, 0, ctx->stream>>>(n_g, keys1, keys2, key2_offset, k_in, v_in);
+    gamete_keys_kernel<<<grid_for(n_g, 256), 256, 0, ctx->stream>>>(n_g, keys1, keys2, key2_offset, k_in, v_in, rot, slot_bits);
     GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs((char*) k_in + 4 * arr, temp_bytes, k_in, k_out, v_in, v_out, (int) n_g, 0, bits, ctx->stream));
     ctx->launches += 3;
     GSB_CUDA_TRY(cudaGetLastError());
@@ -1083,7 +1147,8 @@ int gamete_order(gsb200_ctx* ctx, uint32_t n, const uint32_t* keys1, const uint3
 int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t* d_p2, uint32_t map1, uint32_t map2,
                const uint32_t* d_out, const gsb200_draws* draws, bool may_sync, const char* what, const FusedBv* bv = nullptr,
                const uint32_t* src_base = nullptr /* rows the parents are read from; null: the store */,
-               const uint32_t* d_order = nullptr /* gametes (2 * offspring + which) in processing order; null: as numbered */) {
+               const uint32_t* d_order = nullptr /* gametes (2 * offspring + which) in processing order; null: as numbered */,
+               const PoolWait* pw = nullptr) {
     const DeviceMap *m1, *m2;
     GSB_TRY(get_map(ctx, map1, &m1, what));
     GSB_TRY(get_map(ctx, map2, &m2, what));
@@ -1095,6 +1160,7 @@ int cross_impl(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_p1, const uint32_t
     b.map0 = m1; b.map1 = m2; b.gametes_per_unit = 2; b.doubled = 0; b.tape_xcap = 0;
     if (bv) { b.bv_tab = bv->tab; b.bv_slot = bv->slot; b.bv_q = bv->q; b.bv_acc = bv->acc; b.bv_shift = bv->shift; }
     b.d_order = d_order;
+    b.pw = pw;
     GSB_TRY(make_draw_view(draws, &b.draws, what));
     if (draws->mode == GSB200_DRAWS_TAPE) {
         GSB_REQUIRE(may_sync, GSB200_ERR_ARG, "%s: device-pointer entry points take PHILOX draws only", what);
@@ -1116,7 +1182,7 @@ namespace gsb {
 
 int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_pool, uint32_t n, uint32_t map,
                       const uint32_t* d_out_rows, uint32_t first_out_row, const gsb200_draws* draws, uint32_t* d_picks,
-                      const char* what, uint32_t* h_picks, cudaEvent_t picks_ready) {
+                      const char* what, uint32_t* h_picks, cudaEvent_t picks_ready, const PoolWait* pw) {
     if (n == 0) return GSB200_OK;
     GSB_REQUIRE(n_pool >= 2, GSB200_ERR_ARG, "%s: a pool of %u cannot be crossed at random", what, n_pool);
     GSB_REQUIRE(draws && draws->mode == GSB200_DRAWS_PHILOX, GSB200_ERR_ARG, "%s: needs PHILOX draws", what);
@@ -1164,8 +1230,8 @@ int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_poo
         window = true;
     }
     const uint32_t* d_order = nullptr;
-    GSB_TRY(gamete_order(ctx, n, d_p1, d_p2, 0, n_pool, &d_order));
-    const int st = cross_impl(ctx, n, d_p1, d_p2, map, map, d_out_rows ? d_out_rows : d_run, draws, false, what, nullptr, pool_base, d_order);
+    GSB_TRY(gamete_order(ctx, n, d_p1, d_p2, 0, n_pool, &d_order, pw));
+    const int st = cross_impl(ctx, n, d_p1, d_p2, map, map, d_out_rows ? d_out_rows : d_run, draws, false, what, nullptr, pool_base, d_order, pw);
     if (window) {
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof attr);

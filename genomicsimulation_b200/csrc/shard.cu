@@ -41,7 +41,7 @@ constexpr uint32_t kHandleMagic = 0x67736232u;
 constexpr uint32_t kTimingRing = 256, kTimingEvents = 7;
 constexpr long long kWaitTimeoutCycles = 40000000000ll;      // ~20 s at 1.9 GHz: a peer that never shows up
 
-struct Peers { char* base[kMaxWorld]; };
+struct Peers { char* base[kMaxWorld]; uint32_t row_u4; };      // row_u4: uint4 per packed row
 
 struct ShardHandle {                 // what gsb200_shard_handle exports (GSB200_SHARD_HANDLE_BYTES)
     uint32_t magic, rank, world, device;
@@ -50,6 +50,7 @@ struct ShardHandle {                 // what gsb200_shard_handle exports (GSB200
     uint64_t slab_bytes, row_bytes, max_total;
     void* raw;                       // the slab's address in its owner's process
     cudaIpcMemHandle_t ipc;
+    uint32_t pci;                    // which physical GPU: domain << 16 | bus << 8 | device
 };
 static_assert(sizeof(ShardHandle) <= GSB200_SHARD_HANDLE_BYTES, "shard handle too large");
 
@@ -127,6 +128,76 @@ __global__ void __launch_bounds__(256) shard_push_pool_kernel(const __grid_const
     }
 }
 
+// The same in two parts, for ranks on different GPUs (see shard_select_impl): the rows I own into MY pool buffer and my flag
+// raised here only ...
+__global__ void __launch_bounds__(256) shard_push_pool_local_kernel(const __grid_constant__ Peers P, uint32_t rank, size_t off_ids, size_t off_pool,
+                                                                    const uint32_t* __restrict__ store, uint64_t row_words,
+                                                                    const uint32_t* __restrict__ local_rows, uint32_t lo,
+                                                                    const SelectState* __restrict__ state, const uint32_t* __restrict__ sel,
+                                                                    uint32_t top_n, uint32_t* __restrict__ sel_ids, int with_ids,
+                                                                    uint32_t* counter, uint32_t epoch) {
+    const uint32_t own_lo = state->own_lo, own_cnt = state->own_hi - own_lo;
+    const uint32_t pieces = (uint32_t) (row_words / 4);
+    const uint64_t total = (uint64_t) own_cnt * pieces;
+    uint4* mine = reinterpret_cast<uint4*>(P.base[rank] + off_pool);
+    for (uint64_t flat = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; flat < total; flat += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t p = own_lo + (uint32_t) (flat / pieces), w = (uint32_t) (flat % pieces);
+        const uint32_t row = local_rows[sel[p] - lo];
+        mine[(uint64_t) p * pieces + w] = __ldg(reinterpret_cast<const uint4*>(store + (uint64_t) row * row_words) + w);
+    }
+    const uint32_t* all_ids = reinterpret_cast<const uint32_t*>(P.base[rank] + off_ids);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < top_n; p += gridDim.x * blockDim.x)
+        sel_ids[p] = with_ids ? all_ids[sel[p]] : 0u;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(counter, 1u) == gridDim.x - 1) {
+        __threadfence();
+        reinterpret_cast<volatile uint32_t*>(P.base[rank] + kOffFlags)[1 * kMaxWorld + rank] = epoch;
+        *counter = 0;
+    }
+}
+
+// ... and, on a second stream beside the splice, to one peer after the other: rank + 1 first, so that what a rank receives
+// arrives in the order its splice asks for it (gamete_keys_kernel).  ONE launch, all blocks resident at once (the grid is
+// one block per SM): once it has started it needs no further SM slots, whatever spins beside it.
+__global__ void __launch_bounds__(256) shard_push_pool_remote_kernel(const __grid_constant__ Peers P, uint32_t world, uint32_t rank, size_t off_pool,
+                                                                     const uint32_t* __restrict__ bounds /* shard_owner_bounds_kernel */,
+                                                                     uint32_t* counters /* [kMaxWorld], zero */, uint32_t epoch) {
+    const uint32_t own_lo = bounds[rank], own_cnt = bounds[rank + 1] - own_lo;
+    const uint4* mine = reinterpret_cast<const uint4*>(P.base[rank] + off_pool) + (uint64_t) own_lo * P.row_u4;
+    const uint64_t total = (uint64_t) own_cnt * P.row_u4, stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint32_t k = 1; k < world; ++k) {
+        const uint32_t dest = (rank + k) % world;
+        uint4* theirs = reinterpret_cast<uint4*>(P.base[dest] + off_pool) + (uint64_t) own_lo * P.row_u4;
+        for (uint64_t flat = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; flat < total; flat += 4 * stride) {
+            uint4 v[4];                                        // four loads in flight per thread: NVLink's latency x bandwidth wants ~1.5 MB
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (flat + q * stride < total) v[q] = mine[flat + q * stride];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (flat + q * stride < total) theirs[flat + q * stride] = v[q];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&counters[dest], 1u) == gridDim.x - 1) {
+            __threadfence_system();
+            reinterpret_cast<volatile uint32_t*>(P.base[dest] + kOffFlags)[1 * kMaxWorld + rank] = epoch;
+            counters[dest] = 0;
+        }
+    }
+}
+
+// bounds[r] = first slot of the selection (ascending global indexes) owned by rank r; bounds[world] = top_n
+__global__ void shard_owner_bounds_kernel(const uint32_t* __restrict__ sel, uint32_t top_n, uint64_t n_total, uint32_t world, uint32_t* __restrict__ bounds) {
+    const uint32_t r = threadIdx.x;
+    if (r > world) return;
+    if (r == world) { bounds[r] = top_n; return; }
+    const uint64_t base = n_total / world, extra = n_total % world;
+    const uint64_t lo = r * base + (r < extra ? r : extra);          // gsb200_shard_range
+    uint32_t a = 0, b = top_n;
+    while (a < b) { const uint32_t m = (a + b) / 2; if (sel[m] < lo) a = m + 1; else b = m; }
+    bounds[r] = a;
+}
+
 __global__ void shard_iota_kernel(uint32_t* out, uint32_t first, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = first + i;
@@ -151,6 +222,15 @@ struct gsb200_shard {
     bool opened[kMaxWorld];
     bool connected = false;
     uint32_t epoch = 0, pool_waited = 0;
+    // ranks on different GPUs: the pool goes to the peers on a second stream, beside the splice, which waits per parent
+    bool split_ok = false;               // every peer is on another GPU (a spinning splice on a shared GPU would starve the peer)
+    bool split_now = false;              // this generation's pool is being pushed that way
+    bool push_outstanding = false;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_selected = nullptr, ev_pushed = nullptr;
+    uint32_t* d_bounds = nullptr;        // [kMaxWorld + 1]
+    uint32_t* d_push_counters = nullptr; // [kMaxWorld]
+    uint32_t pci = 0;
     // device state owned by the shard
     uint32_t* d_counters = nullptr;      // [0] values push, [1] pool push
     int* d_err = nullptr;
@@ -214,12 +294,30 @@ int gsb200_shard_create(gsb200_ctx* ctx, uint32_t rank, uint32_t world, uint64_t
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_picks, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_flags, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaHostAlloc((void**) &s->h_flags, 2 * sizeof(int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void**) &s->d_bounds, (kMaxWorld + 1 + kMaxWorld) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(s->d_bounds, 0, (kMaxWorld + 1 + kMaxWorld) * sizeof(uint32_t));
+    if (e == cudaSuccess) {
+        int lo_pri = 0, hi_pri = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+        e = cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, hi_pri);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_selected, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_pushed, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        int dom = 0, bus = 0, dev = 0;
+        cudaDeviceGetAttribute(&dom, cudaDevAttrPciDomainId, ctx->device);
+        cudaDeviceGetAttribute(&bus, cudaDevAttrPciBusId, ctx->device);
+        cudaDeviceGetAttribute(&dev, cudaDevAttrPciDeviceId, ctx->device);
+        s->pci = ((uint32_t) dom << 16) | ((uint32_t) bus << 8) | (uint32_t) dev | 0x80000000u;
+    }
     if (e != cudaSuccess) {
         set_error("gsb200_shard_create: allocating %zu bytes of exchange buffers failed: %s", s->slab_bytes, cudaGetErrorString(e));
         gsb200_shard_destroy(s);
         return e == cudaErrorMemoryAllocation ? GSB200_ERR_OOM : GSB200_ERR_CUDA;
     }
     s->d_sel_ids = s->d_sel + max_pool;
+    s->d_push_counters = s->d_bounds + kMaxWorld + 1;
+    s->peers.row_u4 = (uint32_t) (s->row_words / 4);
     // Every scratch buffer a generation touches is sized here, for the largest generation: nothing is
     // allocated (and, above all, nothing is cudaFree'd — which waits for the whole device, including a
     // peer shard of this process that is spinning on OUR next push) while generations are in flight.
@@ -241,6 +339,10 @@ void gsb200_shard_destroy(gsb200_shard* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); }
+    if (s->ev_selected) cudaEventDestroy(s->ev_selected);
+    if (s->ev_pushed) cudaEventDestroy(s->ev_pushed);
+    if (s->d_bounds) cudaFree(s->d_bounds);
     for (uint32_t r = 0; r < kMaxWorld; ++r) if (s->opened[r]) cudaIpcCloseMemHandle(s->peers.base[r]);
     s->s_local_rows.release();
     if (s->ev_made) for (auto& set : s->ev) for (auto& e : set) cudaEventDestroy(e);
@@ -265,6 +367,7 @@ int gsb200_shard_handle(gsb200_shard* s, void* handle) {
     h.pid = (int32_t) getpid(); h.max_pool = s->max_pool;
     h.slab_bytes = s->slab_bytes; h.row_bytes = s->row_words * sizeof(uint32_t); h.max_total = s->max_total;
     h.raw = s->slab;
+    h.pci = s->pci;
     GSB_CUDA_TRY(cudaIpcGetMemHandle(&h.ipc, s->slab));
     memset(handle, 0, GSB200_SHARD_HANDLE_BYTES);
     memcpy(handle, &h, sizeof h);
@@ -274,6 +377,7 @@ int gsb200_shard_handle(gsb200_shard* s, void* handle) {
 int gsb200_shard_connect(gsb200_shard* s, const void* handles) {
     GSB_REQUIRE(s != nullptr && handles != nullptr, GSB200_ERR_ARG, "gsb200_shard_connect: null argument");
     GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    bool same_gpu = false;
     for (uint32_t r = 0; r < s->world; ++r) {
         ShardHandle h;
         memcpy(&h, (const char*) handles + (size_t) r * GSB200_SHARD_HANDLE_BYTES, sizeof h);
@@ -282,6 +386,7 @@ int gsb200_shard_connect(gsb200_shard* s, const void* handles) {
         GSB_REQUIRE(h.slab_bytes == s->slab_bytes && h.row_bytes == s->row_words * sizeof(uint32_t) && h.max_total == s->max_total
                     && h.max_pool == s->max_pool, GSB200_ERR_ARG, "gsb200_shard_connect: rank %u was created with different sizes", r);
         if (r == s->rank) continue;
+        if (h.pci == s->pci || h.pci == 0) same_gpu = true;
         if (s->opened[r]) { cudaIpcCloseMemHandle(s->peers.base[r]); s->opened[r] = false; }
         if (h.pid == (int32_t) getpid()) {
             // a shard of this very process: its slab is addressable as it is (peer access between two devices is switched on here)
@@ -302,6 +407,7 @@ int gsb200_shard_connect(gsb200_shard* s, const void* handles) {
         }
     }
     s->connected = true;
+    s->split_ok = s->world > 1 && !same_gpu;
     return GSB200_OK;
 }
 
@@ -332,6 +438,10 @@ static int shard_select_impl(gsb200_shard* s, uint32_t n_local, const uint32_t* 
         ++ctx->launches;
         s->pool_waited = prev;
     }
+    if (s->push_outstanding) {             // the previous generation's remote push reads the selection state and the pool
+        GSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_pushed, 0));
+        s->push_outstanding = false;
+    }
     double* all_bv = reinterpret_cast<double*>(s->slab + kOffBv);
     mark(s, epoch, 0);
     if (n_local) GSB_TRY(gsb200_gebv_dev(ctx, n_local, d_local_rows, eff_index, all_bv + lo));
@@ -357,10 +467,33 @@ static int shard_select_impl(gsb200_shard* s, uint32_t n_local, const uint32_t* 
     mark(s, epoch, 2);
     GSB_TRY(select_top_n(ctx, all_bv, (uint32_t) n_total, top_n, low_is_best, ctx->s_select.ptr, s->d_sel, (uint32_t) lo, (uint32_t) hi));
     mark(s, epoch, 3);
-    shard_push_pool_kernel<<<(unsigned) ctx->sm_count * 4, 256, 0, ctx->stream>>>(
-        s->peers, s->world, s->rank, s->off_ids, s->off_pool, ctx->d_store, s->row_words, d_local_rows, (uint32_t) lo,
-        (const SelectState*) ctx->s_select.ptr, s->d_sel, top_n, s->d_sel_ids, with_ids, s->d_counters + 1, epoch);
-    ++ctx->launches;
+    // Ranks on different GPUs and enough to send for it to matter (>= 24 MB: the splice then sorts its gametes, own parents first): my rows go into my own pool buffer here, and to
+    // the peers on the second stream while the splice is already at work on the parents it has (shard_cross_impl).
+    const size_t remote_bytes = (size_t) top_n * s->row_words * sizeof(uint32_t) / s->world * (s->world - 1);
+    // MEASURED AND LEFT OFF (GSB200_SHARD_SPLIT_PUSH=1: from 24 MB to send on, =2: always — the two-GPU test forces it): the
+    // push phase shrinks as intended (N = 4, 100 k offspring per GPU: 0.072 -> 0.025 ms; 1 M-offspring generation: 0.153 ->
+    // 0.041 ms) but the splice beside it takes 0.10 - 0.18 ms longer (0.421 -> 0.526 ms; 1.010 -> 1.188 ms), a net loss of
+    // 0.05 ms per step on 2 and on 4 GPUs (profiles/r2_split_push.txt).
+    static const int split_mode = [] { const char* v = getenv("GSB200_SHARD_SPLIT_PUSH"); return v ? atoi(v) : 0; }();
+    s->split_now = s->split_ok && ((split_mode == 1 && remote_bytes >= ((size_t) 24 << 20)) || split_mode == 2);
+    if (s->split_now) {
+        shard_owner_bounds_kernel<<<1, 32, 0, ctx->stream>>>(s->d_sel, top_n, n_total, s->world, s->d_bounds);
+        shard_push_pool_local_kernel<<<(unsigned) ctx->sm_count * 2, 256, 0, ctx->stream>>>(
+            s->peers, s->rank, s->off_ids, s->off_pool, ctx->d_store, s->row_words, d_local_rows, (uint32_t) lo,
+            (const SelectState*) ctx->s_select.ptr, s->d_sel, top_n, s->d_sel_ids, with_ids, s->d_counters + 1, epoch);
+        GSB_CUDA_TRY(cudaEventRecord(s->ev_selected, ctx->stream));
+        GSB_CUDA_TRY(cudaStreamWaitEvent(s->side, s->ev_selected, 0));
+        shard_push_pool_remote_kernel<<<(unsigned) ctx->sm_count, 256, 0, s->side>>>(
+            s->peers, s->world, s->rank, s->off_pool, s->d_bounds, s->d_push_counters, epoch);
+        GSB_CUDA_TRY(cudaEventRecord(s->ev_pushed, s->side));
+        s->push_outstanding = true;
+        ctx->launches += 3;
+    } else {
+        shard_push_pool_kernel<<<(unsigned) ctx->sm_count * 4, 256, 0, ctx->stream>>>(
+            s->peers, s->world, s->rank, s->off_ids, s->off_pool, ctx->d_store, s->row_words, d_local_rows, (uint32_t) lo,
+            (const SelectState*) ctx->s_select.ptr, s->d_sel, top_n, s->d_sel_ids, with_ids, s->d_counters + 1, epoch);
+        ++ctx->launches;
+    }
     GSB_CUDA_TRY(cudaGetLastError());
     mark(s, epoch, 4);
     s->n_total = n_total;
@@ -409,12 +542,17 @@ static int shard_cross_impl(gsb200_shard* s, uint32_t n, uint32_t map, const uin
     GSB_REQUIRE(!stage_picks || n <= s->max_total, GSB200_ERR_ARG, "%s: %u offspring exceed the %llu the shard was created for", what, n,
                 (unsigned long long) s->max_total);
     GSB_CUDA_TRY(cudaSetDevice(ctx->device));
-    if (s->world > 1 && s->pool_waited < s->epoch) {
-        shard_wait_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const volatile uint32_t*>(s->slab + kOffFlags) + kMaxWorld,
-                                                    s->world, s->epoch, s->d_err);
+    const volatile uint32_t* pool_flags = reinterpret_cast<const volatile uint32_t*>(s->slab + kOffFlags) + kMaxWorld;
+    // a pool pushed in two parts is waited for parent by parent inside the splice (and by everybody once more behind it);
+    // otherwise here, as a whole
+    const bool lazy = s->split_now && s->pool_waited < s->epoch;
+    if (s->world > 1 && s->pool_waited < s->epoch && !lazy) {
+        shard_wait_kernel<<<1, 32, 0, ctx->stream>>>(pool_flags, s->world, s->epoch, s->d_err);
         ++ctx->launches;
         s->pool_waited = s->epoch;
     }
+    PoolWait pw;
+    pw.flags = pool_flags; pw.bounds = s->d_bounds; pw.epoch = s->epoch; pw.world = s->world; pw.rank = s->rank; pw.err = s->d_err;
     mark(s, s->epoch, 5);
     uint32_t* h_picks = nullptr;
     if (stage_picks) {
@@ -422,7 +560,14 @@ static int shard_cross_impl(gsb200_shard* s, uint32_t n, uint32_t map, const uin
         GSB_CUDA_TRY(cudaMemcpyAsync(s->h_pin + s->max_total * 16, s->d_sel_ids, (size_t) s->top_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     GSB_TRY(pool_random_cross(ctx, reinterpret_cast<const uint32_t*>(s->slab + s->off_pool), s->top_n, n, map, d_out_rows, first_out_row,
-                              draws, d_picks, what, h_picks, s->ev_picks));
+                              draws, d_picks, what, h_picks, s->ev_picks, lazy ? &pw : nullptr));
+    if (lazy) {
+        // every peer's rows have been seen before anything that follows on this stream: the GEBVs of the next generation
+        // are pushed only after this, which is what lets the peers reuse their buffers without a barrier
+        shard_wait_kernel<<<1, 32, 0, ctx->stream>>>(pool_flags, s->world, s->epoch, s->d_err);
+        ++ctx->launches;
+        s->pool_waited = s->epoch;
+    }
     s->picks_staged = stage_picks;
     s->staged_offspring = n;
     mark(s, s->epoch, 6);

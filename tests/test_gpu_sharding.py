@@ -259,12 +259,18 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(600)
-def test_two_processes_two_gpus_equal_one_rank():
-    """one process per GPU, exchange buffers opened through CUDA IPC, handles carried by torch.distributed"""
+@pytest.mark.parametrize("split_push", [False, True])
+def test_two_processes_two_gpus_equal_one_rank(split_push, monkeypatch):
+    """one process per GPU, exchange buffers opened through CUDA IPC, handles carried by torch.distributed; also with the
+    pool pushed to the peer on a second stream while the splice — gametes sorted, own parents first — waits parent by
+    parent for the rows it needs (an opt-in path, GSB200_SHARD_SPLIT_PUSH, forced here)"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2); the same property is tested in one process above")
     import torch.multiprocessing as mp
     single, cur1 = host_level_threads(1)
+    monkeypatch.setenv("GSB200_SHARD_SPLIT_PUSH", "2" if split_push else "0")       # read once per (spawned) process
+    if split_push:
+        monkeypatch.setenv("GSB200_SORT_GAMETES_MIN_MB", "0")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
