@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
 
     const uint32_t n_gametes = a.n_units * a.gametes_per_unit;      // host keeps this below 2^32
     uint32_t owners_seen = 0;                                        // pool still arriving: the ranks whose rows this warp has seen
+    const uint32_t my_bound = (a.pw.flags && lane < a.pw.world) ? a.pw.bounds[lane] : 0u;
     for (uint32_t gi = blockIdx.x * warps + warp; gi < n_gametes; gi += gridDim.x * warps) {
         const uint32_t g = a.order ? a.order[gi] : gi;           // gametes sorted by parent: neighbouring warps share their source rows
         const uint32_t unit_local = a.gametes_per_unit == 2 ? g >> 1 : g;
@@ -379,14 +380,13 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
         // by lane 0; the other lanes pass the warp barrier after it, so no row load below is issued before the flag was seen.
         // (A __threadfence() here instead cost 15 % of the kernel: it also waits for the warp's own stores of the gamete before.)
         if (a.pw.flags) {
-            uint32_t owner = 0;
-            while (owner + 1 < a.pw.world && src_row >= a.pw.bounds[owner + 1]) ++owner;
+            // lane r holds the first slot of rank r (read once per warp): the owner is the last rank whose first slot is <= src_row
+            const uint32_t owner = (uint32_t) __popc(__ballot_sync(0xffffffffu, lane > 0 && lane < a.pw.world && src_row >= my_bound));
             if (!((owners_seen >> owner) & 1u)) {                  // (warp-uniform: a rank's rows, once here, stay)
                 if (lane == 0 && owner != a.pw.rank) {
                     const long long t0 = clock64();
                     for (;;) {
-                        uint32_t have;
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(a.pw.flags + owner) : "memory");
+                        const uint32_t have = a.pw.flags[owner];          // volatile: read past L1
                         if (have >= a.pw.epoch) break;
                         if (clock64() - t0 > kPoolWaitCycles) { atomicExch(a.pw.err, 1); break; }
                         __nanosleep(200);

@@ -158,30 +158,55 @@ __global__ void __launch_bounds__(256) shard_push_pool_local_kernel(const __grid
 }
 
 // ... and, on a second stream beside the splice, to one peer after the other: rank + 1 first, so that what a rank receives
-// arrives in the order its splice asks for it (gamete_keys_kernel).  ONE launch, all blocks resident at once (the grid is
-// one block per SM): once it has started it needs no further SM slots, whatever spins beside it.
-__global__ void __launch_bounds__(256) shard_push_pool_remote_kernel(const __grid_constant__ Peers P, uint32_t world, uint32_t rank, size_t off_pool,
-                                                                     const uint32_t* __restrict__ bounds /* shard_owner_bounds_kernel */,
-                                                                     uint32_t* counters /* [kMaxWorld], zero */, uint32_t epoch) {
+// arrives in the order its splice asks for it (gamete_keys_kernel).  The copies are bulk-asynchronous (TMA): ONE thread per
+// SM loads 16 KB chunks of my rows into shared memory and stores them to the peer, two chunks in flight — a kernel of
+// ordinary loads and stores beside the splice took its issue slots and both crawled (profiles/r2_split_push.txt).  One launch,
+// one small block per SM, all resident at once: once started it needs no further SM slots, whatever spins beside it.
+constexpr uint32_t kPushChunk = 16384, kPushStages = 2;
+__global__ void __launch_bounds__(32) shard_push_pool_remote_kernel(const __grid_constant__ Peers P, uint32_t world, uint32_t rank, size_t off_pool,
+                                                                    const uint32_t* __restrict__ bounds /* shard_owner_bounds_kernel */,
+                                                                    uint32_t* counters /* [kMaxWorld], zero */, uint32_t epoch) {
+    __shared__ __align__(128) unsigned char s_buf[kPushStages][kPushChunk];
+    __shared__ __align__(8) unsigned long long s_full[kPushStages];
     const uint32_t own_lo = bounds[rank], own_cnt = bounds[rank + 1] - own_lo;
-    const uint4* mine = reinterpret_cast<const uint4*>(P.base[rank] + off_pool) + (uint64_t) own_lo * P.row_u4;
-    const uint64_t total = (uint64_t) own_cnt * P.row_u4, stride = (uint64_t) gridDim.x * blockDim.x;
-    for (uint32_t k = 1; k < world; ++k) {
-        const uint32_t dest = (rank + k) % world;
-        uint4* theirs = reinterpret_cast<uint4*>(P.base[dest] + off_pool) + (uint64_t) own_lo * P.row_u4;
-        for (uint64_t flat = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; flat < total; flat += 4 * stride) {
-            uint4 v[4];                                        // four loads in flight per thread: NVLink's latency x bandwidth wants ~1.5 MB
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (flat + q * stride < total) v[q] = mine[flat + q * stride];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (flat + q * stride < total) theirs[flat + q * stride] = v[q];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0 && atomicAdd(&counters[dest], 1u) == gridDim.x - 1) {
+    const uint64_t row_bytes = (uint64_t) P.row_u4 * 16, total = (uint64_t) own_cnt * row_bytes;       // a multiple of 16
+    const char* mine = P.base[rank] + off_pool + (uint64_t) own_lo * row_bytes;
+    const uint64_t n_chunks = (total + kPushChunk - 1) / kPushChunk;
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < kPushStages; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t) __cvta_generic_to_shared(&s_full[i])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        uint32_t uses[kPushStages] = { 0, 0 };
+        for (uint32_t k = 1; k < world; ++k) {
+            const uint32_t dest = (rank + k) % world;
+            char* theirs = P.base[dest] + off_pool + (uint64_t) own_lo * row_bytes;
+            uint32_t st = 0;
+            for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x, st ^= 1u) {
+                const uint64_t at = c * kPushChunk;
+                const uint32_t bytes = (uint32_t) min((uint64_t) kPushChunk, total - at);
+                const uint32_t buf = (uint32_t) __cvta_generic_to_shared(s_buf[st]), bar = (uint32_t) __cvta_generic_to_shared(&s_full[st]);
+                // the store that read this stage two chunks ago has finished READING it
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(buf), "l"(mine + at), "r"(bytes), "r"(bar) : "memory");
+                uint32_t done = 0;
+                const uint32_t parity = uses[st] & 1u;
+                while (!done)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                ++uses[st];
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(theirs + at), "r"(buf), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // this block's part of the peer's rows is written
+            asm volatile("fence.proxy.async;" ::: "memory");                // ... by the async proxy: ordered before the flag store below
             __threadfence_system();
-            reinterpret_cast<volatile uint32_t*>(P.base[dest] + kOffFlags)[1 * kMaxWorld + rank] = epoch;
-            counters[dest] = 0;
+            if (atomicAdd(&counters[dest], 1u) == gridDim.x - 1) {
+                __threadfence_system();
+                reinterpret_cast<volatile uint32_t*>(P.base[dest] + kOffFlags)[1 * kMaxWorld + rank] = epoch;
+                counters[dest] = 0;
+            }
         }
     }
 }
@@ -470,23 +495,28 @@ static int shard_select_impl(gsb200_shard* s, uint32_t n_local, const uint32_t* 
     // Ranks on different GPUs and enough to send for it to matter (>= 24 MB: the splice then sorts its gametes, own parents first): my rows go into my own pool buffer here, and to
     // the peers on the second stream while the splice is already at work on the parents it has (shard_cross_impl).
     const size_t remote_bytes = (size_t) top_n * s->row_words * sizeof(uint32_t) / s->world * (s->world - 1);
-    // MEASURED AND LEFT OFF (GSB200_SHARD_SPLIT_PUSH=1: from 24 MB to send on, =2: always — the two-GPU test forces it): the
-    // push phase shrinks as intended (N = 4, 100 k offspring per GPU: 0.072 -> 0.025 ms; 1 M-offspring generation: 0.153 ->
-    // 0.041 ms) but the splice beside it takes 0.10 - 0.18 ms longer (0.421 -> 0.526 ms; 1.010 -> 1.188 ms), a net loss of
-    // 0.05 ms per step on 2 and on 4 GPUs (profiles/r2_split_push.txt).
+    // MEASURED AND LEFT OFF (GSB200_SHARD_SPLIT_PUSH=1: from 64 MB to send on, =2: always — the two-GPU test forces it, =3: the
+    // same kernels on one stream): the push phase shrinks as intended (N = 8: 0.145 -> 0.026 ms) but one peer at a time the push
+    // runs at 0.5 TB/s where the all-peers-at-once kernel reaches 0.6 - 0.8, the splice ends up waiting for the last peers'
+    // rows (0.450 -> 0.603 ms) and the step is 0.03 - 0.05 ms SLOWER on 2, 4 and 8 GPUs (profiles/r2_split_push.txt).
     static const int split_mode = [] { const char* v = getenv("GSB200_SHARD_SPLIT_PUSH"); return v ? atoi(v) : 0; }();
-    s->split_now = s->split_ok && ((split_mode == 1 && remote_bytes >= ((size_t) 24 << 20)) || split_mode == 2);
+    s->split_now = s->split_ok && (((split_mode == 1 || split_mode == 3) && remote_bytes >= ((size_t) 64 << 20)) || split_mode == 2);
     if (s->split_now) {
         shard_owner_bounds_kernel<<<1, 32, 0, ctx->stream>>>(s->d_sel, top_n, n_total, s->world, s->d_bounds);
         shard_push_pool_local_kernel<<<(unsigned) ctx->sm_count * 2, 256, 0, ctx->stream>>>(
             s->peers, s->rank, s->off_ids, s->off_pool, ctx->d_store, s->row_words, d_local_rows, (uint32_t) lo,
             (const SelectState*) ctx->s_select.ptr, s->d_sel, top_n, s->d_sel_ids, with_ids, s->d_counters + 1, epoch);
-        GSB_CUDA_TRY(cudaEventRecord(s->ev_selected, ctx->stream));
-        GSB_CUDA_TRY(cudaStreamWaitEvent(s->side, s->ev_selected, 0));
-        shard_push_pool_remote_kernel<<<(unsigned) ctx->sm_count, 256, 0, s->side>>>(
-            s->peers, s->world, s->rank, s->off_pool, s->d_bounds, s->d_push_counters, epoch);
-        GSB_CUDA_TRY(cudaEventRecord(s->ev_pushed, s->side));
-        s->push_outstanding = true;
+        if (split_mode == 3) {          // measurement: the same kernels, one after the other on one stream
+            shard_push_pool_remote_kernel<<<(unsigned) ctx->sm_count, 32, 0, ctx->stream>>>(
+                s->peers, s->world, s->rank, s->off_pool, s->d_bounds, s->d_push_counters, epoch);
+        } else {
+            GSB_CUDA_TRY(cudaEventRecord(s->ev_selected, ctx->stream));
+            GSB_CUDA_TRY(cudaStreamWaitEvent(s->side, s->ev_selected, 0));
+            shard_push_pool_remote_kernel<<<(unsigned) ctx->sm_count, 32, 0, s->side>>>(
+                s->peers, s->world, s->rank, s->off_pool, s->d_bounds, s->d_push_counters, epoch);
+            GSB_CUDA_TRY(cudaEventRecord(s->ev_pushed, s->side));
+            s->push_outstanding = true;
+        }
         ctx->launches += 3;
     } else {
         shard_push_pool_kernel<<<(unsigned) ctx->sm_count * 4, 256, 0, ctx->stream>>>(
