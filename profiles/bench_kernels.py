@@ -83,11 +83,11 @@ def main():
     t = timeit(lambda: chk(E.gsb200_store_download_chars(ctx, n_io, ptr(out), ptr(chars))), reps=3)
     line("gsb200_store_download_chars 2k x 50k", t, (n_io, "genotypes"), n_io * (M / 4 + 2 * M), "(PCIe-bound)")
     t = timeit(lambda: chk(E.gsb200_store_upload_chars(ctx, n_io, ptr(out2), ptr(chars))), reps=3)
-    line("gsb200_store_upload_chars 2k x 50k", t, (n_io, "genotypes"), n_io * (M / 4 + 2 * M), "(host dictionary scan + PCIe)")
+    line("gsb200_store_upload_chars 2k x 50k", t, (n_io, "genotypes"), n_io * (M / 4 + 2 * M), "(pageable host buffer: staging copy + PCIe; dictionary built on the device; pinned: profiles/r2_chars_boundary.txt)")
     vals = rng.standard_normal(1000000)
     pos = np.zeros(10000, dtype=np.uint32)
     t = timeit(lambda: chk(E.gsb200_top_n(ctx, len(vals), ptr(vals), len(pos), 0, ptr(pos))))
-    line("gsb200_top_n 1M -> top 1%", t, (len(vals), "values"), len(vals) * 8)
+    line("gsb200_top_n 1M -> top 1% (host values)", t, (len(vals), "values"), len(vals) * 8, "(8 MB of values go up first; the selection itself is 0.07 ms per 1 M, bench.py config3_1gpu select_ms)")
     print("\n".join(rows))
     sim.close()
 
