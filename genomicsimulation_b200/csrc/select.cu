@@ -18,6 +18,11 @@
 #include "gsb200_internal.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace gsb {
 
@@ -249,6 +254,175 @@ __global__ void __launch_bounds__(kSweepThreads) select_scatter_kernel(const dou
     }
 }
 
+
+// ---- the same selection as ONE cooperative kernel ------------------------------------------------------------------------
+// The seven launches above are 3-9 us each and the work between them is a few microseconds: at 100 k - 1 M values the
+// selection is launch-latency-bound.  Here one grid of at most one block per SM walks the same phases with grid-wide
+// barriers in between: three histogram sweeps over the block's contiguous slice (every block then scans the 2048 global
+// bins for itself: no "last block" and no second barrier per pass), the last three digits from the candidate keys (every
+// block for itself while they are few), per-block counts, and the ordered scatter.  Same result, bit for bit.
+constexpr int kFusedThreads = 512;
+constexpr uint32_t kFusedMinPerBlock = 1024;       // values per block below which more blocks only add barrier cost
+constexpr uint32_t kRedundantCand = 16384;         // up to here every block resolves the candidates itself
+
+// s_hist[0 .. bins) holds counts; the bin in which the running count reaches `remaining`: prefix is extended by it and
+// remaining reduced by the count before it.  All threads of the block call this; all return the same values.
+__device__ __forceinline__ void fused_find_bin(const uint32_t* s_hist, uint32_t* s_warp, uint32_t* s_out, uint32_t bins, int width,
+                                               unsigned long long& prefix, uint32_t& remaining) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t per = (bins + kFusedThreads - 1) / kFusedThreads;              // 4 or 1 consecutive bins per thread
+    uint32_t mine = 0;
+    for (uint32_t j = 0; j < per; ++j) if (threadIdx.x * per + j < bins) mine += s_hist[threadIdx.x * per + j];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int) lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    for (uint32_t w = 0; w < warp; ++w) incl += s_warp[w];
+    const uint32_t excl = incl - mine;
+    if (excl < remaining && remaining <= incl) {               // exactly one thread
+        uint32_t before = excl;
+        for (uint32_t j = 0; j < per; ++j) {
+            const uint32_t v = s_hist[threadIdx.x * per + j];
+            if (remaining <= before + v) { s_out[0] = threadIdx.x * per + j; s_out[1] = before; break; }
+            before += v;
+        }
+    }
+    __syncthreads();
+    prefix = (prefix << width) | s_out[0];
+    remaining -= s_out[1];
+    __syncthreads();                                           // s_hist, s_warp and s_out are free again
+}
+
+__global__ void __launch_bounds__(kFusedThreads) select_fused_kernel(const double* __restrict__ values, uint32_t n, int low_is_best, uint32_t top_n,
+                                                                     SelectState* state, uint32_t* hist /* [3][kBins], zeroed */,
+                                                                     uint32_t* n_cand /* zeroed */, unsigned long long* cand,
+                                                                     uint2* block_counts /* [gridDim.x] */, uint32_t* __restrict__ sel,
+                                                                     uint32_t own_lo_pos, uint32_t own_hi_pos) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t s_hist[kBins];
+    __shared__ uint32_t s_warp[kFusedThreads / 32];
+    __shared__ uint2 s_warp2[kFusedThreads / 32];
+    __shared__ uint32_t s_out[2];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = min(n, blockIdx.x * chunk), hi = min(n, lo + chunk);      // this block's slice, the same in every phase
+    unsigned long long prefix = 0;
+    uint32_t remaining = top_n;
+
+    constexpr int kSweeps = 3;
+    for (int pass = 0; pass < kSweeps; ++pass) {
+        const int width = pass_width(pass), shift = pass_shift(pass);
+        const uint32_t bins = 1u << width;
+        for (uint32_t b = threadIdx.x; b < bins; b += kFusedThreads) s_hist[b] = 0;
+        __syncthreads();
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += kFusedThreads) {
+            const unsigned long long k = rank_key(values[i], low_is_best);
+            if (pass == 0 || (k >> (shift + width)) == prefix) {
+                atomicAdd(&s_hist[(uint32_t) (k >> shift) & (bins - 1)], 1u);
+                if (pass == kSweeps - 1) cand[atomicAdd(n_cand, 1u)] = k;
+            }
+        }
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < bins; b += kFusedThreads) if (s_hist[b]) atomicAdd(&hist[pass * kBins + b], s_hist[b]);
+        grid.sync();
+        for (uint32_t b = threadIdx.x; b < bins; b += kFusedThreads) s_hist[b] = __ldcg(&hist[pass * kBins + b]);
+        __syncthreads();
+        fused_find_bin(s_hist, s_warp, s_out, bins, width, prefix, remaining);
+    }
+
+    // the last three digits, over the keys that match the 33 bits known by now
+    const uint32_t nc = __ldcg(n_cand);
+    const bool everyone = nc <= kRedundantCand;               // (the same answer in every block)
+    if (everyone || blockIdx.x == 0) {
+        for (int pass = kSweeps; pass < kPasses; ++pass) {
+            const int width = pass_width(pass), shift = pass_shift(pass);
+            const uint32_t bins = 1u << width;
+            for (uint32_t b = threadIdx.x; b < bins; b += kFusedThreads) s_hist[b] = 0;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < nc; i += kFusedThreads) {
+                const unsigned long long k = __ldcg(&cand[i]);
+                if ((k >> (shift + width)) == prefix) atomicAdd(&s_hist[(uint32_t) (k >> shift) & (bins - 1)], 1u);
+            }
+            __syncthreads();
+            fused_find_bin(s_hist, s_warp, s_out, bins, width, prefix, remaining);
+        }
+    }
+    if (!everyone) {                                          // many ties (e.g. a generation of identical values): block 0 tells the others
+        if (blockIdx.x == 0 && threadIdx.x == 0) { state->prefix = prefix; state->remaining = remaining; }
+        grid.sync();
+        prefix = __ldcg(&state->prefix);
+        remaining = __ldcg(&state->remaining);
+    }
+    const unsigned long long T = prefix;
+    const uint32_t ties = remaining;
+
+    // how many better / tied keys my slice holds
+    {
+        uint32_t less = 0, eq = 0;
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += kFusedThreads) {
+            const unsigned long long k = rank_key(values[i], low_is_best);
+            less += k < T;
+            eq += k == T;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { less += __shfl_xor_sync(0xffffffffu, less, o); eq += __shfl_xor_sync(0xffffffffu, eq, o); }
+        if (lane == 0) s_warp2[warp] = make_uint2(less, eq);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint2 t = make_uint2(0, 0);
+            for (int w = 0; w < kFusedThreads / 32; ++w) { t.x += s_warp2[w].x; t.y += s_warp2[w].y; }
+            block_counts[blockIdx.x] = t;
+            if (blockIdx.x == 0) {
+                state->prefix = T; state->remaining = ties; state->done_blocks = 0;
+                state->own_lo = own_lo_pos >= n ? top_n : 0u; state->own_hi = top_n;
+            }
+        }
+    }
+    grid.sync();
+    uint32_t lb = 0, eb = 0;                                  // better / tied keys at positions before my slice
+    if (warp == 0) {
+        for (uint32_t j = lane; j < blockIdx.x; j += 32) { const uint2 c = __ldcg(&block_counts[j]); lb += c.x; eb += c.y; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lb += __shfl_xor_sync(0xffffffffu, lb, o); eb += __shfl_xor_sync(0xffffffffu, eb, o); }
+        if (lane == 0) { s_out[0] = lb; s_out[1] = eb; }
+    }
+    __syncthreads();
+    lb = s_out[0]; eb = s_out[1];
+    __syncthreads();
+
+    // selected positions, ascending: key < T, or key == T and fewer than `ties` ties before it
+    for (uint32_t base = lo; base < hi; base += kFusedThreads) {
+        const uint32_t i = base + threadIdx.x;
+        const bool valid = i < hi;
+        const unsigned long long k = valid ? rank_key(values[i], low_is_best) : ~0ull;
+        const bool is_less = valid && k < T, is_eq = valid && k == T;
+        const uint32_t bl = __ballot_sync(0xffffffffu, is_less), be = __ballot_sync(0xffffffffu, is_eq);
+        if (lane == 0) s_warp2[warp] = make_uint2(__popc(bl), __popc(be));
+        __syncthreads();
+        uint32_t l_before = lb + __popc(bl & ((1u << lane) - 1u)), e_before = eb + __popc(be & ((1u << lane) - 1u));
+        uint32_t l_all = 0, e_all = 0;
+#pragma unroll
+        for (int w = 0; w < kFusedThreads / 32; ++w) {
+            const uint2 c = s_warp2[w];
+            if ((uint32_t) w < warp) { l_before += c.x; e_before += c.y; }
+            l_all += c.x; e_all += c.y;
+        }
+        if (valid) {
+            const uint32_t pos = l_before + min(e_before, ties);            // selected individuals before position i
+            if (i == own_lo_pos) state->own_lo = pos;
+            if (i == own_hi_pos) state->own_hi = pos;
+            if (is_less) sel[pos] = i;
+            else if (is_eq && e_before < ties) sel[pos] = i;
+        }
+        lb += l_all; eb += e_all;
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 size_t select_scratch_bytes(uint32_t n) {
@@ -271,6 +445,22 @@ int select_top_n(gsb200_ctx* ctx, const double* d_values, uint32_t n, uint32_t t
     char* after_tiles = (char*) scratch + ((sizeof(SelectState) + (size_t) kPasses * kBins * sizeof(uint32_t) + (size_t) n_tiles * sizeof(uint2) + 255) & ~(size_t) 255);
     uint32_t* n_cand = (uint32_t*) after_tiles;
     unsigned long long* cand = (unsigned long long*) (after_tiles + 16);
+    // one cooperative kernel (default); GSB200_SELECT_PATH=multi keeps the seven-launch form for comparison
+    static const bool multi = [] { const char* v = getenv("GSB200_SELECT_PATH"); return v && !strcmp(v, "multi"); }();
+    if (!multi) {
+        GSB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(SelectState) + (size_t) 4 * kBins * sizeof(uint32_t), ctx->stream));
+        const double* a_values = d_values;
+        uint32_t a_n = n, a_top = top_n, a_lo = own_lo_pos, a_hi = own_hi_pos;
+        int a_low = low_is_best;
+        uint32_t* a_hist = hist;
+        uint32_t* a_ncand = hist + 3 * kBins;                  // the sweeps use three of the six histograms: the counter and
+        uint2* a_counts = (uint2*) (hist + 4 * kBins);         // the per-block counts live in the others
+        void* args[] = {&a_values, &a_n, &a_low, &a_top, &state, &a_hist, &a_ncand, &cand, &a_counts, &d_sel, &a_lo, &a_hi};
+        const uint32_t blocks = std::max(1u, std::min<uint32_t>((n + kFusedMinPerBlock - 1) / kFusedMinPerBlock, (uint32_t) ctx->sm_count));
+        GSB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*) select_fused_kernel, dim3(blocks), dim3(kFusedThreads), args, 0, ctx->stream));
+        ctx->launches += 1;
+        return GSB200_OK;
+    }
     GSB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(SelectState) + (size_t) kPasses * kBins * sizeof(uint32_t), ctx->stream));
     GSB_CUDA_TRY(cudaMemsetAsync(n_cand, 0, sizeof(uint32_t), ctx->stream));
     const uint32_t grid = (uint32_t) std::min<uint64_t>(((uint64_t) n + kHistThreads * 4 - 1) / (kHistThreads * 4), (uint64_t) ctx->sm_count * 8);

@@ -265,6 +265,11 @@ struct gsb200_shard {
     // pinned host staging, so that what the host mirror needs of a generation (local GEBVs, the picked pairs, the
     // selected parents' ids) comes down while the device carries on: [bvs: max_total f64 | picks: 2 max_total u32 | sel ids: max_pool u32]
     char* h_pin = nullptr;
+    // ids on their way up: two pinned buffers in turn (a copy from pageable memory would make cudaMemcpyAsync wait for
+    // everything queued before it, i.e. for the previous generation's splice and this generation's GEBVs)
+    uint32_t* h_ids[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ids[2] = {nullptr, nullptr};
+    bool ids_in_flight[2] = {false, false};
     cudaEvent_t ev_bv = nullptr, ev_picks = nullptr, ev_flags = nullptr;
     int* h_flags = nullptr;              // pinned: [0] the shard's exchange flag, [1] the context's splice flag, as of the last poll
     bool poll_pending = false;
@@ -315,6 +320,10 @@ int gsb200_shard_create(gsb200_ctx* ctx, uint32_t rank, uint32_t world, uint64_t
     if (e == cudaSuccess) e = cudaMemset(s->d_err, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**) &s->d_sel, 2 * (size_t) max_pool * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaHostAlloc((void**) &s->h_pin, max_total * 16 + (size_t) max_pool * 4, cudaHostAllocDefault);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaHostAlloc((void**) &s->h_ids[k], max_total * sizeof(uint32_t), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_ids[k], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_bv, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_picks, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_flags, cudaEventDisableTiming);
@@ -372,6 +381,7 @@ void gsb200_shard_destroy(gsb200_shard* s) {
     s->s_local_rows.release();
     if (s->ev_made) for (auto& set : s->ev) for (auto& e : set) cudaEventDestroy(e);
     if (s->h_pin) cudaFreeHost(s->h_pin);
+    for (int k = 0; k < 2; ++k) { if (s->h_ids[k]) cudaFreeHost(s->h_ids[k]); if (s->ev_ids[k]) cudaEventDestroy(s->ev_ids[k]); }
     if (s->ev_bv) cudaEventDestroy(s->ev_bv);
     if (s->ev_picks) cudaEventDestroy(s->ev_picks);
     if (s->ev_flags) cudaEventDestroy(s->ev_flags);
@@ -478,9 +488,15 @@ static int shard_select_impl(gsb200_shard* s, uint32_t n_local, const uint32_t* 
         s->staged_local = n_local;
     }
     const int with_ids = local_ids != nullptr;
-    if (with_ids && n_local)
-        GSB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(s->slab + s->off_ids) + lo, local_ids, (size_t) n_local * sizeof(uint32_t),
+    if (with_ids && n_local) {
+        const int b = (int) (epoch & 1u);
+        if (s->ids_in_flight[b]) GSB_CUDA_TRY(cudaEventSynchronize(s->ev_ids[b]));      // two generations ago: long done
+        memcpy(s->h_ids[b], local_ids, (size_t) n_local * sizeof(uint32_t));
+        GSB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(s->slab + s->off_ids) + lo, s->h_ids[b], (size_t) n_local * sizeof(uint32_t),
                                      cudaMemcpyHostToDevice, ctx->stream));
+        GSB_CUDA_TRY(cudaEventRecord(s->ev_ids[b], ctx->stream));
+        s->ids_in_flight[b] = true;
+    }
     mark(s, epoch, 1);
     if (s->world > 1) {
         const unsigned grid = (unsigned) std::max<uint32_t>(1, std::min<uint32_t>((n_local + 255) / 256, (uint32_t) ctx->sm_count * 2));
