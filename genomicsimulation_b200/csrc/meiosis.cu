@@ -1182,7 +1182,7 @@ namespace gsb {
 
 int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_pool, uint32_t n, uint32_t map,
                       const uint32_t* d_out_rows, uint32_t first_out_row, const gsb200_draws* draws, uint32_t* d_picks,
-                      const char* what, uint32_t* h_picks, cudaEvent_t picks_ready, const PoolWait* pw) {
+                      const char* what, uint32_t* h_picks, cudaEvent_t picks_ready, const PoolWait* pw, cudaStream_t copy_stream, cudaEvent_t fork) {
     if (n == 0) return GSB200_OK;
     GSB_REQUIRE(n_pool >= 2, GSB200_ERR_ARG, "%s: a pool of %u cannot be crossed at random", what, n_pool);
     GSB_REQUIRE(draws && draws->mode == GSB200_DRAWS_PHILOX, GSB200_ERR_ARG, "%s: needs PHILOX draws", what);
@@ -1199,8 +1199,15 @@ int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_poo
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
     if (h_picks && d_picks) {      // the picks leave before the splice is enqueued: the host has them while the offspring are being made
-        GSB_CUDA_TRY(cudaMemcpyAsync(h_picks, d_picks, (size_t) 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        if (picks_ready) GSB_CUDA_TRY(cudaEventRecord(picks_ready, ctx->stream));
+        if (copy_stream && fork && picks_ready) {      // on a stream of its own: the splice does not wait for the copy
+            GSB_CUDA_TRY(cudaEventRecord(fork, ctx->stream));
+            GSB_CUDA_TRY(cudaStreamWaitEvent(copy_stream, fork, 0));
+            GSB_CUDA_TRY(cudaMemcpyAsync(h_picks, d_picks, (size_t) 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, copy_stream));
+            GSB_CUDA_TRY(cudaEventRecord(picks_ready, copy_stream));
+        } else {
+            GSB_CUDA_TRY(cudaMemcpyAsync(h_picks, d_picks, (size_t) 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            if (picks_ready) GSB_CUDA_TRY(cudaEventRecord(picks_ready, ctx->stream));
+        }
     }
     // A pool that no longer fits L2 beside the offspring stream (configs[2]: 10 000 parents = 125 MB) is re-read ~200 times
     // per generation; left to LRU it is flushed by the 12.5 GB the same kernel writes.  Part of L2 is therefore set aside
@@ -1238,6 +1245,8 @@ int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_poo
         attr.accessPolicyWindow.num_bytes = 0;
         GSB_CUDA_TRY(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     }
+    // joined behind the splice: whatever comes next on the context stream may reuse the picks' scratch
+    if (h_picks && d_picks && copy_stream && fork && picks_ready) GSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, picks_ready, 0));
     return st;
 }
 

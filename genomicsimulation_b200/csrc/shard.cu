@@ -270,6 +270,10 @@ struct gsb200_shard {
     uint32_t* h_ids[2] = {nullptr, nullptr};
     cudaEvent_t ev_ids[2] = {nullptr, nullptr};
     bool ids_in_flight[2] = {false, false};
+    // host copies (ids up; GEBVs and picks down) ride a stream of their own, forked from and joined to the context stream
+    // by events: on the context stream each would sit between two kernels for the 10 - 30 us it takes
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_fork[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_bv = nullptr, ev_picks = nullptr, ev_flags = nullptr;
     int* h_flags = nullptr;              // pinned: [0] the shard's exchange flag, [1] the context's splice flag, as of the last poll
     bool poll_pending = false;
@@ -320,6 +324,8 @@ int gsb200_shard_create(gsb200_ctx* ctx, uint32_t rank, uint32_t world, uint64_t
     if (e == cudaSuccess) e = cudaMemset(s->d_err, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**) &s->d_sel, 2 * (size_t) max_pool * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaHostAlloc((void**) &s->h_pin, max_total * 16 + (size_t) max_pool * 4, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking);
+    for (int k = 0; k < 3 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&s->ev_fork[k], cudaEventDisableTiming);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
         e = cudaHostAlloc((void**) &s->h_ids[k], max_total * sizeof(uint32_t), cudaHostAllocDefault);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_ids[k], cudaEventDisableTiming);
@@ -374,6 +380,8 @@ void gsb200_shard_destroy(gsb200_shard* s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); }
+    if (s->copy) { cudaStreamSynchronize(s->copy); cudaStreamDestroy(s->copy); }
+    for (int k = 0; k < 3; ++k) if (s->ev_fork[k]) cudaEventDestroy(s->ev_fork[k]);
     if (s->ev_selected) cudaEventDestroy(s->ev_selected);
     if (s->ev_pushed) cudaEventDestroy(s->ev_pushed);
     if (s->d_bounds) cudaFree(s->d_bounds);
@@ -478,25 +486,31 @@ static int shard_select_impl(gsb200_shard* s, uint32_t n_local, const uint32_t* 
         s->push_outstanding = false;
     }
     double* all_bv = reinterpret_cast<double*>(s->slab + kOffBv);
+    const int with_ids = local_ids != nullptr;
+    if (with_ids && n_local) {
+        // behind everything queued so far (the previous generation's readers of the id column), beside this generation's GEBVs
+        const int b = (int) (epoch & 1u);
+        if (s->ids_in_flight[b]) GSB_CUDA_TRY(cudaEventSynchronize(s->ev_ids[b]));      // two generations ago: long done
+        memcpy(s->h_ids[b], local_ids, (size_t) n_local * sizeof(uint32_t));
+        GSB_CUDA_TRY(cudaEventRecord(s->ev_fork[0], ctx->stream));
+        GSB_CUDA_TRY(cudaStreamWaitEvent(s->copy, s->ev_fork[0], 0));
+        GSB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(s->slab + s->off_ids) + lo, s->h_ids[b], (size_t) n_local * sizeof(uint32_t),
+                                     cudaMemcpyHostToDevice, s->copy));
+        GSB_CUDA_TRY(cudaEventRecord(s->ev_ids[b], s->copy));
+        s->ids_in_flight[b] = true;
+    }
     mark(s, epoch, 0);
     if (n_local) GSB_TRY(gsb200_gebv_dev(ctx, n_local, d_local_rows, eff_index, all_bv + lo));
     if (d_local_rows == (const uint32_t*) s->s_local_rows.ptr) {
         // the host-row entry point: this rank's GEBVs start their way down now, behind nothing but the GEBV kernels
-        if (n_local) GSB_CUDA_TRY(cudaMemcpyAsync(s->h_pin, all_bv + lo, (size_t) n_local * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        GSB_CUDA_TRY(cudaEventRecord(s->ev_bv, ctx->stream));
+        GSB_CUDA_TRY(cudaEventRecord(s->ev_fork[1], ctx->stream));
+        GSB_CUDA_TRY(cudaStreamWaitEvent(s->copy, s->ev_fork[1], 0));
+        if (n_local) GSB_CUDA_TRY(cudaMemcpyAsync(s->h_pin, all_bv + lo, (size_t) n_local * sizeof(double), cudaMemcpyDeviceToHost, s->copy));
+        GSB_CUDA_TRY(cudaEventRecord(s->ev_bv, s->copy));
         s->bv_staged = true;
         s->staged_local = n_local;
     }
-    const int with_ids = local_ids != nullptr;
-    if (with_ids && n_local) {
-        const int b = (int) (epoch & 1u);
-        if (s->ids_in_flight[b]) GSB_CUDA_TRY(cudaEventSynchronize(s->ev_ids[b]));      // two generations ago: long done
-        memcpy(s->h_ids[b], local_ids, (size_t) n_local * sizeof(uint32_t));
-        GSB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(s->slab + s->off_ids) + lo, s->h_ids[b], (size_t) n_local * sizeof(uint32_t),
-                                     cudaMemcpyHostToDevice, ctx->stream));
-        GSB_CUDA_TRY(cudaEventRecord(s->ev_ids[b], ctx->stream));
-        s->ids_in_flight[b] = true;
-    }
+    if (with_ids && n_local) GSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_ids[epoch & 1u], 0));      // the ids are up (sent while the GEBVs were computed)
     mark(s, epoch, 1);
     if (s->world > 1) {
         const unsigned grid = (unsigned) std::max<uint32_t>(1, std::min<uint32_t>((n_local + 255) / 256, (uint32_t) ctx->sm_count * 2));
@@ -541,6 +555,7 @@ static int shard_select_impl(gsb200_shard* s, uint32_t n_local, const uint32_t* 
         ++ctx->launches;
     }
     GSB_CUDA_TRY(cudaGetLastError());
+    if (s->bv_staged) GSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_bv, 0));      // joined: nothing later overwrites GEBVs still on their way down
     mark(s, epoch, 4);
     s->n_total = n_total;
     s->top_n = top_n;
@@ -606,7 +621,7 @@ static int shard_cross_impl(gsb200_shard* s, uint32_t n, uint32_t map, const uin
         GSB_CUDA_TRY(cudaMemcpyAsync(s->h_pin + s->max_total * 16, s->d_sel_ids, (size_t) s->top_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     GSB_TRY(pool_random_cross(ctx, reinterpret_cast<const uint32_t*>(s->slab + s->off_pool), s->top_n, n, map, d_out_rows, first_out_row,
-                              draws, d_picks, what, h_picks, s->ev_picks, lazy ? &pw : nullptr));
+                              draws, d_picks, what, h_picks, s->ev_picks, lazy ? &pw : nullptr, s->copy, s->ev_fork[2]));
     if (lazy) {
         // every peer's rows have been seen before anything that follows on this stream: the GEBVs of the next generation
         // are pushed only after this, which is what lets the peers reuse their buffers without a barrier
