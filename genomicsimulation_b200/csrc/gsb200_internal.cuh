@@ -230,6 +230,6 @@ struct PoolWait {
 int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_pool, uint32_t n, uint32_t map,
                       const uint32_t* d_out_rows, uint32_t first_out_row, const gsb200_draws* draws, uint32_t* d_picks,
                       const char* what, uint32_t* h_picks = nullptr /* pinned, 2n: copy of d_picks */, cudaEvent_t picks_ready = nullptr,
-                      const PoolWait* pw = nullptr, cudaStream_t copy_stream = nullptr /* the picks go down on it, beside the splice */,
-                      cudaEvent_t fork = nullptr);
+                      const PoolWait* pw = nullptr, cudaStream_t side_stream = nullptr /* pairs and picks: beside what is queued in front */,
+                      cudaEvent_t side_may_start = nullptr, cudaEvent_t pairs_done = nullptr);
 }  // namespace gsb

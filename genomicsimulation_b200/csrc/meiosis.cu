@@ -1182,32 +1182,39 @@ namespace gsb {
 
 int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_pool, uint32_t n, uint32_t map,
                       const uint32_t* d_out_rows, uint32_t first_out_row, const gsb200_draws* draws, uint32_t* d_picks,
-                      const char* what, uint32_t* h_picks, cudaEvent_t picks_ready, const PoolWait* pw, cudaStream_t copy_stream, cudaEvent_t fork) {
+                      const char* what, uint32_t* h_picks, cudaEvent_t picks_ready, const PoolWait* pw, cudaStream_t side_stream, cudaEvent_t side_may_start,
+                      cudaEvent_t pairs_done) {
     if (n == 0) return GSB200_OK;
     GSB_REQUIRE(n_pool >= 2, GSB200_ERR_ARG, "%s: a pool of %u cannot be crossed at random", what, n_pool);
     GSB_REQUIRE(draws && draws->mode == GSB200_DRAWS_PHILOX, GSB200_ERR_ARG, "%s: needs PHILOX draws", what);
     GSB_REQUIRE(n < (1u << 31), GSB200_ERR_ARG, "%s: too many offspring in one call", what);
     GSB_REQUIRE(d_out_rows || (uint64_t) first_out_row + n <= ctx->capacity, GSB200_ERR_ARG, "%s: offspring rows beyond the store capacity", what);
     // s_rows[3]: parent 1 | parent 2 | offspring rows (when they are a contiguous run)
+    const void* scratch_before = ctx->s_rows[3].ptr;
     GSB_TRY(ctx->s_rows[3].ensure((size_t) 4 * n * sizeof(uint32_t)));
     uint32_t* d_p1 = (uint32_t*) ctx->s_rows[3].ptr;
     uint32_t *d_p2 = d_p1 + n, *d_run = d_p2 + n;
     DrawView dv;
     GSB_TRY(make_draw_view(draws, &dv, what));
-    random_pairs_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, 1, nullptr, n_pool, nullptr, n_pool, 1u, dv, first_out_row, d_p1, d_p2,
-                                                                   d_picks, d_picks ? d_picks + n : nullptr, d_out_rows ? nullptr : d_run);
+    // The pairs depend on the seed, the stream position and the SIZE of the pool only — not on who was selected — so with a side
+    // stream they are drawn (and the picks sent down) as soon as the caller's event says the scratch is free: beside the
+    // evaluation and selection queued in front of this call on the context stream, not behind them.  (Scratch that has just
+    // been re-allocated on the context stream is not visible to another stream yet: then everything stays in line.)
+    const bool early = side_stream && side_may_start && pairs_done && scratch_before == ctx->s_rows[3].ptr;
+    cudaStream_t ps = early ? side_stream : ctx->stream;
+    if (early) GSB_CUDA_TRY(cudaStreamWaitEvent(side_stream, side_may_start, 0));
+    random_pairs_kernel<<<grid_for(n, 256), 256, 0, ps>>>(n, 1, nullptr, n_pool, nullptr, n_pool, 1u, dv, first_out_row, d_p1, d_p2,
+                                                          d_picks, d_picks ? d_picks + n : nullptr, d_out_rows ? nullptr : d_run);
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
-    if (h_picks && d_picks) {      // the picks leave before the splice is enqueued: the host has them while the offspring are being made
-        if (copy_stream && fork && picks_ready) {      // on a stream of its own: the splice does not wait for the copy
-            GSB_CUDA_TRY(cudaEventRecord(fork, ctx->stream));
-            GSB_CUDA_TRY(cudaStreamWaitEvent(copy_stream, fork, 0));
-            GSB_CUDA_TRY(cudaMemcpyAsync(h_picks, d_picks, (size_t) 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, copy_stream));
-            GSB_CUDA_TRY(cudaEventRecord(picks_ready, copy_stream));
-        } else {
-            GSB_CUDA_TRY(cudaMemcpyAsync(h_picks, d_picks, (size_t) 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-            if (picks_ready) GSB_CUDA_TRY(cudaEventRecord(picks_ready, ctx->stream));
-        }
+    if (early) {
+        GSB_CUDA_TRY(cudaEventRecord(pairs_done, side_stream));
+        GSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, pairs_done, 0));
+    }
+    const bool picks_down = h_picks && d_picks;
+    if (picks_down) {      // the picks leave before the splice is enqueued: the host has them while the offspring are being made
+        GSB_CUDA_TRY(cudaMemcpyAsync(h_picks, d_picks, (size_t) 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ps));
+        if (picks_ready) GSB_CUDA_TRY(cudaEventRecord(picks_ready, ps));
     }
     // A pool that no longer fits L2 beside the offspring stream (configs[2]: 10 000 parents = 125 MB) is re-read ~200 times
     // per generation; left to LRU it is flushed by the 12.5 GB the same kernel writes.  Part of L2 is therefore set aside
@@ -1246,7 +1253,7 @@ int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_poo
         GSB_CUDA_TRY(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     }
     // joined behind the splice: whatever comes next on the context stream may reuse the picks' scratch
-    if (h_picks && d_picks && copy_stream && fork && picks_ready) GSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, picks_ready, 0));
+    if (early && picks_down && picks_ready) GSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, picks_ready, 0));
     return st;
 }
 

@@ -274,7 +274,9 @@ struct gsb200_shard {
     // by events: on the context stream each would sit between two kernels for the 10 - 30 us it takes
     cudaStream_t copy = nullptr;
     cudaEvent_t ev_fork[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_bv = nullptr, ev_picks = nullptr, ev_flags = nullptr;
+    uint32_t crosses_since_select = 0;     // only the first cross of a selection may start its pair draws early (ev_fork[0] is its licence)
+    bool picks_scratch_moved = false;
+    cudaEvent_t ev_bv = nullptr, ev_picks = nullptr, ev_flags = nullptr, ev_sel_ids = nullptr;
     int* h_flags = nullptr;              // pinned: [0] the shard's exchange flag, [1] the context's splice flag, as of the last poll
     bool poll_pending = false;
     bool bv_staged = false, picks_staged = false;
@@ -332,6 +334,7 @@ int gsb200_shard_create(gsb200_ctx* ctx, uint32_t rank, uint32_t world, uint64_t
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_bv, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_picks, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_sel_ids, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_flags, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaHostAlloc((void**) &s->h_flags, 2 * sizeof(int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**) &s->d_bounds, (kMaxWorld + 1 + kMaxWorld) * sizeof(uint32_t));
@@ -392,6 +395,7 @@ void gsb200_shard_destroy(gsb200_shard* s) {
     for (int k = 0; k < 2; ++k) { if (s->h_ids[k]) cudaFreeHost(s->h_ids[k]); if (s->ev_ids[k]) cudaEventDestroy(s->ev_ids[k]); }
     if (s->ev_bv) cudaEventDestroy(s->ev_bv);
     if (s->ev_picks) cudaEventDestroy(s->ev_picks);
+    if (s->ev_sel_ids) cudaEventDestroy(s->ev_sel_ids);
     if (s->ev_flags) cudaEventDestroy(s->ev_flags);
     if (s->h_flags) cudaFreeHost(s->h_flags);
     if (s->slab) cudaFree(s->slab);
@@ -487,12 +491,14 @@ static int shard_select_impl(gsb200_shard* s, uint32_t n_local, const uint32_t* 
     }
     double* all_bv = reinterpret_cast<double*>(s->slab + kOffBv);
     const int with_ids = local_ids != nullptr;
+    // "everything queued so far is done": what the copy stream waits for before it touches anything the previous generation used
+    GSB_CUDA_TRY(cudaEventRecord(s->ev_fork[0], ctx->stream));
+    s->crosses_since_select = 0;
     if (with_ids && n_local) {
         // behind everything queued so far (the previous generation's readers of the id column), beside this generation's GEBVs
         const int b = (int) (epoch & 1u);
         if (s->ids_in_flight[b]) GSB_CUDA_TRY(cudaEventSynchronize(s->ev_ids[b]));      // two generations ago: long done
         memcpy(s->h_ids[b], local_ids, (size_t) n_local * sizeof(uint32_t));
-        GSB_CUDA_TRY(cudaEventRecord(s->ev_fork[0], ctx->stream));
         GSB_CUDA_TRY(cudaStreamWaitEvent(s->copy, s->ev_fork[0], 0));
         GSB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(s->slab + s->off_ids) + lo, s->h_ids[b], (size_t) n_local * sizeof(uint32_t),
                                      cudaMemcpyHostToDevice, s->copy));
@@ -616,12 +622,17 @@ static int shard_cross_impl(gsb200_shard* s, uint32_t n, uint32_t map, const uin
     pw.flags = pool_flags; pw.bounds = s->d_bounds; pw.epoch = s->epoch; pw.world = s->world; pw.rank = s->rank; pw.err = s->d_err;
     mark(s, s->epoch, 5);
     uint32_t* h_picks = nullptr;
+    static const bool early_on = [] { const char* v = getenv("GSB200_SHARD_EARLY_PAIRS"); return !v || atoi(v) != 0; }();      // =0: pairs in line (A/B)
+    const bool early_ok = early_on && s->crosses_since_select++ == 0 && !s->picks_scratch_moved;
+    s->picks_scratch_moved = false;
     if (stage_picks) {
         h_picks = reinterpret_cast<uint32_t*>(s->h_pin + s->max_total * 8);
         GSB_CUDA_TRY(cudaMemcpyAsync(s->h_pin + s->max_total * 16, s->d_sel_ids, (size_t) s->top_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        GSB_CUDA_TRY(cudaEventRecord(s->ev_sel_ids, ctx->stream));      // (the picks may be down long before: they do not wait for the selection)
     }
     GSB_TRY(pool_random_cross(ctx, reinterpret_cast<const uint32_t*>(s->slab + s->off_pool), s->top_n, n, map, d_out_rows, first_out_row,
-                              draws, d_picks, what, h_picks, s->ev_picks, lazy ? &pw : nullptr, s->copy, s->ev_fork[2]));
+                              draws, d_picks, what, h_picks, s->ev_picks, lazy ? &pw : nullptr,
+                              early_ok ? s->copy : nullptr, s->ev_fork[0], s->ev_fork[2]));
     if (lazy) {
         // every peer's rows have been seen before anything that follows on this stream: the GEBVs of the next generation
         // are pushed only after this, which is what lets the peers reuse their buffers without a barrier
@@ -659,8 +670,10 @@ int gsb200_shard_cross_begin_run(gsb200_shard* s, uint32_t n, uint32_t map, cons
     }
     uint32_t* d_picks = nullptr;
     if (want_picks) {
+        const void* before = ctx->s_rows[1].ptr;
         GSB_TRY(ctx->s_rows[1].ensure((size_t) 2 * n * sizeof(uint32_t)));
         d_picks = (uint32_t*) ctx->s_rows[1].ptr;
+        s->picks_scratch_moved = before != (const void*) d_picks;
     }
     return shard_cross_impl(s, n, map, d_out, first_out_row, draws, d_picks, want_picks != 0, "gsb200_shard_cross");
 }
@@ -670,6 +683,7 @@ int gsb200_shard_cross_picks(gsb200_shard* s, const uint32_t** picked1, const ui
     GSB_REQUIRE(s->picks_staged, GSB200_ERR_ARG, "gsb200_shard_cross_picks: the last cross was not asked for its picks");
     GSB_CUDA_TRY(cudaSetDevice(s->ctx->device));
     GSB_CUDA_TRY(cudaEventSynchronize(s->ev_picks));
+    GSB_CUDA_TRY(cudaEventSynchronize(s->ev_sel_ids));
     const uint32_t* p = reinterpret_cast<const uint32_t*>(s->h_pin + s->max_total * 8);
     if (picked1) *picked1 = p;
     if (picked2) *picked2 = p + s->staged_offspring;

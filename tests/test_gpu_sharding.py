@@ -41,7 +41,9 @@ def test_top_n_is_a_radix_select_with_the_reference_tie_rule():
     sim = SimData.from_dataset(dataset())
     rng = np.random.default_rng(3)
     cases = [rng.standard_normal(100000), np.round(rng.standard_normal(5000), 1), np.zeros(300), -np.abs(rng.standard_normal(4097)),
-             np.array([1.0, 3.0, 3.0, -2.0, 0.5, 3.0, -0.0, 0.0]), rng.standard_normal(1) * 1e300, rng.standard_normal(2049) * 1e-300]
+             np.array([1.0, 3.0, 3.0, -2.0, 0.5, 3.0, -0.0, 0.0]), rng.standard_normal(1) * 1e300, rng.standard_normal(2049) * 1e-300,
+             # more ties at the cut than one block resolves for itself (select_fused_kernel's block-0 path), and a constant generation
+             np.round(rng.standard_normal(200000), 0), np.full(40000, 2.5)]
     for v in cases:
         v = np.ascontiguousarray(v, dtype=np.float64)
         for top in sorted(t for t in {1, 2, len(v) // 100 + 1, len(v) // 2 + 1, len(v)} if t <= len(v)):
