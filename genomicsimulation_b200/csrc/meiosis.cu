@@ -78,6 +78,7 @@ struct MeiosisArgs {
     uint32_t n_units;
     uint32_t gametes_per_unit; // 2: cross / selfing generation, 1: doubled haploid
     uint32_t doubled;          // write the gamete to both strands
+    uint32_t fix_chunked;      // fast kernel: apply the toggles' fix-ups chunk by chunk, while the lines are still in L2 (see E1/E2)
     MapView map[2];
     DrawView draws;
     // fast-kernel plan geometry
@@ -238,8 +239,8 @@ __device__ __forceinline__ void emit_toggles(uint32_t t, uint32_t lane, const Me
 // the word boundary and the toggle are summed here from the parent's words.  The strand a toggle
 // leaves = the strand its 128-marker piece starts on, flipped once per earlier toggle in the
 // same piece (rare: found with two bitsets, ranked by scanning the list only then).
-template <bool kBv>
-__global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a) {
+template <bool kBv, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) splice_flat_kernel(const MeiosisArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint2* xinfo = reinterpret_cast<uint2*>(smem + (size_t) warp * a.warp_smem_words);
@@ -401,7 +402,12 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
         //     32 * kUnroll pieces run without bounds checks; 32-bit piece offsets from two bases.
         const uint32_t hap_pieces = hap_stride >> 2;
         const uint32_t full = a.n_u & ~(32u * kUnroll - 1u);
-        for (uint32_t p = 0; p < a.planes; ++p) {
+        // With rows too long for everything the resident warps have in flight to stay in L2 (M = 100 k: 25 - 37 KB per gamete x
+        // 5 920 warps > 126 MB), fix-ups applied after the WHOLE gamete find their lines evicted again: every toggle then re-reads
+        // a sector of each strand from DRAM and its atomics read and write back the output's (ncu: 25 KB read per doubled haploid
+        // where 12.5 KB are needed).  fix_chunked applies them after every 2 KB chunk instead (one plane; not the GEBV variant).
+        const bool chunked = !kBv && a.fix_chunked && a.planes == 1;
+        for (uint32_t p = 0; p < a.planes && !chunked; ++p) {
             const uint4* s4 = reinterpret_cast<const uint4*>(src + p * a.plane_words);
             uint4* o4 = reinterpret_cast<uint4*>(dst + (gam * a.planes + p) * a.plane_words);
             uint32_t u = lane;
@@ -466,10 +472,12 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
                 n_multi = 0;
             }
         }
+        auto fix_pieces = [&](const uint32_t u_lo, const uint32_t u_hi) {
         for (uint32_t i0 = 0; i0 < n_list; i0 += 32) {
             const uint32_t i = i0 + lane;
             if (i >= n_list) continue;
             const uint32_t t = list[i], u = t >> 7;
+            if (u < u_lo || u >= u_hi) continue;
             const int o = (int) (t & 127u);
             const uint32_t m0 = shl_clamp(0xffffffffu, o), m1 = shl_clamp(0xffffffffu, max(o - 32, 0));
             const uint32_t m2 = shl_clamp(0xffffffffu, max(o - 64, 0)), m3 = shl_clamp(0xffffffffu, max(o - 96, 0));
@@ -521,6 +529,38 @@ __global__ void __launch_bounds__(256, 5) splice_flat_kernel(const MeiosisArgs a
                     if (hi) atomicXor(out2 + 1, hi);
                 }
             }
+        }
+        };
+        if (chunked) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* o4 = reinterpret_cast<uint4*>(dst + gam * a.plane_words);
+            uint32_t u0 = 0;
+            for (; u0 < full; u0 += 32 * kUnroll) {
+                const uint32_t u = u0 + lane;
+                uint4 v[kUnroll];
+#pragma unroll
+                for (int q = 0; q < kUnroll; ++q) {
+                    const uint32_t on1 = (piece_parity[(u >> 5) + q] >> lane) & 1u;
+                    v[q] = __ldg(s4 + (u + q * 32 + on1 * hap_pieces));
+                }
+#pragma unroll
+                for (int q = 0; q < kUnroll; ++q) {
+                    o4[u + q * 32] = v[q];
+                    if (a.doubled) o4[u + q * 32 + hap_pieces] = v[q];
+                }
+                __syncwarp();
+                fix_pieces(u0, u0 + 32 * kUnroll);
+            }
+            for (uint32_t u = u0 + lane; u < a.n_u; u += 32) {
+                const uint32_t on1 = (piece_parity[u >> 5] >> lane) & 1u;
+                const uint4 v = __ldg(s4 + (u + on1 * hap_pieces));
+                o4[u] = v;
+                if (a.doubled) o4[u + hap_pieces] = v;
+            }
+            __syncwarp();
+            fix_pieces(u0, a.n_u);
+        } else {
+            fix_pieces(0u, 0xffffffffu);
         }
         if (kBv) {
 #pragma unroll
@@ -934,6 +974,7 @@ int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
     a.dst_base = b.dst_base; a.dst_rows = b.d_dst;
     a.row_words = ctx->row_words(); a.plane_words = ctx->plane_words; a.planes = ctx->planes; a.n_markers = ctx->n_markers;
     a.n_units = b.n_units; a.gametes_per_unit = b.gametes_per_unit; a.doubled = b.doubled;
+    a.fix_chunked = 0;
     a.map[0] = view_of(*b.map0);
     a.map[1] = view_of(b.gametes_per_unit > 1 ? *b.map1 : *b.map0);
     a.draws = b.draws;
@@ -979,11 +1020,20 @@ int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
     GSB_REQUIRE(fast || !b.bv_acc, GSB200_ERR_UNSUPPORTED, "%s: internal: fused GEBV needs the flat splice kernel", b.what);
     if (fast) {
         const size_t smem = (size_t) warps * a.warp_smem_words * 4;
-        auto* kernel = b.bv_acc ? splice_flat_kernel<true> : splice_flat_kernel<false>;
+        // resident blocks per SM the plain kernel is compiled for (registers per thread: 5 -> 48, 6 -> 40, 8 -> 32 with a few spills)
+        static const int occ = [] { const char* v = getenv("GSB200_SPLICE_OCC"); return v ? atoi(v) : 5; }();
+        auto* kernel = b.bv_acc ? splice_flat_kernel<true, 5> : occ == 8 ? splice_flat_kernel<false, 8> : occ == 6 ? splice_flat_kernel<false, 6> : splice_flat_kernel<false, 5>;
         if (smem > 48 * 1024)
             GSB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_limit));
         const uint64_t n_gametes = (uint64_t) a.n_units * a.gametes_per_unit;
         const uint64_t blocks = (n_gametes + warps - 1) / warps;
+        {
+            // what the resident warps (5 blocks per SM) read and write between a piece's copy and its fix-ups, against the L2
+            static const int fix_mode = [] { const char* v = getenv("GSB200_SPLICE_FIX"); return v ? atoi(v) : -1; }();      // 0 / 1 force it
+            const uint64_t resident = std::min<uint64_t>(n_gametes, (uint64_t) ctx->sm_count * 5 * warps);
+            const uint64_t in_flight = resident * (uint64_t) a.plane_words * 4 * a.planes * (a.doubled ? 3 : 2);
+            a.fix_chunked = fix_mode >= 0 ? (uint32_t) fix_mode : (in_flight > ((uint64_t) 96 << 20) ? 1u : 0u);
+        }
         const unsigned grid = (unsigned) std::min<uint64_t>(blocks, (uint64_t) ctx->sm_count * 64);
         kernel<<<grid, warps * 32, smem, ctx->stream>>>(a);
         ++ctx->launches;
