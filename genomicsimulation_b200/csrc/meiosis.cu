@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) splice_flat_kernel(const Meio
         if (chunked) {
             const uint4* s4 = reinterpret_cast<const uint4*>(src);
             uint4* o4 = reinterpret_cast<uint4*>(dst + gam * a.plane_words);
-            uint32_t u0 = 0;
+            uint32_t u0 = 0, fixed_to = 0, groups = 0;
             for (; u0 < full; u0 += 32 * kUnroll) {
                 const uint32_t u = u0 + lane;
                 uint4 v[kUnroll];
@@ -548,8 +548,12 @@ __global__ void __launch_bounds__(256, kMinBlocks) splice_flat_kernel(const Meio
                     o4[u + q * 32] = v[q];
                     if (a.doubled) o4[u + q * 32 + hap_pieces] = v[q];
                 }
-                __syncwarp();
-                fix_pieces(u0, u0 + 32 * kUnroll);
+                if (++groups == a.fix_chunked) {          // fix_chunked = groups of 2 KB per round of fix-ups
+                    __syncwarp();
+                    fix_pieces(fixed_to, u0 + 32 * kUnroll);
+                    fixed_to = u0 + 32 * kUnroll;
+                    groups = 0;
+                }
             }
             for (uint32_t u = u0 + lane; u < a.n_u; u += 32) {
                 const uint32_t on1 = (piece_parity[u >> 5] >> lane) & 1u;
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) splice_flat_kernel(const Meio
                 if (a.doubled) o4[u + hap_pieces] = v;
             }
             __syncwarp();
-            fix_pieces(u0, a.n_u);
+            fix_pieces(fixed_to, a.n_u);
         } else {
             fix_pieces(0u, 0xffffffffu);
         }
@@ -1029,10 +1033,10 @@ int run_batch(gsb200_ctx* ctx, const Batch& b, bool may_sync) {
         const uint64_t blocks = (n_gametes + warps - 1) / warps;
         {
             // what the resident warps (5 blocks per SM) read and write between a piece's copy and its fix-ups, against the L2
-            static const int fix_mode = [] { const char* v = getenv("GSB200_SPLICE_FIX"); return v ? atoi(v) : -1; }();      // 0 / 1 force it
+            static const int fix_mode = [] { const char* v = getenv("GSB200_SPLICE_FIX"); return v ? atoi(v) : -1; }();      // 0: never, k: every k groups
             const uint64_t resident = std::min<uint64_t>(n_gametes, (uint64_t) ctx->sm_count * 5 * warps);
             const uint64_t in_flight = resident * (uint64_t) a.plane_words * 4 * a.planes * (a.doubled ? 3 : 2);
-            a.fix_chunked = fix_mode >= 0 ? (uint32_t) fix_mode : (in_flight > ((uint64_t) 96 << 20) ? 1u : 0u);
+            a.fix_chunked = fix_mode >= 0 ? (uint32_t) fix_mode : (in_flight > ((uint64_t) 96 << 20) ? 2u : 0u);      // groups of 2 KB per round of fix-ups
         }
         const unsigned grid = (unsigned) std::min<uint64_t>(blocks, (uint64_t) ctx->sm_count * 64);
         kernel<<<grid, warps * 32, smem, ctx->stream>>>(a);
