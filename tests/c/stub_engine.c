@@ -1,5 +1,5 @@
 /* stub_engine.c — a do-nothing stand-in for libgsb200.so, for PROFILING THE HOST MIRROR on a box without a GPU
- * (profiles/scripts/host_profile/run.sh).  Not a product path and not a test oracle: every engine call succeeds at once,
+ * (profiles/scripts/host_profile/run.sh) and for MODEL-CHECKING ITS BOOKKEEPING on CPU (tests/test_host_bookkeeping.py).  Not a product path and not a test oracle: every engine call succeeds at once,
  * so what the clock sees is the host mirror's own bookkeeping per generation (group scans, row lists, ids, pedigrees).
  * Only the calls the sharded generation makes return data; the rest are declared without prototypes on purpose. */
 #include <stdint.h>
