@@ -35,11 +35,11 @@ def opts(**kw):
 def lib(tmp_path_factory):
     out = tmp_path_factory.mktemp("host_stub")
     cc = os.environ.get("CC", "gcc")
-    subprocess.check_call([cc, "-O1", "-g", "-fPIC", "-shared", "-w", "-o", str(out / "libgsb200.so"), os.path.join(ROOT, "tests/c/stub_engine.c")])
     extra = os.environ.get("GSB_TEST_CFLAGS", "").split()      # e.g. -fsanitize=address with LD_PRELOAD=libasan.so
-    subprocess.check_call([cc, "-O2", "-g", "-std=gnu11", "-fPIC", "-shared", *extra, "-I" + os.path.join(ROOT, "include"),
+    # mirror and stub in ONE shared object, bound to each other (-Bsymbolic): the real libgsb200.so may be loaded in this process too
+    subprocess.check_call([cc, "-O2", "-g", "-std=gnu11", "-fPIC", "-shared", "-w", *extra, "-I" + os.path.join(ROOT, "include"),
                            "-o", str(out / "libhost.so"), os.path.join(ROOT, "genomicsimulation_b200/host/gsb_simdata.c"),
-                           "-L" + str(out), "-lgsb200", "-lm", "-Wl,-rpath," + str(out)])
+                           os.path.join(ROOT, "tests/c/stub_engine.c"), "-lm", "-Wl,-Bsymbolic"])
     L = C.CDLL(str(out / "libhost.so"))
     vp, u = C.c_void_p, C.c_uint
     L.gsb_create_simdata.restype = vp
