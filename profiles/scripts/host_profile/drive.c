@@ -43,6 +43,26 @@ int main(int argc, char** argv) {
     }
     printf("n = %u: select_and_cross %.3f ms, local_bvs %.3f ms, delete_group %.3f ms, total %.3f ms per generation (host only)\n",
            n, ta / steps, tb / steps, tc / steps, (ta + tb + tc) / steps);
+    /* the single-GPU calls a user of the reference makes: gsb_make_random_crosses from 1000 parents + gsb_get_group_bvs + gsb_delete_group */
+    {
+        gsb_GenOptions o2 = GSB_BASIC_OPT;
+        o2.will_track_pedigree = 1;
+        double tx = 0, ty = 0, tz = 0;
+        for (unsigned s = 0; s < steps + 3; ++s) {
+            if (s == 3) tx = ty = tz = 0;
+            const double t0 = now();
+            gsb_GroupNum ng = gsb_make_random_crosses(d, 1, n, 0, map, o2);
+            const double t1 = now();
+            gsb_get_group_bvs(d, ng, e, n, bv);
+            const double t2 = now();
+            gsb_delete_group(d, ng);
+            const double t3 = now();
+            if (!ng) { puts("make_random_crosses failed"); return 1; }
+            tx += t1 - t0; ty += t2 - t1; tz += t3 - t2;
+        }
+        printf("n = %u: make_random_crosses %.3f ms, get_group_bvs %.3f ms, delete_group %.3f ms, total %.3f ms per batch (host only)\n",
+               n, tx / steps, ty / steps, tz / steps, (tx + ty + tz) / steps);
+    }
 #ifdef GSB_HOST_PROFILE
     { extern void gsb_host_profile_report(unsigned); gsb_host_profile_report(steps + 3); }
 #endif

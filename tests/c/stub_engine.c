@@ -50,9 +50,23 @@ uint64_t gsb200_shard_generation_size(const shard_t* s) { return s->n_total; }
 uint32_t gsb200_shard_pool_size(const shard_t* s) { return s->top_n; }
 int gsb200_shard_selected() { return 0; }
 
+int gsb200_cross_random_pairs_begin(ctx_t* c, uint32_t n_crosses, uint32_t family, const uint32_t* rows1, uint32_t n1, const uint32_t* rows2, uint32_t n2,
+                                    uint32_t map1, uint32_t map2, const uint32_t* out_rows, uint32_t first_out, const void* draws, uint32_t* k1, uint32_t* k2) {
+    (void) c; (void) rows1; (void) rows2; (void) map1; (void) map2; (void) out_rows; (void) first_out; (void) draws;
+    const uint64_t n = (uint64_t) n_crosses * family;
+    const uint32_t m2 = rows2 ? n2 : n1;
+    if (k1 && k2) {          /* cheap on purpose (no division per offspring): what is timed is the mirror, not the stub */
+        uint32_t a = 0, b = 7 % m2;
+        for (uint64_t i = 0; i < n; ++i) {
+            k1[i] = a; k2[i] = b;
+            if (family == 1 || (i + 1) % family == 0) { a += 3; if (a >= n1) a -= n1 < 3 ? a : n1; b += 5; if (b >= m2) b -= m2 < 5 ? b : m2; }
+        }
+    }
+    return 0;
+}
+
 #define STUB(name) int name() { return 0; }
-STUB(gsb200_allele_counts) STUB(gsb200_allele_presence) STUB(gsb200_clone) STUB(gsb200_cross) STUB(gsb200_cross_random_pairs_begin)
-STUB(gsb200_cross_random_pairs_end) STUB(gsb200_doubled_haploid) STUB(gsb200_effects_delete) STUB(gsb200_effects_set) STUB(gsb200_gebv)
+STUB(gsb200_allele_counts) STUB(gsb200_allele_presence) STUB(gsb200_clone) STUB(gsb200_cross) STUB(gsb200_cross_random_pairs_end) STUB(gsb200_doubled_haploid) STUB(gsb200_effects_delete) STUB(gsb200_effects_set) STUB(gsb200_gebv)
 STUB(gsb200_local_gebv) STUB(gsb200_map_delete) STUB(gsb200_map_set) STUB(gsb200_self_n_times) STUB(gsb200_store_dictionary)
 STUB(gsb200_store_download_chars) STUB(gsb200_store_download_chars_range) STUB(gsb200_store_reserve) STUB(gsb200_store_upload_chars)
 STUB(gsb200_top_n)
