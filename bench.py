@@ -499,6 +499,28 @@ def engine_arm(a):
                   "(include/gsb200_gsc.h), native draws: the generation's row list, ids and the offspring's row list go up; the picked "
                   "pairs and the selected parents' ids (for pedigrees) and the GEBVs come down"}
 
+    # ---- the same work through the calls a user of the reference makes on ONE GPU (round 1's e2e): gsc_make_random_crosses from
+    #      the founders + gsc_get_group_bvs of the offspring + gsc_delete_group, host buffers, pedigrees tracked
+    e2e_api = None
+    if world == 1:
+        sim.shard_finish()
+        sim.delete_group(g)
+        k_warm, k_steps = 2, min(a.steps, 20)
+        t0 = 0.0
+        for i in range(k_warm + k_steps):
+            if i == k_warm:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            new = sim.make_random_crosses(sim.founders, n, 0, 1, track_pedigree=True)
+            bv = sim.get_group_bvs(new, 1, out=bv_host)
+            sim.delete_group(new)
+            assert bv.shape[0] == n
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / k_steps
+        e2e_api = {"value": n / sec, "unit": UNIT, "ms_per_step": sec * 1e3,
+                   "api": "gsb_make_random_crosses (%d founders -> %d offspring, pedigrees tracked) + gsb_get_group_bvs + gsb_delete_group, "
+                          "native draws, host buffers: no selection step (round 1's e2e definition)" % (F, n)}
+
     # ---- rooflines of the two dominant kernels
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -509,7 +531,7 @@ def engine_arm(a):
     alg_cross = n * (M / 2.0)                 # M/2 bytes per diploid offspring
     alg_gebv = n * (M / 4.0 + 8.0)            # M/4 bytes read + 8 written per individual
     pool_mb = top * 12544 * (M / 50000.0) / 1e6
-    roof = {"bound": "hbm", "kernel": "splice_flat_kernel (meiosis; the phase also holds the pair-draw kernel, ~3 us)",
+    roof = {"bound": "hbm", "kernel": "splice_flat_kernel (meiosis; the pair-draw kernel, ~3 us, runs beside the GEBV kernel on a second stream)",
             "achieved": alg_cross / (cross_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src,
             "ms_per_launch": cross_ms, "algorithmic_bytes_per_launch": alg_cross,
             "regime": ("parent pool of %d rows = %.1f MB: re-read from L2" % (top, pool_mb)) if pool_mb < 24 else
@@ -563,6 +585,8 @@ def engine_arm(a):
             out["per_rank_kernel_ms"] = per_rank
         if config3_full:
             out["config3_full"] = config3_full
+        if e2e_api:
+            out["e2e_single_gpu_api"] = e2e_api
         out.update(extras)
         if world == 1 and not a.no_cpu_baseline:
             kind, n_done, sec = cpu_run(a, a.cpu_sample, 1, 0, 1)
