@@ -549,6 +549,15 @@ def engine_arm(a):
         roof["traffic"] = tr.get("splice_flat_kernel")
         roof_g["traffic"] = tr.get("gebv_counts_kernel")
         roof["traffic_source"] = roof_g["traffic_source"] = tr.get("source")
+        if roof["traffic"] and world == 1 and n == 100000 and M == 50000:
+            # the same kernel in DRAM terms: with the pool in L2 it is a pure write stream, and a pure write stream reaches
+            # 7.4 TB/s on this GPU (profiles/r2_write_bw_probe.txt) — the kernel is bound by its instructions, not by HBM
+            wr_peak = 7446.0
+            roof["dram_terms"] = {"achieved": roof["traffic"] / (cross_ms * 1e-3) / 1e9, "peak": wr_peak, "unit": "GB/s",
+                                  "frac": roof["traffic"] / (cross_ms * 1e-3) / 1e9 / wr_peak,
+                                  "peak_source": "write-only stream (torch zero_ of 4 GiB), profiles/r2_write_bw_probe.txt",
+                                  "bound": "issue / latency: 1 270 instructions per gamete, 56.8 % issue-active at 40 warps per SM "
+                                           "(profiles/r2_ncu_full_summary.txt; DESIGN.md 7.2)"}
         if tr.get("gebv_issue"):
             gi = dict(tr["gebv_issue"])
             gi["frac"] = gi["alu_pipe_active_frac"] + gi["imma_pipe_active_frac"]

@@ -397,3 +397,38 @@ def test_device_pairs_in_two_halves():
     assert E.gsb200_store_download_chars(ctx, 2 * n, _p(rows), _p(chars)) == 0, E.gsb200_last_error()
     assert (chars[:n] == chars[n:]).all() and (chars[0] != chars[1]).any()
     sim.close()
+
+
+_FIXUP_SCRIPT = r"""
+import hashlib, sys
+sys.path.insert(0, %r)
+from genomicsimulation_b200 import SimData, synthetic
+sim = SimData.from_dataset(synthetic.founders(12, 100000, 7, 150.0, seed=11))
+sim.use_native_draws(424242)
+f1 = sim.make_random_crosses(1, 300)
+s3 = sim.self_n_times(3, f1)
+dh = sim.make_doubled_haploids(s3)
+h = hashlib.sha256()
+for g in (f1, s3, dh):
+    h.update(sim.export_group(g)["genotypes"].tobytes())
+print("DIGEST", h.hexdigest())
+sim.close()
+"""
+
+
+def test_fixups_in_chunks_change_nothing():
+    """splice_flat_kernel applies a gamete's toggle fix-ups either after the whole gamete or after every k groups of 2 KB
+    (fix_chunked: picked from the in-flight estimate, i.e. only at sizes no parity test reaches; GSB200_SPLICE_FIX forces it,
+    read once per process): crosses, chained selfing and doubled haploids of 100 000-marker lines — six full groups and a
+    tail per gamete — must come out bit-identical for every k."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for k in ("0", "1", "2", "4"):
+        env = dict(os.environ, GSB200_SPLICE_FIX=k)
+        out = subprocess.run([sys.executable, "-c", _FIXUP_SCRIPT % root], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests[k] = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0]
+    assert len(set(digests.values())) == 1, digests
