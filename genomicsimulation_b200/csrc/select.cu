@@ -457,9 +457,15 @@ int select_top_n(gsb200_ctx* ctx, const double* d_values, uint32_t n, uint32_t t
         uint2* a_counts = (uint2*) (hist + 4 * kBins);         // the per-block counts live in the others
         void* args[] = {&a_values, &a_n, &a_low, &a_top, &state, &a_hist, &a_ncand, &cand, &a_counts, &d_sel, &a_lo, &a_hi};
         const uint32_t blocks = std::max(1u, std::min<uint32_t>((n + kFusedMinPerBlock - 1) / kFusedMinPerBlock, (uint32_t) ctx->sm_count));
-        GSB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*) select_fused_kernel, dim3(blocks), dim3(kFusedThreads), args, 0, ctx->stream));
-        ctx->launches += 1;
-        return GSB200_OK;
+        const cudaError_t le = cudaLaunchCooperativeKernel((const void*) select_fused_kernel, dim3(blocks), dim3(kFusedThreads), args, 0, ctx->stream);
+        if (le == cudaSuccess) {
+            ctx->launches += 1;
+            return GSB200_OK;
+        }
+        // a device that cannot hold the grid at once right now (another client's kernels resident): the same selection as
+        // separate launches below; anything else is an error
+        if (le != cudaErrorCooperativeLaunchTooLarge && le != cudaErrorLaunchOutOfResources) GSB_CUDA_TRY(le);
+        cudaGetLastError();
     }
     GSB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(SelectState) + (size_t) kPasses * kBins * sizeof(uint32_t), ctx->stream));
     GSB_CUDA_TRY(cudaMemsetAsync(n_cand, 0, sizeof(uint32_t), ctx->stream));

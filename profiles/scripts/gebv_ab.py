@@ -42,6 +42,15 @@ def main():
             assert st == 0, E.gsb200_last_error()
             b.synchronize()
             ts.append(a.elapsed_time(b))
+    # ... and back to back without a host synchronisation in between (what the kernel does inside a long step)
+    with torch.cuda.stream(stream):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for it in range(300):
+            assert E.gsb200_gebv_dev(ctx, N, d_rows.data_ptr(), 0, d_bv.data_ptr()) == 0
+        b.record(stream)
+        b.synchronize()
+    print("sustained: 300 calls back to back, %.4f ms per call" % (a.elapsed_time(b) / 300))
     ts = sorted(ts[5:])
     bv = d_bv.cpu().numpy()
     alg = N * (M / 4 + 8)
