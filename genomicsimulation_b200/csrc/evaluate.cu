@@ -56,6 +56,20 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     return v;
 }
 
+// ... with an L2 eviction policy: lines this stream brings in are the first to go, so that it replaces ITSELF in L2 rather
+// than the dirty lines the kernel in front (the splice) left there — evicting those costs a write-back per read miss
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ldg_stream_hint(const uint4* p, unsigned long long pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+
 // Persistent blocks, three per SM.  A block keeps the B fragments of ONE marker segment (<= 16
 // chunks = 64 KB) in shared memory, loaded once, and its 8 warps pull groups of 16 individuals from
 // the segment's counter: no per-chunk staging, no barrier after the first, no tail.
@@ -80,6 +94,7 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 constexpr int kGebvWarps = 8;
 constexpr int kGebvBlocksPerSm = 3;
 constexpr uint32_t kGebvSegChunks = 16;        // B of a segment: 64 KB of shared memory; 8192 markers * 128 * 128 < 2^31
+template <bool kEvictFirst>
 __global__ void __launch_bounds__(kGebvWarps * 32, kGebvBlocksPerSm) gebv_counts_kernel(
         const uint32_t* __restrict__ store, uint64_t row_words, uint32_t plane_words,
         const uint32_t* __restrict__ rows, uint32_t n, const uint4* __restrict__ bfrag,
@@ -121,10 +136,16 @@ __global__ void __launch_bounds__(kGebvWarps * 32, kGebvBlocksPerSm) gebv_counts
     uint32_t nxt = take();
     Ptrs lp = ptrs(cur), np = ptrs(nxt);
     struct Rows { uint4 a0, a1, b0, b1; };
+    const unsigned long long pol = kEvictFirst ? l2_evict_first_policy() : 0ull;
     auto load = [&](const Ptrs& p, uint32_t ch, Rows& r) {
         const uint32_t o = min(ch, segc - 1) * 4;
-        r.a0 = ldg_stream(p.a + o); r.a1 = ldg_stream(p.a + strand1 + o);
-        r.b0 = ldg_stream(p.b + o); r.b1 = ldg_stream(p.b + strand1 + o);
+        if (kEvictFirst) {
+            r.a0 = ldg_stream_hint(p.a + o, pol); r.a1 = ldg_stream_hint(p.a + strand1 + o, pol);
+            r.b0 = ldg_stream_hint(p.b + o, pol); r.b1 = ldg_stream_hint(p.b + strand1 + o, pol);
+        } else {
+            r.a0 = ldg_stream(p.a + o); r.a1 = ldg_stream(p.a + strand1 + o);
+            r.b0 = ldg_stream(p.b + o); r.b1 = ldg_stream(p.b + strand1 + o);
+        }
     };
     int acc0[4] = { 0, 0, 0, 0 }, acc1[4] = { 0, 0, 0, 0 };
     auto word = [&](uint32_t a_s0, uint32_t a_s1, uint32_t b_s0, uint32_t b_s1, const uint4* fw) {
@@ -619,9 +640,12 @@ int gebv_launch(gsb200_ctx* ctx, uint32_t n, const uint32_t* d_rows, uint32_t ef
             const uint32_t n_segments = (chunks + seg_chunks - 1) / seg_chunks;
             const uint64_t useful = (uint64_t) ((n_groups + kGebvWarps - 1) / kGebvWarps) * n_segments;
             const uint32_t grid = (uint32_t) std::min<uint64_t>(std::max<uint64_t>((uint64_t) ctx->sm_count * kGebvBlocksPerSm, n_segments), useful);
-            GSB_CUDA_TRY(cudaFuncSetAttribute(gebv_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kGebvSegChunks * 4096));   // per device
+            // GSB200_GEBV_L2=evict_first: the row stream marked evict-first in L2 (A/B; see ldg_stream_hint)
+            static const bool evict_first = [] { const char* v = getenv("GSB200_GEBV_L2"); return v && strcmp(v, "evict_first") == 0; }();
+            auto* kernel = evict_first ? gebv_counts_kernel<true> : gebv_counts_kernel<false>;
+            GSB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kGebvSegChunks * 4096));   // per device
             unsigned int* d_next = reinterpret_cast<unsigned int*>(d_digits + (size_t) n * 8);     // one counter per segment, zeroed above
-            gebv_counts_kernel<<<grid, kGebvWarps * 32, ((seg_chunks + 1) & ~1u) * 4096, ctx->stream>>>(
+            kernel<<<grid, kGebvWarps * 32, ((seg_chunks + 1) & ~1u) * 4096, ctx->stream>>>(
                 ctx->d_store, ctx->row_words(), ctx->plane_words, d_rows, n, (const uint4*) e->d_digit_frag, n_groups, n_segments, seg_chunks,
                 d_digits, d_next);
             ++ctx->launches;

@@ -51,6 +51,21 @@ def main():
         b.record(stream)
         b.synchronize()
     print("sustained: 300 calls back to back, %.4f ms per call" % (a.elapsed_time(b) / 300))
+    # ... and each call behind a kernel that leaves L2 full of dirty lines (what the splice does in the step): 256 MB written
+    scratch = torch.empty(64 << 20, dtype=torch.int32, device="cuda")
+    for label, dirty in (("clean", False), ("behind 256 MB of writes", True), ("clean", False), ("behind 256 MB of writes", True)):
+        evs = []
+        with torch.cuda.stream(stream):
+            for it in range(100):
+                if dirty:
+                    scratch.fill_(it)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                assert E.gsb200_gebv_dev(ctx, N, d_rows.data_ptr(), 0, d_bv.data_ptr()) == 0
+                b.record(stream)
+                evs.append((a, b))
+            stream.synchronize()
+        print("back to back, %-24s %.4f ms per call" % (label + ":", sum(a.elapsed_time(b) for a, b in evs[10:]) / 90))
     ts = sorted(ts[5:])
     bv = d_bv.cpu().numpy()
     alg = N * (M / 4 + 8)
