@@ -1150,9 +1150,14 @@ __global__ void gamete_keys_kernel(uint32_t n_gametes, const uint32_t* __restric
 // per 200 k; the 12.5 MB pool of the headline step sits in L2 anyway and would only pay the sort's ~27 us.
 // keys1 / keys2: per offspring, which of the n_keys candidate parents made gamete 0 / 1 (keys2 counted from key2_offset on).
 // *d_order stays null when sorting is not worth it.
+// st: the stream the sort runs on (null: the context stream).  On another stream the scratch must not move (memory that has just
+// been allocated on the context stream is not that stream's yet): then *deferred is set and nothing is enqueued.
 int gamete_order(gsb200_ctx* ctx, uint32_t n, const uint32_t* keys1, const uint32_t* keys2, uint32_t key2_offset, uint32_t n_keys,
-                 const uint32_t** d_order, const PoolWait* pw = nullptr) {
+                 const uint32_t** d_order, const PoolWait* pw = nullptr, cudaStream_t st = nullptr, bool* deferred = nullptr, bool free_ride = false) {
     *d_order = nullptr;
+    if (deferred) *deferred = false;
+    const bool aside = st != nullptr && st != ctx->stream;
+    if (!st) st = ctx->stream;
     // Worth it when the DRAM reads it saves outweigh the sort (~30 us, mostly launches): the saving is the parents' half of
     // the algorithmic bytes times the share of them that misses L2 in numbered order — ~0 for a 12 MB pool, ~1 from 110 MB
     // on (measured: 0.2 at 25 MB, 0.4 at 50 MB, 0.9 at 100 MB).  GSB200_SORT_GAMETES_MIN_MB, read at every call so that
@@ -1168,6 +1173,12 @@ int gamete_order(gsb200_ctx* ctx, uint32_t n, const uint32_t* keys1, const uint3
         // a pool that is still arriving: sorted, the splice starts on the rank's own parents while the others' rows come in
         // over NVLink (~0.6 TB/s) instead of waiting for all of them
         if (pw && pw->world > 1) saved_us += (double) pool_bytes * (pw->world - 1) / pw->world / 0.6e6;
+        // MEASURED: with the sort beside the GEBV kernel (free_ride) it pays on the device for ANY pool — neighbouring warps that
+        // share their source rows help even a pool that sits in L2: 0.390 -> 0.372 ms per 100 k offspring from 1 000 parents,
+        // step 0.739 -> 0.716 ms — but its enqueue (cub: key kernel + radix passes, ~25 us of host time) makes the host-bound
+        // end-to-end path slower by more (0.770 -> 0.805 ms per generation; a one-launch cooperative counting sort: 0.83).
+        // The break-even therefore stays where the in-line sort put it (GSB200_SORT_GAMETES_MIN_MB=0 sorts always).
+        (void) free_ride;
         if (saved_us < 45.0 && !(pw && pw->world > 1)) return GSB200_OK;          // (shard.cu splits the push only when it is worth this)
     }
     const uint32_t n_g = 2 * n;
@@ -1183,15 +1194,20 @@ int gamete_order(gsb200_ctx* ctx, uint32_t n, const uint32_t* keys1, const uint3
     }
     size_t temp_bytes = 0;
     GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*) nullptr, (uint32_t*) nullptr,
-                                                 (const uint32_t*) nullptr, (uint32_t*) nullptr, (int) n_g, 0, bits, ctx->stream));
+                                                 (const uint32_t*) nullptr, (uint32_t*) nullptr, (int) n_g, 0, bits, st));
     const size_t arr = ((size_t) n_g * sizeof(uint32_t) + 255) & ~(size_t) 255;
+    if (aside && ctx->s_plan[0].bytes < 4 * arr + temp_bytes) {
+        if (deferred) *deferred = true;
+        GSB_TRY(ctx->s_plan[0].ensure(4 * arr + temp_bytes));      // grown now, in line: the next generation finds it in place
+        return GSB200_OK;
+    }
     GSB_TRY(ctx->s_plan[0].ensure(4 * arr + temp_bytes));
     uint32_t* k_in = (uint32_t*) ctx->s_plan[0].ptr;
     uint32_t* k_out = (uint32_t*) ((char*) k_in + arr);
     uint32_t* v_in = (uint32_t*) ((char*) k_in + 2 * arr);
     uint32_t* v_out = (uint32_t*) ((char*) k_in + 3 * arr);
-    gamete_keys_kernel<<<grid_for(n_g, 256), 256, 0, ctx->stream>>>(n_g, keys1, keys2, key2_offset, k_in, v_in, rot, slot_bits);
-    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs((char*) k_in + 4 * arr, temp_bytes, k_in, k_out, v_in, v_out, (int) n_g, 0, bits, ctx->stream));
+    gamete_keys_kernel<<<grid_for(n_g, 256), 256, 0, st>>>(n_g, keys1, keys2, key2_offset, k_in, v_in, rot, slot_bits);
+    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs((char*) k_in + 4 * arr, temp_bytes, k_in, k_out, v_in, v_out, (int) n_g, 0, bits, st));
     ctx->launches += 3;
     GSB_CUDA_TRY(cudaGetLastError());
     *d_order = v_out;
@@ -1261,6 +1277,15 @@ int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_poo
                                                           d_picks, d_picks ? d_picks + n : nullptr, d_out_rows ? nullptr : d_run);
     ++ctx->launches;
     GSB_CUDA_TRY(cudaGetLastError());
+    // ... and so does the order the gametes are spliced in (sorted by parent SLOT when the pool outgrows L2): sorted over there too,
+    // unless the order also depends on who owns which slot (a pool still arriving, pw)
+    const uint32_t* d_order = nullptr;
+    bool order_pending = true;
+    if (early && !pw) {
+        bool deferred = false;
+        GSB_TRY(gamete_order(ctx, n, d_p1, d_p2, 0, n_pool, &d_order, nullptr, side_stream, &deferred, true));
+        order_pending = deferred;
+    }
     if (early) {
         GSB_CUDA_TRY(cudaEventRecord(pairs_done, side_stream));
         GSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, pairs_done, 0));
@@ -1297,8 +1322,7 @@ int pool_random_cross(gsb200_ctx* ctx, const uint32_t* pool_base, uint32_t n_poo
         GSB_CUDA_TRY(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
         window = true;
     }
-    const uint32_t* d_order = nullptr;
-    GSB_TRY(gamete_order(ctx, n, d_p1, d_p2, 0, n_pool, &d_order, pw));
+    if (order_pending) GSB_TRY(gamete_order(ctx, n, d_p1, d_p2, 0, n_pool, &d_order, pw));
     const int st = cross_impl(ctx, n, d_p1, d_p2, map, map, d_out_rows ? d_out_rows : d_run, draws, false, what, nullptr, pool_base, d_order, pw);
     if (window) {
         cudaStreamAttrValue attr;

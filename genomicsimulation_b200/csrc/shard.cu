@@ -276,6 +276,7 @@ struct gsb200_shard {
     cudaEvent_t ev_fork[3] = {nullptr, nullptr, nullptr};
     uint32_t crosses_since_select = 0;     // only the first cross of a selection may start its pair draws early (ev_fork[0] is its licence)
     bool picks_scratch_moved = false;
+    uint64_t launches_at_select = 0;       // ... and only when nothing else was launched on this context in between (shared scratch)
     cudaEvent_t ev_bv = nullptr, ev_picks = nullptr, ev_flags = nullptr, ev_sel_ids = nullptr;
     int* h_flags = nullptr;              // pinned: [0] the shard's exchange flag, [1] the context's splice flag, as of the last poll
     bool poll_pending = false;
@@ -563,6 +564,7 @@ static int shard_select_impl(gsb200_shard* s, uint32_t n_local, const uint32_t* 
     GSB_CUDA_TRY(cudaGetLastError());
     if (s->bv_staged) GSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_bv, 0));      // joined: nothing later overwrites GEBVs still on their way down
     mark(s, epoch, 4);
+    s->launches_at_select = ctx->launches;
     s->n_total = n_total;
     s->top_n = top_n;
     s->have_selection = true;
@@ -605,6 +607,7 @@ static int shard_cross_impl(gsb200_shard* s, uint32_t n, uint32_t map, const uin
                             const gsb200_draws* draws, uint32_t* d_picks, bool stage_picks, const char* what) {
     GSB_REQUIRE(s->have_selection, GSB200_ERR_ARG, "%s: nothing has been selected yet", what);
     gsb200_ctx* ctx = s->ctx;
+    const uint64_t launches_before = ctx->launches;
     GSB_REQUIRE(ctx->row_words() == s->row_words, GSB200_ERR_ARG, "%s: the store changed its width since the shard was created", what);
     GSB_REQUIRE(!stage_picks || n <= s->max_total, GSB200_ERR_ARG, "%s: %u offspring exceed the %llu the shard was created for", what, n,
                 (unsigned long long) s->max_total);
@@ -623,7 +626,7 @@ static int shard_cross_impl(gsb200_shard* s, uint32_t n, uint32_t map, const uin
     mark(s, s->epoch, 5);
     uint32_t* h_picks = nullptr;
     static const bool early_on = [] { const char* v = getenv("GSB200_SHARD_EARLY_PAIRS"); return !v || atoi(v) != 0; }();      // =0: pairs in line (A/B)
-    const bool early_ok = early_on && s->crosses_since_select++ == 0 && !s->picks_scratch_moved;
+    const bool early_ok = early_on && s->crosses_since_select++ == 0 && !s->picks_scratch_moved && launches_before == s->launches_at_select;
     s->picks_scratch_moved = false;
     if (stage_picks) {
         h_picks = reinterpret_cast<uint32_t*>(s->h_pin + s->max_total * 8);
