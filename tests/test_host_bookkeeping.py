@@ -224,8 +224,13 @@ def test_sharded_generations_keep_the_books_of_one_process(lib):
     bv = (C.c_double * n)()
     k1 = [(i * 2654435761) % top for i in range(n)]       # tests/c/stub_engine.c: 64-bit products
     k2 = [(i * 40503 + 7) % top for i in range(n)]
-    for gen in range(6):
+    for gen in range(7):
         named = gen in (2, 3)
+        if gen == 5:            # more than 63 groups in use: the new group's number no longer fits the one-pass bit mask
+            for _ in range(70):
+                q = L.gsb_load_genotypes(d, 1, chars, None)
+                assert q == m.new_group()
+                m.append(1, q)
         if gen == 4:            # break the run: the generation's members are no longer contiguous in storage order
             extra = L.gsb_load_genotypes(d, 2, chars, None)
             m.append(2, extra)
