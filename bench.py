@@ -494,10 +494,11 @@ def engine_arm(a):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_sec = float(te.item())
     e2e = {"value": n_total / e2e_sec, "unit": UNIT, "ms_per_step": e2e_sec * 1e3,
-           "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": 16 * n + 4 * top,
+           "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 16 * n + 4 * top,
            "api": "gsb_shard_select_and_cross (pedigrees tracked, ids allocated) + gsb_shard_get_local_bvs + gsb_delete_group "
-                  "(include/gsb200_gsc.h), native draws: the generation's row list, ids and the offspring's row list go up; the picked "
-                  "pairs and the selected parents' ids (for pedigrees) and the GEBVs come down"}
+                  "(include/gsb200_gsc.h), native draws: the generation's ids go up (its rows and the offspring's are ascending runs of "
+                  "the store in this loop, so only their first row numbers go with the calls; row lists of 4 bytes per genotype "
+                  "would go up otherwise); the picked pairs, the selected parents' ids (for pedigrees) and the GEBVs come down"}
 
     # ---- the same work through the calls a user of the reference makes on ONE GPU (round 1's e2e): gsc_make_random_crosses from
     #      the founders + gsc_get_group_bvs of the offspring + gsc_delete_group, host buffers, pedigrees tracked
