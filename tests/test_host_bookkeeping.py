@@ -100,13 +100,18 @@ def snapshot(L, d):
     return [[ids[i], names[i].decode() if names[i] else None, groups[i]] for i in range(n)]
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3])
-def test_random_operation_sequences_match_the_model(lib, seed):
+@pytest.mark.parametrize("seed,native", [(1, False), (2, False), (3, False), (4, True), (5, True)])
+def test_random_operation_sequences_match_the_model(lib, seed, native):
+    """native: GSB_DRAWS_NATIVE, where random crosses take the batched device path (scaffold_device_pairs: the picks come back
+    from the engine — here from the stub — and the pedigrees are filled from them)"""
     L = lib
     rng = random.Random(seed)
     d = L.gsb_create_simdata(0, M)
     assert d
     L.gsb_set_print(d, None)
+    if native:
+        L.gsb_set_draw_mode.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        L.gsb_set_draw_mode(d, 1, 99)
     lam = (C.c_double * 1)(1.0)
     off = (C.c_uint * 2)(0, M)
     dists = (C.c_double * M)(*[i / M for i in range(M)])
@@ -142,7 +147,7 @@ def test_random_operation_sequences_match_the_model(lib, seed):
             size = sum(1 for r in m.g if r[2] == src)
             n = rng.choice([1, 5, 1200, 2300])
             o = opts(will_name_offspring=(op == "cross_named"), offspring_name_prefix=b"X" if op == "cross_named" else None,
-                     will_save_to_simdata=(op != "cross_drop"))
+                     will_save_to_simdata=(op != "cross_drop"), will_track_pedigree=native)
             g = L.gsb_make_random_crosses(d, src, n, 0, 0, o)
             if size < 2:
                 assert g == 0        # the reference refuses to cross a group with itself when it has one member
